@@ -1,0 +1,136 @@
+/* b200q — C ABI of the B200-native statevector engine behind the `b200.qubit` PennyLane device.
+ *
+ * The reference (PennyLane, /root/reference) is pure Python and has NO FFI of its own: the
+ * functions below are what its numerical engine `pennylane/devices/qubit/*.py` would bind if its
+ * numpy calls were replaced by a native library.  Each entry point cites the reference routine
+ * it stands in for.  `pennylane_b200/_lib.py` is the ctypes binding; INTEGRATION.md shows the
+ * stub a PennyLane maintainer would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; b200q_last_error() describes
+ *     the last failure on the calling thread;
+ *   - `state` is a DEVICE pointer to batch * 2^n complex amplitudes (dtype 0 = complex64,
+ *     1 = complex128), batch-major; the caller (torch) owns all device memory;
+ *   - qubits are addressed by BIT POSITION q of the flat index (q = 0 has stride 1).
+ *     default.qubit's wire w of an n-wire state is bit n-1-w (initialize_state.py:43-44);
+ *   - matrices are row-major complex128 on the HOST (`*_host`) or dtype-typed on the DEVICE
+ *     (`*_dev`); matrix-index bit (k-1-j) belongs to tgt_bits[j] (PennyLane: first wire = MSB);
+ *   - `stream` is a cudaStream_t passed as void*; nothing synchronises unless documented;
+ *   - `work` is a caller-provided device scratch buffer of >= b200q_workspace_bytes() bytes;
+ *   - reductions are deterministic (fixed summation order).
+ */
+#ifndef B200Q_H
+#define B200Q_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200Q_ABI_VERSION 1
+#define B200Q_DTYPE_C64 0
+#define B200Q_DTYPE_C128 1
+#define B200Q_CDF_EXACT 0 /* numpy-ordered float64 additions: bit-exact shots      */
+#define B200Q_CDF_FAST 1  /* blocked parallel scan: fastest, ~1e-16 CDF differences */
+
+const char* b200q_last_error(void);
+int b200q_version(void);
+int b200q_sm_count(void);
+size_t b200q_workspace_bytes(void);
+
+/* |index> for every batch element.  initialize_state.py:41-45 (create_initial_state). */
+int b200q_set_basis_state(void* state, int n, int dtype, int64_t batch, uint64_t index,
+                          void* stream);
+
+/* Dense 2^k x 2^k matrix on tgt_bits with controls.  apply_operation.py:151-255
+ * (apply_operation_einsum / _tensordot), :645-723 (_apply_rotation_1q), :613-642 (Hadamard),
+ * :521-524 (PauliX), :763-832 (CNOT, MultiControlledX: pass X with controls).
+ * k <= 3: mat_host (by value) or mat_dev; 4 <= k <= 10: mat_dev only.
+ * mat_bstride (complex elements) != 0 selects a different matrix per batch element
+ * (parameter broadcasting, apply_operation.py:191-197); mat_dev only. */
+int b200q_apply_matrix(void* state, int n, int dtype, int64_t batch, const int* tgt_bits, int k,
+                       const int* ctrl_bits, const int* ctrl_vals, int nc, const void* mat_host,
+                       const void* mat_dev, int64_t mat_bstride, void* stream);
+
+/* General diagonal gate, 2^k entries.  apply_operation.py:528-609 and every op whose matrix is
+ * diagonal.  k <= 6: diag_host or diag_dev; k <= 20: diag_dev. */
+int b200q_apply_diag(void* state, int n, int dtype, int64_t batch, const int* bits, int k,
+                     const void* diag_host, const void* diag_dev, int64_t diag_bstride,
+                     void* stream);
+
+/* Multiply the subspace selected by (ctrl_bits == ctrl_vals) by one complex scalar; nc = 0 is
+ * GlobalPhase / rescale.  apply_operation.py:507-517, :528-609 (Z, PhaseShift, T, S), CZ, CCZ,
+ * ControlledPhaseShift.  phase_dev (nullable): per-batch scalars of the state's dtype. */
+int b200q_apply_phase(void* state, int n, int dtype, int64_t batch, const int* ctrl_bits,
+                      const int* ctrl_vals, int nc, double phase_re, double phase_im,
+                      const void* phase_dev, void* stream);
+
+/* amp *= popcount(i & mask) odd ? p1 : p0.  RZ / IsingZZ / MultiRZ / PauliRot("Z..Z") of any
+ * width (ops/qubit/parametric_ops_multi_qubit.py:93).  phases_dev (nullable): per-batch
+ * (p0, p1) pairs of the state's dtype. */
+int b200q_apply_parity_phase(void* state, int n, int dtype, int64_t batch, uint64_t mask,
+                             double p0_re, double p0_im, double p1_re, double p1_im,
+                             const void* phases_dev, void* stream);
+
+/* exp(-i theta/2 P), P a Pauli word with >= 1 X/Y factor: xmask = X|Y bits, zmask = Z|Y bits,
+ * ny = number of Y.  c = cos(theta/2), s = sin(theta/2).  parametric_ops_multi_qubit.py:380-436.
+ * cs_dev (nullable): per-batch (c, s) packed as one complex of the state's dtype. */
+int b200q_apply_pauli_rot(void* state, int n, int dtype, int64_t batch, uint64_t xmask,
+                          uint64_t zmask, int ny, double c, double s, const void* cs_dev,
+                          void* stream);
+
+/* Marginal probabilities over bits[0..m) (bin MSB = bits[0]) -> out_dev[batch][2^m] float64.
+ * measurements/probs.py:101-135 (ProbabilityMP.process_state). */
+int b200q_probs(const void* state, int n, int dtype, int64_t batch, const int* bits, int m,
+                double* out_dev, void* work, size_t work_bytes, void* stream);
+
+/* <psi| sum_t coeff_t P_t |psi> -> out_dev[batch].  Terms are HOST arrays.
+ * measure.py:74-99 (csr_dot_products, Pauli branch) + pauli_arithmetic.py:924-950. */
+int b200q_expval_pauli_sum(const void* state, int n, int dtype, int64_t batch,
+                           const uint64_t* xmasks, const uint64_t* zmasks, const int* nys,
+                           const double* coeffs, int nterms, double* out_dev, void* work,
+                           size_t work_bytes, void* stream);
+
+/* <a|b> per batch element -> out_dev[0..batch) real parts, out_dev[batch..2*batch) imaginary.
+ * measure.py:121-139 (full_dot_products), adjoint_jacobian.py:36-40. */
+int b200q_inner(const void* a, const void* b, int n, int dtype, int64_t batch, double* out_dev,
+                void* work, size_t work_bytes, void* stream);
+
+/* out = scale * sum_t (cre_t + i cim_t) P_t |in>  (out != in).  adjoint_jacobian.py:113-115
+ * (bras = 2 * obs|ket>), :315-317 (pauli_rep.dot). */
+int b200q_pauli_sum_apply(const void* in, void* out, int n, int dtype, int64_t batch,
+                          const uint64_t* xmasks, const uint64_t* zmasks, const int* nys,
+                          const double* cre, const double* cim, int nterms, double scale,
+                          void* work, size_t work_bytes, void* stream);
+
+/* <bra|P|ket> for one Pauli word -> out_dev[0] = Re, out_dev[1] = Im. */
+int b200q_pauli_braket(const void* bra, const void* ket, int n, int dtype, uint64_t xmask,
+                       uint64_t zmask, int ny, double* out_dev, void* work, size_t work_bytes,
+                       void* stream);
+
+/* Shot sampler.  probs_dev: 2^m float64 probabilities, OVERWRITTEN with the normalised CDF.
+ * uniforms_dev: `shots` float64 in [0,1) drawn by the host Generator.  Writes basis-state
+ * indices to idx_out_dev (nullable, int64[shots]) and bit rows to bits_out_dev (nullable,
+ * int64[shots][m], column 0 = most significant bit).  norm_out_dev[0] receives the numpy-order
+ * sum of the probabilities (host checks |norm-1| <= 1e-6, sampling.py:514-519);
+ * flags_dev[0] is set to 1 if any probability is NaN (sampling.py:322-325).
+ * sampling.py:500-531 (_sample_probs_numpy) == Generator.choice(arange(2^m), shots, p). */
+int b200q_sample(double* probs_dev, int m, const double* uniforms_dev, int64_t shots, int mode,
+                 int64_t* idx_out_dev, int64_t* bits_out_dev, double* norm_out_dev,
+                 int* flags_dev, void* work, size_t work_bytes, void* stream);
+
+/* One reverse-sweep step of adjoint differentiation on vecs = [1 + n_bras][2^n] (row 0 = ket):
+ *   z_b = <bra_b| G |ket>,  ket <- A ket,  bra_b <- A bra_b      (A = U^dagger, k <= 3)
+ * out_dev[b] = -Im z_b  (= Re <bra_b| i G |ket>, the Jacobian entry when bras carry the factor
+ * 2 of adjoint_jacobian.py:115).  gen_host == NULL: non-trainable op, only applies A.
+ * adjoint_jacobian.py:121-137. */
+int b200q_adjoint_step(void* vecs, int n, int dtype, int n_bras, const int* tgt_bits, int k,
+                       const int* ctrl_bits, const int* ctrl_vals, int nc, const void* adj_host,
+                       const void* gen_host, double* out_dev, void* work, size_t work_bytes,
+                       void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200Q_H */

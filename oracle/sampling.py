@@ -1,0 +1,226 @@
+"""ORACLE (test infrastructure only — never imported by ``pennylane_b200``).
+
+CPU restatement of pennylane/devices/qubit/sampling.py: ``sample_state`` (:439-476),
+``_sample_probs_numpy`` (:500-531) — which IS ``numpy.random.Generator.choice`` — the grouping of
+measurements (:46-98) and ``measure_with_samples`` (:205-335, :377-436).
+"""
+import numpy as np
+
+from .apply_operation import apply_operation
+from .measure import diagonalizing_gates, eigvals, flatten_state, probs_process_state
+
+_PROB_NORMALISATION_TOLERANCE = 1e-6    # sampling.py:33
+
+
+def _sample_probs_numpy(probs, shots, num_wires, is_state_batched, rng):   # sampling.py:500-531
+    rng = np.random.default_rng(rng)
+    norm = np.sum(probs, axis=-1)
+    norm_err = np.abs(norm - 1.0)
+    norm_err = norm_err if is_state_batched else norm_err[..., np.newaxis]
+    if np.any(norm_err > _PROB_NORMALISATION_TOLERANCE):
+        raise ValueError("probabilities do not sum to 1")
+    basis_states = np.arange(2**num_wires)
+    if is_state_batched:
+        probs = probs / norm[:, np.newaxis] if norm.shape else probs / norm
+        samples = np.stack([rng.choice(basis_states, shots, p=p) for p in probs])
+    else:
+        probs = probs / norm
+        samples = rng.choice(basis_states, shots, p=probs)
+    powers_of_two = 1 << np.arange(num_wires, dtype=np.int64)[::-1]
+    states_sampled_base_ten = samples[..., None] & powers_of_two
+    return (states_sampled_base_ten > 0).astype(np.int64)
+
+
+def choice_restated(probs, shots, rng):
+    """What ``Generator.choice(arange(N), shots, p=probs)`` computes (numpy/random/_generator.pyx,
+    ``choice`` with replacement and ``p``): used to pin the CUDA sampler's algorithm."""
+    cdf = probs.cumsum()
+    cdf /= cdf[-1]
+    u = rng.random(shots)
+    return cdf.searchsorted(u, side="right")
+
+
+def sample_state(state, shots, is_state_batched=False, wires=None, rng=None):   # :439-476
+    total_indices = state.ndim - is_state_batched
+    wires_to_sample = list(wires) if wires else list(range(total_indices))
+    flat_state = flatten_state(state, total_indices)
+    probs = probs_process_state(flat_state, wires_to_sample
+                                if wires_to_sample != list(range(total_indices)) else [],
+                                total_indices)
+    return _sample_probs_numpy(probs, shots, len(wires_to_sample), is_state_batched, rng)
+
+
+def process_samples(mp, samples, wire_order):
+    """measurements/{sample,expval,var,probs,counts}.py ``process_samples`` for one shot bin.
+    ``samples``: (shots, n_wires) ints (or with a leading batch axis)."""
+    wire_order = list(wire_order)
+    wires = list(mp.wires) if len(mp.wires) else wire_order
+    cols = [wire_order.index(w) for w in wires]
+    sub = samples[..., cols]
+    if mp.obs is None:
+        if mp.kind == "sample":
+            return sub
+        powers = 2 ** np.arange(len(wires))[::-1]
+        idx = sub @ powers
+        if mp.kind == "probs":
+            dim = 2 ** len(wires)
+            if idx.ndim == 1:
+                return np.bincount(idx, minlength=dim) / idx.shape[0]
+            return np.stack([np.bincount(i, minlength=dim) / i.shape[0] for i in idx])
+        if mp.kind == "counts":
+            out = {}
+            for i in idx:
+                key = format(int(i), f"0{len(wires)}b")
+                out[key] = out.get(key, 0) + 1
+            return out
+        raise NotImplementedError(mp.kind)
+    ev = np.asarray(eigvals(mp.obs))
+    powers = 2 ** np.arange(len(wires))[::-1]
+    idx = sub @ powers
+    vals = ev[idx]
+    if mp.kind == "sample":
+        return vals
+    if mp.kind == "expval":
+        return np.squeeze(np.mean(vals, axis=-1))
+    if mp.kind == "var":
+        return np.squeeze(np.var(vals, axis=-1))
+    if mp.kind == "counts":
+        out = {}
+        for v in vals:
+            out[float(v)] = out.get(float(v), 0) + 1
+        return out
+    raise NotImplementedError(mp.kind)
+
+
+def _pauli_word_of(obs):
+    ps = getattr(obs, "pauli_rep", None)
+    if ps is None or len(ps) != 1:
+        return None
+    (w, c), = ps.items()
+    return w
+
+
+def _qwc(w1, w2):
+    return all(w1[k] == w2[k] for k in w1 if k in w2)
+
+
+def _group_measurements(mps):                  # sampling.py:46-98
+    if len(mps) == 1:
+        return [mps], [[0]]
+    pauli, other, other_idx, no_obs, no_obs_idx = [], [], [], [], []
+    for i, mp in enumerate(mps):
+        if mp.obs is None:
+            no_obs.append(mp); no_obs_idx.append(i)
+        elif _pauli_word_of(mp.obs) is not None and mp.obs.name not in ("LinearCombination", "Sum", "Hamiltonian"):
+            pauli.append((i, mp))
+        else:
+            other.append([mp]); other_idx.append([i])
+    groups, gidx = [], []
+    # qubit-wise-commuting partition, greedy in order (compute_partition_indices, 'qwc')
+    for i, mp in pauli:
+        w = _pauli_word_of(mp.obs)
+        for g, gi in zip(groups, gidx):
+            if all(_qwc(w, _pauli_word_of(m.obs)) for m in g):
+                g.append(mp); gi.append(i)
+                break
+        else:
+            groups.append([mp]); gidx.append([i])
+    if no_obs:
+        groups.append(no_obs); gidx.append(no_obs_idx)
+    return groups + other, gidx + other_idx
+
+
+def _apply_diagonalizing_gates(mps, state, is_state_batched=False):   # sampling.py:188-202
+    from types import SimpleNamespace
+
+    if len(mps) == 1:
+        gates = diagonalizing_gates(mps[0].obs) if mps[0].obs is not None else []
+    elif all(mp.obs is not None for mp in mps):
+        # pauli/utils.py:1059-1081 (diagonalize_qwc_pauli_words): one rotation per wire
+        full = {}
+        for mp in mps:
+            for wire, ch in _pauli_word_of(mp.obs).items():
+                full.setdefault(wire, ch)
+        gates = []
+        for w, ch in full.items():
+            if ch == "X":
+                gates.append(SimpleNamespace(name="RY", wires=(w,), data=(-np.pi / 2,),
+                                             hyperparameters={}))
+            elif ch == "Y":
+                gates.append(SimpleNamespace(name="RX", wires=(w,), data=(np.pi / 2,),
+                                             hyperparameters={}))
+    else:
+        gates = []
+    for op in gates:
+        state = apply_operation(op, state, is_state_batched=is_state_batched)
+    return state
+
+
+def shot_bins(shot_vector):
+    lower = 0
+    for s, copies in shot_vector:
+        for _ in range(copies):
+            yield lower, lower + s
+            lower += s
+
+
+def measure_with_samples(mps, state, shots, is_state_batched=False, rng=None):   # :205-273
+    """``shots``: object with ``total_shots``, ``shot_vector`` [(shots, copies)...],
+    ``has_partitioned_shots``."""
+    groups, indices = _group_measurements(list(mps))
+    all_res = []
+    for group in groups:
+        mp0 = group[0]
+        if mp0.kind == "expval" and mp0.obs is not None and mp0.obs.name in (
+                "LinearCombination", "Hamiltonian", "Sum"):
+            all_res.extend(_measure_sum_with_samples(group, state, shots, is_state_batched, rng))
+        else:
+            all_res.extend(_measure_with_samples_diagonalizing_gates(
+                group, state, shots, is_state_batched, rng))
+    flat_indices = [i for idx in indices for i in idx]
+    sorted_res = tuple(res for _, res in sorted(enumerate(all_res), key=lambda r: flat_indices[r[0]]))
+    if shots.has_partitioned_shots:
+        sorted_res = tuple(zip(*sorted_res))
+    return sorted_res
+
+
+def _measure_with_samples_diagonalizing_gates(mps, state, shots, is_state_batched, rng):  # :276-335
+    state = _apply_diagonalizing_gates(mps, state, is_state_batched)
+    total_indices = state.ndim - is_state_batched
+    wires = list(range(total_indices))
+    try:
+        samples = sample_state(state, shots.total_shots, is_state_batched, wires=wires, rng=rng)
+    except ValueError as e:
+        if "probabilities contain nan" not in str(e).lower():
+            raise
+        samples = np.zeros((shots.total_shots, len(wires)), dtype=np.int64)
+    processed = []
+    for lower, upper in shot_bins(shots.shot_vector):
+        processed.append(tuple(process_samples(mp, samples[..., lower:upper, :], wires) for mp in mps))
+    if shots.has_partitioned_shots:
+        return tuple(zip(*processed))
+    return processed[0]
+
+
+class _OneShots:
+    has_partitioned_shots = False
+
+    def __init__(self, s):
+        self.total_shots = s
+        self.shot_vector = [(s, 1)]
+
+
+def _measure_sum_with_samples(mps, state, shots, is_state_batched, rng):   # :377-436
+    from types import SimpleNamespace
+
+    mp = mps[0]
+    cs, os_ = mp.obs.terms()
+
+    def one(s):
+        res = measure_with_samples(
+            [SimpleNamespace(kind="expval", obs=o, wires=o.wires) for o in os_], state,
+            _OneShots(s), is_state_batched, rng)
+        return sum(c * r for c, r in zip(cs, res))
+
+    unsq = tuple(one(s) for s, copies in shots.shot_vector for _ in range(copies))
+    return [unsq] if shots.has_partitioned_shots else [unsq[0]]

@@ -1,0 +1,63 @@
+"""ORACLE (test infrastructure only — never imported by ``pennylane_b200``).
+
+CPU restatement of pennylane/devices/qubit/simulate.py (``get_final_state`` :174-242,
+``measure_final_state`` :246-304, ``simulate`` :308-393) and initialize_state.py:24-59.
+"""
+import numpy as np
+
+from .apply_operation import apply_operation
+from .measure import measure
+from .sampling import measure_with_samples
+
+
+def create_initial_state(num_wires, prep_operation=None):   # initialize_state.py:24-59
+    if prep_operation is None:
+        state = np.zeros((2,) * num_wires, dtype=complex)
+        state[(0,) * num_wires] = 1
+        return state
+    sv = prep_operation.state_vector(wire_order=list(range(num_wires)))
+    dtype = "complex64" if str(sv.dtype) in ("float32", "complex64") else "complex128"
+    return np.asarray(sv).astype(dtype)
+
+
+def _is_prep(op):
+    return hasattr(op, "state_vector")
+
+
+def _op_batch(op):
+    bs = getattr(op, "batch_size", None)
+    return bs
+
+
+def get_final_state(circuit):                               # simulate.py:174-242
+    ops = list(circuit.operations)
+    prep = ops[0] if ops and _is_prep(ops[0]) else None
+    op_wires = sorted({w for op in ops for w in op.wires})
+    state = create_initial_state(len(op_wires), prep)
+    is_state_batched = bool(prep is not None and _op_batch(prep) is not None)
+    for op in ops[bool(prep):]:
+        state = apply_operation(op, state, is_state_batched=is_state_batched)
+        is_state_batched = is_state_batched or (_op_batch(op) is not None)
+    for _ in range(circuit.num_wires - len(op_wires)):
+        state = np.stack([state, np.zeros_like(state)], axis=-1)
+    return state, is_state_batched
+
+
+def measure_final_state(circuit, state, is_state_batched, rng=None):   # simulate.py:246-304
+    if not circuit.shots:
+        if len(circuit.measurements) == 1:
+            return measure(circuit.measurements[0], state, is_state_batched)
+        return tuple(measure(mp, state, is_state_batched) for mp in circuit.measurements)
+    rng = np.random.default_rng(rng)
+    results = measure_with_samples(circuit.measurements, state, circuit.shots,
+                                   is_state_batched=is_state_batched, rng=rng)
+    if len(circuit.measurements) == 1:
+        if circuit.shots.has_partitioned_shots:
+            return tuple(res[0] for res in results)
+        return results[0]
+    return results
+
+
+def simulate(circuit, rng=None):                            # simulate.py:308-393
+    state, is_state_batched = get_final_state(circuit)
+    return measure_final_state(circuit, state, is_state_batched, rng=rng)

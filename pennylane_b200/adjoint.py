@@ -1,0 +1,246 @@
+"""Adjoint differentiation on the CUDA engine — mirror of
+pennylane/devices/qubit/adjoint_jacobian.py (``adjoint_jacobian`` :77-149, ``adjoint_jvp``
+:153-223, ``adjoint_vjp`` :327-419).
+
+The ket and all bras live in ONE device buffer ``vecs[1 + n_bras][2^n]`` so that a
+non-trainable op is a single batched launch, and a trainable op is the fused
+``b200q_adjoint_step`` (U^dagger on ket and bra + generator inner product in the same pass).
+The Jacobian entries accumulate in a device array and come back in one copy at the end.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import ops as _ops
+from ._lib import check, int_array
+from .pauli import sentence_terms
+from .simulate import _pauli_rep, get_final_state
+from .statevector import StateVector, _torch
+from ._lib import f64_array, u64_array
+
+
+def _op_adjoint(op):
+    adj = getattr(op, "adjoint", None)
+    if callable(adj):
+        try:
+            return adj()
+        except Exception:  # pragma: no cover - foreign operator without adjoint rule
+            pass
+    return _ops.QubitUnitary(np.conj(np.asarray(op.matrix())).T, wires=op.wires)
+
+
+def _generator_matrix(op) -> np.ndarray:
+    """``qml.matrix(qml.generator(op, format="observable"), wire_order=op.wires)``
+    (pennylane/operation.py:59)."""
+    gen = op.generator()
+    if isinstance(gen, tuple):  # legacy (observable, prefactor) format
+        gen = _ops.SProd(gen[1], gen[0])
+    return np.asarray(gen.matrix(wire_order=list(op.wires)), dtype=np.complex128)
+
+
+class _Sweep:
+    """Reverse sweep state: ``vecs`` buffer, a batched view for plain gate application and the
+    device-side accumulator for inner products."""
+
+    def __init__(self, tape, dtype, device, n_bras):
+        torch = _torch()
+        self.tape = tape
+        self.n = tape.num_wires
+        self.n_bras = n_bras
+        np_dtype = np.dtype(dtype)
+        t_dtype = torch.complex128 if np_dtype == np.complex128 else torch.complex64
+        dev = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.vecs = torch.empty((1 + n_bras, 1 << self.n), dtype=t_dtype, device=dev)
+        self.ket = StateVector(self.n, np_dtype, 1, dev, buffer=self.vecs[0:1])
+        self.all = StateVector(self.n, np_dtype, 1 + n_bras, dev, buffer=self.vecs)
+        self.bras_view = (StateVector(self.n, np_dtype, n_bras, dev, buffer=self.vecs[1:])
+                          if n_bras else None)
+        self.lib = self.ket.lib
+
+    def bra(self, k) -> StateVector:
+        return StateVector(self.n, self.ket.np_dtype, 1, self.ket.device,
+                           buffer=self.vecs[1 + k: 2 + k])
+
+    def fill_bra_from_observable(self, k, obs, scale):
+        """bra_k = scale * O |ket>   (adjoint_jacobian.py:113-115)."""
+        ket, bra = self.ket, self.bra(k)
+        ps = _pauli_rep(obs)
+        if ps is not None and len(ps) <= 1024:
+            wire_to_bit = {w: ket.bit(w) for pw in ps for w in pw}
+            xs, zs, ys, cs = sentence_terms(ps, wire_to_bit)
+            cre = [float(np.real(c)) for c in cs]
+            cim = [float(np.imag(c)) for c in cs]
+            w, wb = ket.workspace()
+            check(self.lib.b200q_pauli_sum_apply(
+                ket.ptr, bra.ptr, self.n, ket.dtype_code, 1, u64_array(xs), u64_array(zs),
+                int_array(ys) if ys else int_array([0]), f64_array(cre), f64_array(cim), len(cs),
+                float(scale), w, wb, ket.stream))
+            return
+        bra.data.copy_(ket.data)
+        wires = list(obs.wires)
+        if wires:
+            bra.apply_matrix(np.asarray(obs.matrix()), wires)
+            bra.apply_phase(scale)
+        else:
+            bra.apply_phase(scale * complex(np.asarray(obs.matrix()).ravel()[0]))
+
+    def step(self, op, trainable: bool, acc, offset: int):
+        """One iteration of adjoint_jacobian.py:121-137.  When ``trainable``, writes
+        ``-Im <bra_b|G|ket>`` for every bra to ``acc[offset : offset + n_bras]`` (device)."""
+        adj = _op_adjoint(op)
+        if not trainable:
+            self.all.apply_operation(adj)
+            return
+        wires = list(op.wires)
+        k = len(wires)
+        ket = self.ket
+        if k <= 3 and getattr(op, "batch_size", None) is None:
+            amat = np.ascontiguousarray(np.conj(np.asarray(op.matrix())).T, dtype=np.complex128)
+            gmat = np.ascontiguousarray(_generator_matrix(op), dtype=np.complex128)
+            w, wb = ket.workspace()
+            check(self.lib.b200q_adjoint_step(
+                C.c_void_p(self.vecs.data_ptr()), self.n, ket.dtype_code, self.n_bras,
+                int_array(ket.bits(wires)), k, None, None, 0,
+                amat.ctypes.data_as(C.c_void_p), gmat.ctypes.data_as(C.c_void_p),
+                C.c_void_p(acc.data_ptr() + 8 * offset), w, wb, ket.stream))
+            return
+        # wide trainable gate: generator inner products first, then U^dagger on all rows
+        self._wide_generator_products(op, acc, offset)
+        self.all.apply_operation(adj)
+
+    def _wide_generator_products(self, op, acc, offset):
+        torch = _torch()
+        ket = self.ket
+        gen = op.generator()
+        ps = _pauli_rep(gen)
+        vals = np.zeros(self.n_bras)
+        w, wb = ket.workspace()
+        scal = ket._scal
+        if ps is not None:
+            wire_to_bit = {wr: ket.bit(wr) for pw in ps for wr in pw}
+            xs, zs, ys, cs = sentence_terms(ps, wire_to_bit)
+            for b in range(self.n_bras):
+                z = 0j
+                for xm, zm, ny, c in zip(xs, zs, ys, cs):
+                    check(self.lib.b200q_pauli_braket(self.bra(b).ptr, ket.ptr, self.n,
+                                                      ket.dtype_code, xm, zm, ny,
+                                                      C.c_void_p(scal.data_ptr()), w, wb, ket.stream))
+                    r = scal[:2].cpu().numpy()
+                    z += c * (r[0] + 1j * r[1])
+                vals[b] = -np.imag(z)
+        else:
+            tmp = ket.clone()
+            tmp.apply_matrix(_generator_matrix(op), list(op.wires))
+            for b in range(self.n_bras):
+                vals[b] = -np.imag(self.bra(b).inner(tmp))
+        acc[offset: offset + self.n_bras].copy_(torch.from_numpy(vals))
+
+
+def _param_bookkeeping(tape):
+    n_op_params = sum(len(op.data) for op in tape.operations)
+    trainable = list(tape.trainable_params)
+    return n_op_params, trainable
+
+
+def _reverse_sweep(tape, sweep: _Sweep, n_rows_out: int):
+    """Shared loop of adjoint_jacobian / adjoint_jvp / adjoint_vjp.  Returns an array
+    ``vals[n_trainable_op_params][n_bras]`` of ``-Im <bra|G|ket>`` and the list of trainable
+    indices (positions in ``tape.trainable_params``) it filled."""
+    torch = _torch()
+    n_op_params, trainable = _param_bookkeeping(tape)
+    n_bras = sweep.n_bras
+    acc = torch.zeros(max(1, len(trainable)) * n_bras, dtype=torch.float64, device=sweep.ket.device)
+    param_number = n_op_params - 1
+    t_number = len(trainable) - 1
+    while t_number >= 0 and trainable[t_number] > param_number:
+        t_number -= 1                                    # trainable observable parameters
+    filled = []
+    for op in reversed(tape.operations[tape.num_preps:]):
+        if op.name == "Snapshot":
+            continue
+        npar = len(op.data)
+        is_trainable = npar == 1 and param_number in trainable
+        if npar > 1 and any((param_number - j) in trainable for j in range(npar)):
+            raise ValueError(
+                f"adjoint differentiation: operation {op.name} has {npar} parameters; it must "
+                "be decomposed into one-parameter gates first (default_qubit.py:286-292)")
+        sweep.step(op, is_trainable, acc, n_bras * max(t_number, 0))
+        if is_trainable:
+            filled.append(t_number)
+            t_number -= 1
+        param_number -= npar
+    vals = acc.cpu().numpy().reshape(max(1, len(trainable)), n_bras)
+    return vals, filled, trainable
+
+
+def adjoint_jacobian(tape, dtype=np.complex128, device=None, return_state: bool = False):
+    """adjoint_jacobian.py:77-149.  Runs the forward pass itself (directly into row 0 of the
+    sweep buffer).  Returns the Jacobian in the reference's nested-tuple layout; with
+    ``return_state`` also a ``StateVector`` copy of the final state taken before the sweep."""
+    tape = tape.map_to_standard_wires()
+    obs = [m.obs for m in tape.measurements]
+    if any(o is None for o in obs) or any(m.kind != "expval" for m in tape.measurements):
+        raise ValueError("adjoint differentiation supports expectation values only")
+    if tape.batch_size is not None:
+        raise ValueError("adjoint differentiation does not support broadcasting "
+                         "(default_qubit.py:348 expands broadcast tapes first)")
+    n_obs = len(obs)
+    sweep = _Sweep(tape, dtype, device, n_obs)
+    get_final_state(tape, dtype=dtype, device=device, buffer=sweep.vecs[0:1])
+    final = sweep.ket.clone() if return_state else None
+    for k, o in enumerate(obs):
+        sweep.fill_bra_from_observable(k, o, 2.0)
+    vals, filled, trainable = _reverse_sweep(tape, sweep, n_obs)
+    jac = np.zeros((n_obs, len(trainable)))
+    for t in filled:
+        jac[:, t] = vals[t]
+    jac = np.squeeze(jac)
+    if jac.ndim == 0:
+        res = np.array(jac)
+    elif jac.ndim == 1:
+        res = tuple(np.array(j) for j in jac)
+    else:
+        res = tuple(tuple(np.array(j_) for j_ in j) for j in jac)
+    return (res, final) if return_state else res
+
+
+def adjoint_jvp(tape, tangents, dtype=np.complex128, device=None):
+    """adjoint_jacobian.py:153-223: ``tangents_out[k] = sum_p J[k, p] * tangents[p]``."""
+    tape = tape.map_to_standard_wires()
+    obs = [m.obs for m in tape.measurements]
+    n_obs = len(obs)
+    sweep = _Sweep(tape, dtype, device, n_obs)
+    get_final_state(tape, dtype=dtype, device=device, buffer=sweep.vecs[0:1])
+    for k, o in enumerate(obs):
+        sweep.fill_bra_from_observable(k, o, 2.0)
+    vals, filled, trainable = _reverse_sweep(tape, sweep, n_obs)
+    tangents = np.atleast_1d(np.asarray(tangents, dtype=float))
+    out = np.zeros(n_obs)
+    for t in filled:
+        out += vals[t] * tangents[t]
+    if n_obs == 1:
+        return np.array(out[0])
+    return tuple(np.array(t) for t in out)
+
+
+def adjoint_vjp(tape, cotangents, dtype=np.complex128, device=None):
+    """adjoint_jacobian.py:327-419 (unbatched cotangents): the cotangents are folded into one
+    effective observable so a single bra is swept regardless of the number of measurements."""
+    tape = tape.map_to_standard_wires()
+    obs = [m.obs for m in tape.measurements]
+    cots = np.atleast_1d(np.asarray(cotangents, dtype=float))
+    n_op_params, trainable = _param_bookkeeping(tape)
+    if np.allclose(cots, 0.0):
+        return tuple(0.0 for _ in trainable)
+    keep = [(c, o) for c, o in zip(cots, obs) if not np.allclose(c, 0.0)]
+    new_obs = _ops.dot([c for c, _ in keep], [o for _, o in keep])
+    sweep = _Sweep(tape, dtype, device, 1)
+    get_final_state(tape, dtype=dtype, device=device, buffer=sweep.vecs[0:1])
+    sweep.fill_bra_from_observable(0, new_obs, 2.0)
+    vals, filled, trainable = _reverse_sweep(tape, sweep, 1)
+    out = np.zeros(len(trainable))
+    for t in filled:
+        out[t] = vals[t][0]
+    return tuple(out)

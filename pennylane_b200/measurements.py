@@ -1,0 +1,160 @@
+"""Measurement processes — mirror of the part of ``pennylane.measurements`` the device consumes.
+
+Reference: pennylane/measurements/{expval,var,probs,sample,counts,state}.py and
+pennylane/core/measurements (``MeasurementProcess``: ``obs``, ``wires``, ``eigvals()``,
+``diagonalizing_gates()``, ``process_samples``).  ``kind`` is the duck-typing tag used by the
+engine and the oracle instead of ``isinstance`` checks.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+class MeasurementProcess:
+    kind = None
+
+    def __init__(self, obs=None, wires=None):
+        if obs is not None and wires is not None:
+            raise ValueError("Cannot set the wires if an observable is provided.")
+        self.obs = obs
+        if obs is not None:
+            self.wires = tuple(obs.wires)
+        elif wires is None:
+            self.wires = ()
+        elif isinstance(wires, (str, bytes)) or not hasattr(wires, "__iter__"):
+            self.wires = (wires,)
+        else:
+            self.wires = tuple(wires)
+
+    def __repr__(self):
+        inner = repr(self.obs) if self.obs is not None else f"wires={list(self.wires)}"
+        return f"{self.kind}({inner})"
+
+    def map_wires(self, wire_map):
+        new = self.__class__.__new__(self.__class__)
+        new.__dict__.update(self.__dict__)
+        if self.obs is not None:
+            new.obs = self.obs.map_wires(wire_map)
+            new.wires = tuple(new.obs.wires)
+        else:
+            new.wires = tuple(wire_map.get(w, w) for w in self.wires)
+        return new
+
+    def diagonalizing_gates(self):
+        return [] if self.obs is None else list(self.obs.diagonalizing_gates())
+
+    def eigvals(self):
+        return None if self.obs is None else np.asarray(self.obs.eigvals())
+
+    # ---- measurements/*.py process_samples -------------------------------------------------
+    def _indices(self, samples, wire_order):
+        wire_order = list(wire_order)
+        wires = list(self.wires) if len(self.wires) else wire_order
+        cols = [wire_order.index(w) for w in wires]
+        sub = samples[..., cols]
+        powers = 2 ** np.arange(len(wires))[::-1]
+        return sub, sub @ powers, wires
+
+    def process_samples(self, samples, wire_order):  # pragma: no cover - abstract
+        raise NotImplementedError
+
+
+class ExpectationMP(MeasurementProcess):
+    """measurements/expval.py (process_samples :60-79, process_state :81-93)."""
+    kind = "expval"
+
+    def process_samples(self, samples, wire_order):
+        _, idx, _ = self._indices(samples, wire_order)
+        vals = np.asarray(self.eigvals())[idx]
+        return np.squeeze(np.mean(vals, axis=-1))
+
+
+class VarianceMP(MeasurementProcess):
+    """measurements/var.py."""
+    kind = "var"
+
+    def process_samples(self, samples, wire_order):
+        _, idx, _ = self._indices(samples, wire_order)
+        vals = np.asarray(self.eigvals())[idx]
+        return np.squeeze(np.var(vals, axis=-1))
+
+
+class ProbabilityMP(MeasurementProcess):
+    """measurements/probs.py (process_samples :70-99, process_state :101-135)."""
+    kind = "probs"
+
+    def process_samples(self, samples, wire_order):
+        _, idx, wires = self._indices(samples, wire_order)
+        dim = 2 ** len(wires)
+        if idx.ndim == 1:
+            return np.bincount(idx, minlength=dim) / idx.shape[0]
+        return np.stack([np.bincount(i, minlength=dim) / i.shape[0] for i in idx])
+
+
+class SampleMP(MeasurementProcess):
+    """measurements/sample.py."""
+    kind = "sample"
+
+    def process_samples(self, samples, wire_order):
+        sub, idx, _ = self._indices(samples, wire_order)
+        if self.obs is None:
+            return sub
+        return np.asarray(self.eigvals())[idx]
+
+
+class CountsMP(MeasurementProcess):
+    """measurements/counts.py."""
+    kind = "counts"
+
+    def __init__(self, obs=None, wires=None, all_outcomes=False):
+        super().__init__(obs, wires)
+        self.all_outcomes = all_outcomes
+
+    def process_samples(self, samples, wire_order):
+        sub, idx, wires = self._indices(samples, wire_order)
+        out = {}
+        if self.obs is None:
+            if self.all_outcomes:
+                for i in range(2 ** len(wires)):
+                    out[format(i, f"0{len(wires)}b")] = 0
+            vals, cnts = np.unique(idx, return_counts=True)
+            for v, c in zip(vals, cnts):
+                out[format(int(v), f"0{len(wires)}b")] = int(c)
+            return out
+        ev = np.asarray(self.eigvals())
+        if self.all_outcomes:
+            for e in np.unique(ev):
+                out[float(e)] = 0
+        vals, cnts = np.unique(ev[idx], return_counts=True)
+        for v, c in zip(vals, cnts):
+            out[float(v)] = int(c)
+        return out
+
+
+class StateMP(MeasurementProcess):
+    """measurements/state.py."""
+    kind = "state"
+
+
+def expval(op):
+    return ExpectationMP(obs=op)
+
+
+def var(op):
+    return VarianceMP(obs=op)
+
+
+def probs(wires=None, op=None):
+    return ProbabilityMP(obs=op, wires=wires)
+
+
+def sample(op=None, wires=None):
+    return SampleMP(obs=op, wires=wires)
+
+
+def counts(op=None, wires=None, all_outcomes=False):
+    return CountsMP(obs=op, wires=wires, all_outcomes=all_outcomes)
+
+
+def state():
+    return StateMP()

@@ -1,0 +1,275 @@
+"""Circuit execution on the CUDA engine — the device-side mirror of
+pennylane/devices/qubit/simulate.py (``get_final_state`` :174-242, ``measure_final_state``
+:246-304, ``simulate`` :308-393), measure.py (``measure`` :224-239 and its strategy choice
+:165-221) and sampling.py (``measure_with_samples`` :205-335, ``_group_measurements`` :46-98,
+``sample_state`` :439-476).
+
+Every amplitude-sized operation is a kernel call on a :class:`StateVector`; the host only
+handles scalars, 2^m-sized marginals (m = observable wires) and the shot bookkeeping.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .pauli import PauliSentence, PauliWord
+from .statevector import StateVector
+
+
+def _is_prep(op) -> bool:
+    return hasattr(op, "state_vector")
+
+
+def get_final_state(circuit, dtype=np.complex128, device=None, buffer=None):
+    """Run the gate loop (simulate.py:214-235).  ``circuit`` must be in standard wire order.
+
+    Returns ``(StateVector, is_state_batched)``.  Measurement-only wires are simply extra
+    low-order qubits left in |0> (the reference pads them afterwards, simulate.py:237-240).
+    """
+    ops_ = list(circuit.operations)
+    n = circuit.num_wires
+    prep = ops_[0] if ops_ and _is_prep(ops_[0]) else None
+    sv = StateVector(n, dtype=dtype, device=device, buffer=buffer)
+    if buffer is not None:
+        sv.reset()
+    if prep is not None:
+        vec = np.asarray(prep.state_vector(wire_order=list(range(n))))
+        # single-precision StatePrep gives a complex64 simulation (initialize_state.py:47-51)
+        sv.set_state(vec)
+    for op in ops_[bool(prep):]:
+        sv.apply_operation(op)
+    return sv, sv.batch > 1
+
+
+# ---------------------------------------------------------------------------------------------
+# analytic measurements
+# ---------------------------------------------------------------------------------------------
+def _rotated(sv: StateVector, gates):
+    """State after the diagonalizing gates; a copy only when there is something to apply."""
+    if not gates:
+        return sv
+    rot = sv.clone()
+    for g in gates:
+        rot.apply_operation(g)
+    return rot
+
+
+def _squeeze(res, batched):
+    res = np.asarray(res)
+    return res if batched else (res[0] if res.ndim and res.shape[0] == 1 else res)
+
+
+def _pauli_rep(obs):
+    try:
+        return obs.pauli_rep
+    except Exception:  # pragma: no cover - foreign operator classes
+        return None
+
+
+def _expval_pauli(sv, ps):
+    return sv.expval_pauli_sentence(ps)
+
+
+def measure(mp, sv: StateVector, is_state_batched: bool = False):
+    """One analytic measurement (measure.py:224-239).
+
+    Strategy (the kernel-side replacement of ``get_measurement_function``, measure.py:165-221):
+    observables with a Pauli representation go through the fused Pauli-sum reduction (no copy of
+    the state, no diagonalizing gates); other observables rotate a copy with their diagonalizing
+    gates and reduce marginal probabilities against the eigenvalues.
+    """
+    kind = mp.kind
+    obs = mp.obs
+    if kind == "state":
+        flat = sv.data.cpu().numpy()
+        return flat if is_state_batched else flat[0]
+    if kind == "probs":
+        rot = _rotated(sv, mp.diagonalizing_gates()) if obs is not None else sv
+        wires = list(mp.wires) if len(mp.wires) else list(range(sv.n))
+        p = rot.probs(wires)
+        return p
+    if kind == "expval":
+        ps = _pauli_rep(obs)
+        if ps is not None:
+            return np.float64(_expval_pauli(sv, ps)) if not is_state_batched else _expval_pauli(sv, ps)
+        if getattr(obs, "has_diagonalizing_gates", False):
+            rot = _rotated(sv, mp.diagonalizing_gates())
+            p = rot.probs(list(mp.wires))
+            return np.dot(p, np.real(np.asarray(mp.eigvals())))
+        if hasattr(obs, "terms"):                       # sum_of_terms_method, measure.py:142-161
+            cs, os_ = obs.terms()
+            from .measurements import ExpectationMP
+            return sum(c * measure(ExpectationMP(o), sv, is_state_batched) for c, o in zip(cs, os_))
+        # full_dot_products (measure.py:121-139): <psi| O |psi> with O applied to a copy
+        tmp = sv.clone()
+        tmp.apply_matrix(np.asarray(obs.matrix()), list(obs.wires))
+        return np.real(sv.inner(tmp))
+    if kind == "var":
+        if getattr(obs, "has_diagonalizing_gates", False):
+            rot = _rotated(sv, mp.diagonalizing_gates())
+            p = rot.probs(list(mp.wires))
+            ev = np.real(np.asarray(mp.eigvals(), dtype=complex)).astype("float64")
+            return np.dot(p, ev**2) - np.dot(p, ev) ** 2      # var.py:107-115
+        ps = _pauli_rep(obs)
+        if ps is not None:                              # <H^2> - <H>^2 without diagonalising
+            ps2 = ps @ ps
+            return _expval_pauli(sv, _real_sentence(ps2)) - _expval_pauli(sv, ps) ** 2
+        raise NotImplementedError(f"variance of {obs} is not supported")
+    raise NotImplementedError(f"analytic measurement {kind} is not supported")
+
+
+def _real_sentence(ps):
+    out = PauliSentence()
+    for w, c in ps.items():
+        if abs(c) > 0:
+            out[w] = np.real(c)
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# finite shots
+# ---------------------------------------------------------------------------------------------
+def _pauli_word_of(obs):
+    if obs is None or obs.name in ("LinearCombination", "Hamiltonian", "Sum"):
+        return None
+    ps = _pauli_rep(obs)
+    if ps is None or len(ps) != 1:
+        return None
+    (w, _c), = ps.items()
+    return w
+
+
+def _qwc(w1, w2) -> bool:
+    return all(w1[k] == w2[k] for k in w1 if k in w2)
+
+
+def _group_measurements(mps):
+    """sampling.py:46-98.  Pauli-word observables are partitioned into qubit-wise commuting
+    groups greedily in tape order (the reference colours the QWC graph with rustworkx's
+    largest-first heuristic, pauli/grouping/group_observables.py:389-432 — same groups whenever
+    the greedy and the colouring agree, which covers single-group tapes; the order of several
+    non-commuting groups, and hence RNG consumption order, may differ)."""
+    if len(mps) == 1:
+        return [list(mps)], [[0]]
+    pauli, other, other_idx, no_obs, no_obs_idx = [], [], [], [], []
+    for i, mp in enumerate(mps):
+        if mp.obs is None:
+            no_obs.append(mp); no_obs_idx.append(i)
+        elif _pauli_word_of(mp.obs) is not None:
+            pauli.append((i, mp))
+        else:
+            other.append([mp]); other_idx.append([i])
+    groups, gidx = [], []
+    for i, mp in pauli:
+        w = _pauli_word_of(mp.obs)
+        for g, gi in zip(groups, gidx):
+            if all(_qwc(w, _pauli_word_of(m.obs)) for m in g):
+                g.append(mp); gi.append(i)
+                break
+        else:
+            groups.append([mp]); gidx.append([i])
+    if no_obs:
+        groups.append(no_obs); gidx.append(no_obs_idx)
+    return groups + other, gidx + other_idx
+
+
+def _group_diagonalizing_gates(mps):
+    """sampling.py:188-202 (and pauli/utils.py:1059-1081 for a QWC group)."""
+    from . import ops as _ops
+
+    if len(mps) == 1:
+        return mps[0].diagonalizing_gates()
+    if all(mp.obs is not None for mp in mps):
+        full = {}
+        for mp in mps:
+            for wire, ch in _pauli_word_of(mp.obs).items():
+                full.setdefault(wire, ch)
+        gates = []
+        for w, ch in full.items():
+            if ch == "X":
+                gates.append(_ops.RY(-np.pi / 2, wires=w))
+            elif ch == "Y":
+                gates.append(_ops.RX(np.pi / 2, wires=w))
+        return gates
+    return []
+
+
+def sample_state(sv: StateVector, shots: int, rng, wires=None, exact: bool = True):
+    """sampling.py:439-476 + :500-531 on the device (uniforms from the host Generator)."""
+    return sv.sample(shots, rng, wires=wires, exact=exact)
+
+
+def _measure_group(mps, sv, shots, rng, exact):
+    """sampling.py:276-335."""
+    rot = _rotated(sv, _group_diagonalizing_gates(mps))
+    wires = list(range(sv.n))
+    samples = sample_state(rot, shots.total_shots, rng, wires=wires, exact=exact)
+    processed = []
+    for lower, upper in shots.bins():
+        processed.append(tuple(mp.process_samples(samples[..., lower:upper, :], wires) for mp in mps))
+    if shots.has_partitioned_shots:
+        return tuple(zip(*processed))
+    return processed[0]
+
+
+def _measure_sum(mps, sv, shots, rng, exact):
+    """sampling.py:377-436: term-by-term sampling of LinearCombination / Sum expectation values."""
+    from .measurements import ExpectationMP
+    from .tape import Shots
+
+    mp = mps[0]
+    cs, os_ = mp.obs.terms()
+
+    def one(s):
+        res = measure_with_samples([ExpectationMP(o) for o in os_], sv, Shots(s), rng, exact)
+        return sum(c * r for c, r in zip(cs, res))
+
+    unsq = tuple(one(s) for s in shots)
+    return [unsq] if shots.has_partitioned_shots else [unsq[0]]
+
+
+def measure_with_samples(mps, sv: StateVector, shots, rng, exact: bool = True):
+    """sampling.py:205-273."""
+    groups, indices = _group_measurements(list(mps))
+    all_res = []
+    for group in groups:
+        mp0 = group[0]
+        if mp0.kind == "expval" and mp0.obs is not None and mp0.obs.name in (
+                "LinearCombination", "Hamiltonian", "Sum"):
+            all_res.extend(_measure_sum(group, sv, shots, rng, exact))
+        else:
+            all_res.extend(_measure_group(group, sv, shots, rng, exact))
+    flat_indices = [i for idx in indices for i in idx]
+    sorted_res = tuple(r for _, r in sorted(enumerate(all_res), key=lambda t: flat_indices[t[0]]))
+    if shots.has_partitioned_shots:
+        sorted_res = tuple(zip(*sorted_res))
+    return sorted_res
+
+
+def measure_final_state(circuit, sv: StateVector, is_state_batched: bool, rng=None,
+                        exact_sampling: bool = True):
+    """simulate.py:246-304."""
+    if not circuit.shots:
+        if len(circuit.measurements) == 1:
+            return measure(circuit.measurements[0], sv, is_state_batched)
+        return tuple(measure(mp, sv, is_state_batched) for mp in circuit.measurements)
+    rng = np.random.default_rng(rng)
+    results = measure_with_samples(circuit.measurements, sv, circuit.shots, rng, exact_sampling)
+    if len(circuit.measurements) == 1:
+        if circuit.shots.has_partitioned_shots:
+            return tuple(res[0] for res in results)
+        return results[0]
+    return results
+
+
+def simulate(circuit, rng=None, dtype=np.complex128, device=None, exact_sampling: bool = True,
+             state_cache=None):
+    """simulate.py:308-393 (without native mid-circuit measurements)."""
+    circuit = circuit.map_to_standard_wires()
+    sv, batched = get_final_state(circuit, dtype=dtype, device=device)
+    if state_cache is not None:
+        state_cache[circuit.hash] = sv
+    return measure_final_state(circuit, sv, batched, rng=rng, exact_sampling=exact_sampling)
+
+
+__all__ = ["get_final_state", "measure", "measure_with_samples", "measure_final_state",
+           "simulate", "sample_state", "PauliWord"]

@@ -1,0 +1,405 @@
+"""Device-resident statevector: the host-side handle on the CUDA engine.
+
+One ``StateVector`` owns a torch CUDA buffer of ``batch * 2**n`` complex amplitudes laid out
+exactly like default.qubit's ``(B, 2, ..., 2)`` array flattened
+(pennylane/devices/qubit/initialize_state.py:43-44), and forwards every numerical operation to
+the C ABI in ``include/b200q.h``.  torch is used for memory, streams and (sharded mode)
+``torch.distributed`` only; no torch arithmetic touches the amplitudes.
+
+There is no CPU path: constructing a ``StateVector`` without a CUDA device, or without the built
+``libb200q.so``, raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import B200QError, check, f64_array, int_array, u64_array
+from .pauli import sentence_terms
+
+_TORCH = None
+
+
+def _torch():
+    global _TORCH
+    if _TORCH is None:
+        import torch
+
+        _TORCH = torch
+    return _TORCH
+
+
+_PHASE_GATES = {  # name -> phase applied to the |1> subspace of the (single) wire
+    "PauliZ": -1.0 + 0j,
+    "S": 1j,
+    "T": np.exp(1j * np.pi / 4),
+}
+_CTRL_X_LIKE = {"CNOT": 1, "Toffoli": 2}
+
+
+def _is_diagonal(mat: np.ndarray) -> bool:
+    d = mat.shape[-1]
+    off = mat[..., ~np.eye(d, dtype=bool)]
+    return not np.any(off)
+
+
+class StateVector:
+    """``batch`` statevectors of ``num_wires`` qubits on one GPU.
+
+    Args:
+        num_wires: number of qubits (wire ``w`` is bit ``num_wires-1-w`` of the flat index).
+        dtype: ``np.complex128`` (default, like default.qubit) or ``np.complex64``.
+        batch: leading broadcast dimension (parameter broadcasting, simulate.py:211,235).
+        device: torch device string.
+    """
+
+    def __init__(self, num_wires: int, dtype=np.complex128, batch: int = 1, device=None,
+                 buffer=None):
+        torch = _torch()
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise B200QError("pennylane_b200 needs a CUDA device (no CPU fallback exists)")
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.n = int(num_wires)
+        self.np_dtype = np.dtype(dtype)
+        if self.np_dtype not in (np.dtype(np.complex64), np.dtype(np.complex128)):
+            raise ValueError("dtype must be complex64 or complex128")
+        self.dtype_code = 1 if self.np_dtype == np.complex128 else 0
+        self.t_dtype = torch.complex128 if self.dtype_code else torch.complex64
+        self.batch = int(batch)
+        if buffer is not None:
+            self.data = buffer
+        else:
+            self.data = torch.empty((self.batch, 1 << self.n), dtype=self.t_dtype, device=self.device)
+            self.reset()
+        self._work = None
+        self._scal = torch.empty(4096, dtype=torch.float64, device=self.device)
+
+    # ---- plumbing -----------------------------------------------------------------------
+    @property
+    def stream(self):
+        return C.c_void_p(_torch().cuda.current_stream(self.device).cuda_stream)
+
+    @property
+    def ptr(self):
+        return C.c_void_p(self.data.data_ptr())
+
+    def workspace(self, min_bytes: int = 0):
+        torch = _torch()
+        need = max(int(self.lib.b200q_workspace_bytes()), int(min_bytes))
+        if self._work is None or self._work.numel() < need:
+            self._work = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return C.c_void_p(self._work.data_ptr()), C.c_size_t(self._work.numel())
+
+    def bit(self, wire: int) -> int:
+        return self.n - 1 - int(wire)
+
+    def bits(self, wires: Sequence[int]):
+        return [self.n - 1 - int(w) for w in wires]
+
+    def _upload(self, arr: np.ndarray):
+        torch = _torch()
+        arr = np.ascontiguousarray(arr, dtype=self.np_dtype)
+        return torch.from_numpy(arr).to(self.device, non_blocking=False)
+
+    # ---- state management ------------------------------------------------------------------
+    def reset(self, index: int = 0):
+        check(self.lib.b200q_set_basis_state(self.ptr, self.n, self.dtype_code, self.batch,
+                                             int(index), self.stream))
+
+    def set_state(self, state: np.ndarray):
+        """Load amplitudes from the host: shape (2**n,), (2,)*n, or with a leading batch axis."""
+        torch = _torch()
+        state = np.asarray(state)
+        dim = 1 << self.n
+        flat = state.reshape(-1, dim) if state.size != dim else state.reshape(1, dim)
+        if flat.shape[0] != self.batch:
+            self._resize_batch(flat.shape[0], copy=False)
+        self.data.copy_(torch.from_numpy(np.ascontiguousarray(flat, dtype=self.np_dtype)))
+
+    def _resize_batch(self, batch: int, copy: bool = True):
+        torch = _torch()
+        if batch == self.batch:
+            return
+        if self.batch != 1 and copy:
+            raise ValueError(f"cannot broadcast a batch of {self.batch} states to {batch}")
+        new = torch.empty((batch, 1 << self.n), dtype=self.t_dtype, device=self.device)
+        if copy:
+            new.copy_(self.data.expand(batch, -1))
+        self.data = new
+        self.batch = batch
+
+    def clone(self) -> "StateVector":
+        return StateVector(self.n, self.np_dtype, self.batch, self.device, buffer=self.data.clone())
+
+    def to_numpy(self) -> np.ndarray:
+        """Host copy shaped like default.qubit's state: (2,)*n, or (B, 2, ..., 2) if batched."""
+        out = self.data.cpu().numpy()
+        shape = (2,) * self.n
+        return out.reshape((self.batch,) + shape) if self.batch > 1 else out.reshape(shape)
+
+    # ---- raw kernel wrappers ----------------------------------------------------------------
+    def apply_matrix(self, mat: np.ndarray, wires: Sequence[int], control_wires: Sequence[int] = (),
+                     control_values: Sequence[int] | None = None):
+        """Dense (2^k x 2^k, optionally batched) matrix on ``wires`` controlled on
+        ``control_wires``."""
+        mat = np.asarray(mat)
+        k = len(wires)
+        d = 1 << k
+        batched = mat.ndim == 3
+        if batched and mat.shape[0] != self.batch:
+            self._resize_batch(mat.shape[0])
+        cvals = [1] * len(control_wires) if control_values is None else [int(bool(v)) for v in control_values]
+        tgt = int_array(self.bits(wires))
+        cb = int_array(self.bits(control_wires))
+        cv = int_array(cvals)
+        if not batched and k <= 3:
+            host = np.ascontiguousarray(mat, dtype=np.complex128)
+            check(self.lib.b200q_apply_matrix(self.ptr, self.n, self.dtype_code, self.batch, tgt, k,
+                                              cb, cv, len(cvals), host.ctypes.data_as(C.c_void_p),
+                                              None, 0, self.stream))
+            return
+        dev = self._upload(mat)
+        check(self.lib.b200q_apply_matrix(self.ptr, self.n, self.dtype_code, self.batch, tgt, k, cb,
+                                          cv, len(cvals), None, C.c_void_p(dev.data_ptr()),
+                                          d * d if batched else 0, self.stream))
+        self._keepalive = dev
+
+    def apply_diag(self, diag: np.ndarray, wires: Sequence[int]):
+        diag = np.asarray(diag)
+        k = len(wires)
+        batched = diag.ndim == 2
+        if batched and diag.shape[0] != self.batch:
+            self._resize_batch(diag.shape[0])
+        bits = int_array(self.bits(wires))
+        if not batched and k <= 6:
+            host = np.ascontiguousarray(diag, dtype=np.complex128)
+            check(self.lib.b200q_apply_diag(self.ptr, self.n, self.dtype_code, self.batch, bits, k,
+                                            host.ctypes.data_as(C.c_void_p), None, 0, self.stream))
+            return
+        dev = self._upload(diag)
+        check(self.lib.b200q_apply_diag(self.ptr, self.n, self.dtype_code, self.batch, bits, k, None,
+                                        C.c_void_p(dev.data_ptr()), (1 << k) if batched else 0,
+                                        self.stream))
+        self._keepalive = dev
+
+    def apply_phase(self, phase, control_wires: Sequence[int] = (), control_values=None):
+        """Multiply the subspace where ``control_wires == control_values`` by ``phase``
+        (scalar, or one value per batch element)."""
+        phase = np.asarray(phase, dtype=np.complex128)
+        cvals = [1] * len(control_wires) if control_values is None else [int(bool(v)) for v in control_values]
+        cb = int_array(self.bits(control_wires))
+        cv = int_array(cvals)
+        if phase.ndim == 0:
+            check(self.lib.b200q_apply_phase(self.ptr, self.n, self.dtype_code, self.batch, cb, cv,
+                                             len(cvals), float(phase.real), float(phase.imag), None,
+                                             self.stream))
+            return
+        if phase.shape[0] != self.batch:
+            self._resize_batch(phase.shape[0])
+        dev = self._upload(phase)
+        check(self.lib.b200q_apply_phase(self.ptr, self.n, self.dtype_code, self.batch, cb, cv,
+                                         len(cvals), 0.0, 0.0, C.c_void_p(dev.data_ptr()),
+                                         self.stream))
+        self._keepalive = dev
+
+    def apply_parity_phase(self, theta, wires: Sequence[int]):
+        """exp(-i theta/2 Z..Z) on ``wires``."""
+        theta = np.asarray(theta, dtype=np.float64)
+        mask = 0
+        for b in self.bits(wires):
+            mask |= 1 << b
+        p0, p1 = np.exp(-0.5j * theta), np.exp(0.5j * theta)
+        if theta.ndim == 0:
+            check(self.lib.b200q_apply_parity_phase(self.ptr, self.n, self.dtype_code, self.batch,
+                                                    mask, p0.real, p0.imag, p1.real, p1.imag, None,
+                                                    self.stream))
+            return
+        if theta.shape[0] != self.batch:
+            self._resize_batch(theta.shape[0])
+        dev = self._upload(np.stack([p0, p1], axis=-1))
+        check(self.lib.b200q_apply_parity_phase(self.ptr, self.n, self.dtype_code, self.batch, mask,
+                                                0, 0, 0, 0, C.c_void_p(dev.data_ptr()), self.stream))
+        self._keepalive = dev
+
+    def apply_pauli_rot(self, theta, pauli_word: str, wires: Sequence[int]):
+        """exp(-i theta/2 P) for any Pauli word, one sweep."""
+        active = [(c, w) for c, w in zip(pauli_word, wires) if c != "I"]
+        if not active:
+            self.apply_phase(np.exp(-0.5j * np.asarray(theta)))
+            return
+        if all(c == "Z" for c, _ in active):
+            self.apply_parity_phase(theta, [w for _, w in active])
+            return
+        xm = zm = ny = 0
+        for c, w in active:
+            b = 1 << self.bit(w)
+            if c in "XY":
+                xm |= b
+            if c in "ZY":
+                zm |= b
+            ny += c == "Y"
+        theta = np.asarray(theta, dtype=np.float64)
+        cs, sn = np.cos(theta / 2), np.sin(theta / 2)
+        if theta.ndim == 0:
+            check(self.lib.b200q_apply_pauli_rot(self.ptr, self.n, self.dtype_code, self.batch, xm,
+                                                 zm, ny, float(cs), float(sn), None, self.stream))
+            return
+        if theta.shape[0] != self.batch:
+            self._resize_batch(theta.shape[0])
+        dev = self._upload(cs + 1j * sn)
+        check(self.lib.b200q_apply_pauli_rot(self.ptr, self.n, self.dtype_code, self.batch, xm, zm,
+                                             ny, 0.0, 0.0, C.c_void_p(dev.data_ptr()), self.stream))
+        self._keepalive = dev
+
+    # ---- operator dispatch (apply_operation.py:258-351 singledispatch, re-done for kernels) --
+    def apply_operation(self, op):
+        """Apply one operator (ours or a duck-typed PennyLane one) in place."""
+        name = op.name
+        wires = list(op.wires)
+        if name in ("Identity", "Barrier", "WireCut", "Snapshot"):
+            return
+        if name == "GlobalPhase":
+            self.apply_phase(np.exp(-1j * np.asarray(op.data[0], dtype=np.float64)))
+            return
+        if name in _PHASE_GATES:
+            self.apply_phase(_PHASE_GATES[name], wires)
+            return
+        if name in ("PhaseShift", "U1"):
+            self.apply_phase(np.exp(1j * np.asarray(op.data[0], dtype=np.float64)), wires)
+            return
+        if name in ("CZ", "CCZ"):
+            self.apply_phase(-1.0, wires)
+            return
+        if name == "ControlledPhaseShift":
+            self.apply_phase(np.exp(1j * np.asarray(op.data[0], dtype=np.float64)), wires)
+            return
+        if name in ("RZ", "IsingZZ", "MultiRZ"):
+            self.apply_parity_phase(op.data[0], wires)
+            return
+        if name == "PauliRot":
+            self.apply_pauli_rot(op.data[0], op.hyperparameters["pauli_word"], wires)
+            return
+        if name in _CTRL_X_LIKE:
+            nc = _CTRL_X_LIKE[name]
+            self.apply_matrix(_XMAT, wires[nc:], wires[:nc])
+            return
+        if name == "MultiControlledX":
+            cvals = op.hyperparameters.get("control_values")
+            if cvals is None:
+                cvals = getattr(op, "control_values", None)
+            self.apply_matrix(_XMAT, wires[-1:], wires[:-1], cvals)
+            return
+        base = getattr(op, "base", None)
+        cw = list(getattr(op, "control_wires", ()) or ())
+        if base is not None and cw and (name.startswith("C(") or name == "ControlledQubitUnitary"):
+            cvals = getattr(op, "control_values", None)
+            tw = [w for w in wires if w not in cw]
+            if getattr(base, "has_matrix", True):
+                m = np.asarray(base.matrix())
+                if len(tw) and m.shape[-1] == (1 << len(tw)):
+                    bw = list(base.wires)
+                    self._apply_matrix_auto(m, bw, cw, cvals)
+                    return
+        if name in ("CRX", "CRY", "CRZ", "CRot", "CY", "CH", "CSWAP") and cw:
+            # textbook controlled gates: apply the base block to the target subspace only
+            m = np.asarray(op.matrix())
+            tw = [w for w in wires if w not in cw]
+            d = 1 << len(tw)
+            self._apply_matrix_auto(m[..., -d:, -d:], tw, cw, None)
+            return
+        if not getattr(op, "has_matrix", True):
+            raise B200QError(f"operator {name} has no matrix and no dedicated kernel")
+        self._apply_matrix_auto(np.asarray(op.matrix()), wires, (), None)
+
+    def _apply_matrix_auto(self, mat, wires, cw, cvals):
+        if _is_diagonal(mat) and not cw:
+            idx = np.arange(mat.shape[-1])
+            self.apply_diag(mat[..., idx, idx], wires)
+        else:
+            self.apply_matrix(mat, wires, cw, cvals)
+
+    # ---- measurements -----------------------------------------------------------------------
+    def probs(self, wires: Sequence[int] | None = None) -> np.ndarray:
+        """Marginal probabilities over ``wires`` in the given order (probs.py:101-135)."""
+        return self.probs_device(wires).cpu().numpy().reshape(
+            (self.batch, -1) if self.batch > 1 else (-1,))
+
+    def probs_device(self, wires: Sequence[int] | None = None):
+        torch = _torch()
+        wires = list(range(self.n)) if wires is None else list(wires)
+        m = len(wires)
+        out = torch.empty((self.batch, 1 << m), dtype=torch.float64, device=self.device)
+        w, wb = self.workspace()
+        check(self.lib.b200q_probs(self.ptr, self.n, self.dtype_code, self.batch,
+                                   int_array(self.bits(wires)), m, C.c_void_p(out.data_ptr()), w, wb,
+                                   self.stream))
+        return out
+
+    def expval_pauli_sentence(self, ps, wire_map=None) -> np.ndarray:
+        """<psi| sum_t c_t P_t |psi> for a Pauli sentence (mapping word -> coeff).
+        Returns a float (or (B,) array when batched)."""
+        wire_to_bit = {w: self.bit(w if wire_map is None else wire_map[w])
+                       for pw in ps for w in pw}
+        xs, zs, ys, cs = sentence_terms(ps, wire_to_bit)
+        cs = [float(np.real(c)) for c in cs]
+        w, wb = self.workspace()
+        check(self.lib.b200q_expval_pauli_sum(
+            self.ptr, self.n, self.dtype_code, self.batch, u64_array(xs), u64_array(zs),
+            int_array(ys) if ys else None, f64_array(cs), len(cs),
+            C.c_void_p(self._scal.data_ptr()), w, wb, self.stream))
+        res = self._scal[: self.batch].cpu().numpy().copy()
+        return res if self.batch > 1 else res[0]
+
+    def inner(self, other: "StateVector") -> np.ndarray:
+        """<self|other> per batch element."""
+        w, wb = self.workspace()
+        check(self.lib.b200q_inner(self.ptr, other.ptr, self.n, self.dtype_code, self.batch,
+                                   C.c_void_p(self._scal.data_ptr()), w, wb, self.stream))
+        r = self._scal[: 2 * self.batch].cpu().numpy()
+        res = r[: self.batch] + 1j * r[self.batch:]
+        return res if self.batch > 1 else res[0]
+
+    def norm2(self):
+        return np.real(self.inner(self))
+
+    def scale(self, factor):
+        self.apply_phase(factor)
+
+    def sample(self, shots: int, rng: np.random.Generator, wires: Sequence[int] | None = None,
+               exact: bool = True) -> np.ndarray:
+        """``shots`` samples of ``wires`` as a (shots, len(wires)) int64 array — or
+        (B, shots, len(wires)) when batched — drawn exactly like sampling.py:500-531 with the
+        HOST generator ``rng`` (one ``rng.random(shots)`` per batch element)."""
+        torch = _torch()
+        wires = list(range(self.n)) if wires is None else list(wires)
+        m = len(wires)
+        probs = self.probs_device(wires)
+        outs = []
+        need = ((1 << m) // 128 + (1 << m) // (128 * 2047) + 128) * 8 + (4 << 20)
+        w, wb = self.workspace(need)
+        for b in range(self.batch):
+            u = torch.from_numpy(rng.random(shots)).to(self.device)
+            bits = torch.empty((shots, m), dtype=torch.int64, device=self.device)
+            flags = torch.zeros(1, dtype=torch.int32, device=self.device)
+            pb = probs[b]
+            check(self.lib.b200q_sample(C.c_void_p(pb.data_ptr()), m, C.c_void_p(u.data_ptr()),
+                                        shots, 0 if exact else 1, None,
+                                        C.c_void_p(bits.data_ptr()),
+                                        C.c_void_p(self._scal.data_ptr()),
+                                        C.c_void_p(flags.data_ptr()), w, wb, self.stream))
+            norm = float(self._scal[0].item())
+            if int(flags.item()):
+                # sampling.py:322-325 — NaN probabilities give all-zero samples
+                outs.append(np.zeros((shots, m), dtype=np.int64))
+                continue
+            if abs(norm - 1.0) > 1e-6:  # sampling.py:33, 514-519
+                raise ValueError("probabilities do not sum to 1")
+            outs.append(bits.cpu().numpy())
+        return np.stack(outs) if self.batch > 1 else outs[0]
+
+
+_XMAT = np.array([[0, 1], [1, 0]], dtype=np.complex128)

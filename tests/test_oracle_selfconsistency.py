@@ -1,0 +1,93 @@
+"""CPU: the oracle's apply_operation (reference numpy kernels, independent gate matrices) against
+a brute-force Kronecker expansion of the package's operator matrices — the differential check of
+tests/devices/qubit/test_apply_operation.py:1028-1083 in the reference.  Two independently
+written sets of gate matrices (oracle/gates.py via expm of generators, pennylane_b200/ops.py
+closed forms) must agree on every gate."""
+import itertools
+
+import numpy as np
+import pytest
+
+from conftest import random_state
+from oracle.apply_operation import apply_operation
+from oracle.gates import matrix_of
+from pennylane_b200 import ops as q
+
+
+def all_ops(n, rng):
+    w = [int(x) for x in rng.permutation(n)]
+    a, b = w[0], w[1 % n]
+    out = [q.PauliX(wires=a), q.PauliY(wires=a), q.PauliZ(wires=a), q.Hadamard(wires=a),
+           q.S(wires=a), q.T(wires=a), q.SX(wires=a), q.RX(0.432, wires=a), q.RY(-1.2, wires=a),
+           q.RZ(2.1, wires=a), q.PhaseShift(0.77, wires=a), q.U1(0.3, wires=a),
+           q.Rot(0.1, 0.2, 0.3, wires=a), q.U2(0.3, -0.4, wires=a), q.U3(0.5, 0.6, 0.7, wires=a),
+           q.GlobalPhase(0.31, wires=a), q.adjoint(q.S(wires=a)), q.adjoint(q.RX(0.3, wires=a))]
+    if n >= 2:
+        out += [q.CNOT(wires=[a, b]), q.CZ(wires=[a, b]), q.CY(wires=[a, b]), q.CH(wires=[a, b]),
+                q.SWAP(wires=[a, b]), q.ISWAP(wires=[a, b]), q.SISWAP(wires=[a, b]),
+                q.ECR(wires=[a, b]), q.CRX(0.3, wires=[a, b]), q.CRY(0.4, wires=[a, b]),
+                q.CRZ(0.5, wires=[a, b]), q.CRot(0.1, 0.2, 0.3, wires=[a, b]),
+                q.ControlledPhaseShift(0.9, wires=[a, b]), q.IsingXX(0.3, wires=[a, b]),
+                q.IsingYY(0.4, wires=[a, b]), q.IsingZZ(0.5, wires=[a, b]),
+                q.IsingXY(0.6, wires=[a, b]), q.PSWAP(0.7, wires=[a, b]),
+                q.SingleExcitation(0.8, wires=[a, b]), q.SingleExcitationPlus(0.8, wires=[a, b]),
+                q.SingleExcitationMinus(0.8, wires=[a, b]), q.MultiRZ(0.45, wires=[a, b]),
+                q.PauliRot(0.3, "XY", wires=[a, b]), q.ctrl(q.RY(0.2, wires=b), a, [0]),
+                q.adjoint(q.ISWAP(wires=[a, b]))]
+    if n >= 3:
+        c = w[2]
+        out += [q.Toffoli(wires=[a, b, c]), q.CSWAP(wires=[a, b, c]), q.CCZ(wires=[a, b, c]),
+                q.MultiControlledX(wires=[a, b, c], control_values=[0, 1]),
+                q.PauliRot(0.7, "YIX", wires=[a, b, c]), q.MultiRZ(0.2, wires=[a, b, c])]
+    if n >= 4:
+        out += [q.DoubleExcitation(0.5, wires=w[:4])]
+    return out
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 5])
+def test_oracle_matches_kronecker_expansion(n):
+    rng = np.random.default_rng(n)
+    state = random_state(n, seed=n)
+    for op in all_ops(n, rng):
+        ref = (q.matrix(op, wire_order=range(n)) @ state.reshape(-1)).reshape(state.shape)
+        got = apply_operation(op, state)
+        assert np.allclose(got, ref, atol=1e-13), op
+
+
+def test_oracle_gate_matrices_match_package():
+    rng = np.random.default_rng(0)
+    for op in all_ops(5, rng):
+        if op.name in ("GlobalPhase",):
+            continue
+        assert np.allclose(matrix_of(op), op.matrix(), atol=1e-14), op.name
+
+
+def test_oracle_tensordot_branch_and_batching():
+    n = 13      # state.ndim >= 13 -> tensordot (apply_operation.py:29-30)
+    state = random_state(n, seed=1)
+    for op in [q.RY(0.3, wires=12), q.CNOT(wires=[12, 0]), q.IsingXX(0.2, wires=[3, 9]),
+               q.Hadamard(wires=5), q.Toffoli(wires=[1, 11, 6])]:
+        ref = (q.matrix(op, wire_order=range(n)) @ state.reshape(-1)).reshape(state.shape)
+        assert np.allclose(apply_operation(op, state), ref, atol=1e-13)
+    th = np.array([0.1, 0.2, 0.3])
+    st = random_state(4, seed=2)
+    for op in [q.RX(th, wires=2), q.IsingZZ(th, wires=[0, 3]), q.PhaseShift(th, wires=1),
+               q.GlobalPhase(th, wires=0)]:
+        got = apply_operation(op, st)
+        assert got.shape == (3,) + st.shape
+        for b in range(3):
+            single = op._with_params([th[b]])
+            assert np.allclose(got[b], apply_operation(single, st), atol=1e-14)
+    bst = random_state(4, seed=3, batch=3)
+    got = apply_operation(q.RX(th, wires=1), bst, is_state_batched=True)
+    for b in range(3):
+        assert np.allclose(got[b], apply_operation(q.RX(th[b], wires=1), bst[b]), atol=1e-14)
+
+
+def test_oracle_multicontrolledx_wide_path():
+    n = 10
+    state = random_state(n, seed=4)
+    cv = [1, 0, 1, 1, 0, 1, 1, 0, 1]
+    op = q.MultiControlledX(wires=[3, 0, 9, 1, 7, 4, 2, 8, 6, 5], control_values=cv)
+    ref = (q.matrix(op, wire_order=range(n)) @ state.reshape(-1)).reshape(state.shape)
+    assert np.allclose(apply_operation(op, state), ref, atol=1e-14)
