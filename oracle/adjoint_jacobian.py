@@ -94,6 +94,8 @@ def adjoint_jvp(tape, tangents, state):                    # adjoint_jacobian.py
     _, n_op_params = _op_param_layout(tape)
     param_number = n_op_params - 1
     trainable_param_number = len(trainable) - 1
+    while trainable_param_number >= 0 and trainable[trainable_param_number] > param_number:
+        trainable_param_number -= 1
     tangents_out = np.zeros(n_obs)
     for op in reversed(tape.operations[tape.num_preps:]):
         adj_op = _adjoint_op(op)
@@ -137,6 +139,8 @@ def adjoint_vjp(tape, cotangents, state):                  # adjoint_jacobian.py
     _, n_op_params = _op_param_layout(tape)
     param_number = n_op_params - 1
     trainable_param_number = len(trainable) - 1
+    while trainable_param_number >= 0 and trainable[trainable_param_number] > param_number:
+        trainable_param_number -= 1
     out = np.zeros(len(trainable))
     for op in reversed(tape.operations[tape.num_preps:]):
         adj_op = _adjoint_op(op)
