@@ -213,7 +213,7 @@ def workload_config(args, n):
             "qubits": n, "layers": args.layers, "gates": 3 * n * args.layers,
             "state_bytes": 16 * (1 << n), "l2_policy": "inputs larger than L2 (state >> 126 MB)"
             if n >= 24 else "state fits L2: flushed between steps",
-            "fusion": args.fusion, "parallelism": f"shard{args.gpus}" if args.gpus > 1 else "single"}
+            "fusion": f"{args.fusion} (level {args.fusion_level})" if args.fusion == "on" else "off", "parallelism": f"shard{args.gpus}" if args.gpus > 1 else "single"}
 
 
 # --------------------------------------------------------------------------------------------
@@ -255,11 +255,28 @@ def run_ours(args):
     fam = {}          # kernel family -> [events...]
     launches = 0
 
+    fused_segments = None
+    if args.fusion == "on":
+        from pennylane_b200.compiler import compile_ops
+        dT, dL = sv.default_tile()
+        fused_segments = compile_ops(ops_, n, level=args.fusion_level, T=dT, L=dL)
+
     def forward(record):
         nonlocal launches
         sv.reset()
         launches += 2
-        for op in ops_:
+        if fused_segments is not None:
+            S2 = 2.0 * 16 * (1 << n)
+            for seg in fused_segments:
+                if record:
+                    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                sv.run_segment(seg)
+                launches += 1
+                if record:
+                    e1.record()
+                    fam.setdefault("tile_segment", []).append((e0, e1, S2))
+        for op in (ops_ if fused_segments is None else ()):
             if record:
                 e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
                 e0.record()
@@ -318,7 +335,8 @@ def run_ours(args):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
-    kernel_of = {"RY": "k_dense<double,1,byval>", "RZ": "k_parity_phase<double>",
+    kernel_of = {"tile_segment": "k_tile<double,256> (fused segment: 2*S per launch)",
+                 "RY": "k_dense<double,1,byval>", "RZ": "k_parity_phase<double>",
                  "CNOT": "k_dense<double,1,byval> (1 control)"}
     all_gate_bytes = sum(v["bytes"] for k, v in fam_stats.items() if k != "expval")
     all_gate_secs = sum(v["seconds"] for k, v in fam_stats.items() if k != "expval")
@@ -333,7 +351,7 @@ def run_ours(args):
                 "all_gates_gbps": all_gate_bytes / all_gate_secs / 1e9}
 
     # e2e: public API, host parameters in / host scalar out, wall clock
-    dev = qb.B200Qubit(wires=n, seed=0)
+    dev = qb.B200Qubit(wires=n, seed=0, fusion=args.fusion_level if args.fusion == "on" else 0)
     par = np.random.default_rng(3).uniform(0, 2 * np.pi, (args.layers, n, 2))
     pinned = torch.from_numpy(par).pin_memory()
 
@@ -390,6 +408,7 @@ def run_ours(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "c128",
         "data": "synthetic", "config": workload_config(args, n),
         "hbm_gbps": roofline["all_gates_gbps"], "expval": float(val),
+        "state_sweeps_per_step": (len(fused_segments) if fused_segments is not None else ngates),
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "adjoint": adjoint,
         "gpu_launches": int(timed_launches), "clocks": clk,
     }
@@ -404,7 +423,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--qubits", type=int, default=30, help="qubits per GPU shard (30 = 16 GiB)")
     ap.add_argument("--layers", type=int, default=8)
-    ap.add_argument("--fusion", default="off", choices=["off", "on"])
+    ap.add_argument("--fusion", default="on", choices=["off", "on"])
+    ap.add_argument("--fusion-level", type=int, default=1)
     ap.add_argument("--no-adjoint", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--quick", action="store_true")

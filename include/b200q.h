@@ -120,6 +120,29 @@ int b200q_sample(double* probs_dev, int m, const double* uniforms_dev, int64_t s
                  int64_t* idx_out_dev, int64_t* bits_out_dev, double* norm_out_dev,
                  int* flags_dev, void* work, size_t work_bytes, void* stream);
 
+/* Fused gate segment: ONE read + ONE write of the state applies `nops` gates through a
+ * shared-memory tile spanning `tile_bits` (T ascending bit positions, the first L equal to
+ * 0..L-1).  ops_host: array of 64-byte b200q_tile_op records (layout below); mats_host: the
+ * segment's complex128 matrix / phase table.  Replaces `nops` iterations of the gate loop
+ * simulate.py:214-235 (the reference has no fusion).
+ *
+ *   struct b200q_tile_op {
+ *     int32  kind;        // 0 dense 2x2, 1 dense 4x4, 2 controlled-X, 3 parity phase,
+ *                         // 4 diagonal table (<= 4 bits), 5 swap
+ *     int32  t0, t1;      // tile-local target bits (t0 = matrix MSB)
+ *     int32  mat_off;     // offset into mats_host (complex entries)
+ *     uint32 ctrl_mask_l, ctrl_val_l;   // controls on tile-local bits
+ *     uint32 par_mask_l;  // parity phase: tile-local bits
+ *     int32  ndiag;       // diagonal table: number of index bits
+ *     uint64 ctrl_mask_e, ctrl_val_e;   // controls on bits outside the tile (global positions)
+ *     uint64 par_mask_e;  // parity phase: bits outside the tile
+ *     int8   dbits[8];    // diagonal table index bits, MSB first: >= 0 tile-local, < 0 -(global)-1
+ *   };
+ */
+int b200q_apply_tile(void* state, int n, int dtype, int64_t batch, const int* tile_bits, int T,
+                     int L, const void* ops_host, int nops, const void* mats_host, int nmat,
+                     void* work, size_t work_bytes, void* stream);
+
 /* One reverse-sweep step of adjoint differentiation on vecs = [1 + n_bras][2^n] (row 0 = ket):
  *   z_b = <bra_b| G |ket>,  ket <- A ket,  bra_b <- A bra_b      (A = U^dagger, k <= 3)
  * out_dev[b] = -Im z_b  (= Re <bra_b| i G |ket>, the Jacobian entry when bras carry the factor

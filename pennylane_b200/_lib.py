@@ -45,6 +45,7 @@ SIGNATURES = {
         _i, [_p, _p, _i, _i, _i64, _u64p, _u64p, _ip, _dp, _dp, _i, _d, _p, _sz, _p]),
     "b200q_pauli_braket": (_i, [_p, _p, _i, _i, _u64, _u64, _i, _p, _p, _sz, _p]),
     "b200q_sample": (_i, [_p, _i, _p, _i64, _i, _p, _p, _p, _p, _p, _sz, _p]),
+    "b200q_apply_tile": (_i, [_p, _i, _i, _i64, _ip, _i, _i, _p, _i, _p, _i, _p, _sz, _p]),
     "b200q_adjoint_step": (_i, [_p, _i, _i, _i, _ip, _i, _ip, _ip, _i, _p, _p, _p, _p, _sz, _p]),
 }
 

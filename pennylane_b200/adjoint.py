@@ -175,7 +175,8 @@ def _reverse_sweep(tape, sweep: _Sweep, n_rows_out: int):
     return vals, filled, trainable
 
 
-def adjoint_jacobian(tape, dtype=np.complex128, device=None, return_state: bool = False):
+def adjoint_jacobian(tape, dtype=np.complex128, device=None, return_state: bool = False,
+                     fusion: int = 0):
     """adjoint_jacobian.py:77-149.  Runs the forward pass itself (directly into row 0 of the
     sweep buffer).  Returns the Jacobian in the reference's nested-tuple layout; with
     ``return_state`` also a ``StateVector`` copy of the final state taken before the sweep."""
@@ -188,7 +189,7 @@ def adjoint_jacobian(tape, dtype=np.complex128, device=None, return_state: bool 
                          "(default_qubit.py:348 expands broadcast tapes first)")
     n_obs = len(obs)
     sweep = _Sweep(tape, dtype, device, n_obs)
-    get_final_state(tape, dtype=dtype, device=device, buffer=sweep.vecs[0:1])
+    get_final_state(tape, dtype=dtype, device=device, buffer=sweep.vecs[0:1], fusion=fusion)
     final = sweep.ket.clone() if return_state else None
     for k, o in enumerate(obs):
         sweep.fill_bra_from_observable(k, o, 2.0)

@@ -10,6 +10,7 @@
 #include "gates.cuh"
 #include "measure.cuh"
 #include "sample.cuh"
+#include "tile.cuh"
 
 namespace b200q {
 
@@ -422,6 +423,57 @@ static int np_sum(const double* p, uint64_t count, double* out, double* scratch,
   return 0;
 }
 
+template <typename T>
+static int tile_t(void* state, int n, int64_t batch, const int* tile_bits, int Tn, int L,
+                  const TileOp* ops_host, int nops, const double2* mats_host, int nmat,
+                  void* work, size_t work_bytes, cudaStream_t s) {
+  B200Q_REQUIRE(Tn >= 1 && Tn <= n && Tn <= 14 && L >= 0 && L <= Tn, "tile: bad T=%d L=%d n=%d",
+                Tn, L, n);
+  B200Q_REQUIRE(nops >= 1 && nops <= 4096 && nmat >= 0, "tile: bad nops=%d nmat=%d", nops, nmat);
+  TileArgs a;
+  memset(&a, 0, sizeof(a));
+  a.n = n; a.T = Tn; a.L = L; a.nops = nops; a.nmat = nmat;
+  uint64_t inmask = 0;
+  for (int i = 0; i < Tn; ++i) {
+    const int b = tile_bits[i];
+    B200Q_REQUIRE(b >= 0 && b < n && !((inmask >> b) & 1), "tile: bad tile bit %d", b);
+    B200Q_REQUIRE(i < L ? b == i : (i == 0 || b > tile_bits[i - 1]),
+                  "tile: bits must be ascending with the first L equal to 0..L-1");
+    inmask |= 1ull << b;
+    if (i >= L) a.hi_bits[i - L] = (int8_t)b;
+  }
+  int no = 0;
+  for (int b = 0; b < n; ++b)
+    if (!((inmask >> b) & 1)) a.out_bits[no++] = (int8_t)b;
+  a.ntiles = 1ull << (n - Tn);
+  const size_t ops_bytes = (size_t)nops * sizeof(TileOp);
+  const size_t mat_bytes = (size_t)nmat * sizeof(double2);
+  B200Q_REQUIRE(work && ops_bytes + mat_bytes + 512 <= kTermRegion && work_bytes >= kTermRegion,
+                "tile: segment tables too large for the workspace");
+  char* w = (char*)work;
+  B200Q_CHECK(cudaMemcpyAsync(w, ops_host, ops_bytes, cudaMemcpyHostToDevice, s));
+  const size_t moff = (ops_bytes + 255) & ~(size_t)255;
+  if (nmat) B200Q_CHECK(cudaMemcpyAsync(w + moff, mats_host, mat_bytes, cudaMemcpyHostToDevice, s));
+  const size_t smem = (sizeof(cx<T>) << Tn) + sizeof(cx<T>) * ((nmat + 1) & ~1) + ops_bytes;
+  B200Q_REQUIRE(smem <= 227 * 1024, "tile: %zu bytes of shared memory needed (T=%d, %d ops)", smem,
+                Tn, nops);
+  constexpr int THREADS = 256;
+  static size_t attr_set[2] = {0, 0};
+  const int ti = sizeof(T) == 8 ? 1 : 0;
+  if (attr_set[ti] < smem) {
+    B200Q_CHECK(cudaFuncSetAttribute(k_tile<T, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     227 * 1024));
+    attr_set[ti] = 227 * 1024;
+  }
+  const uint64_t per_sm = std::max<uint64_t>(1, (227 * 1024) / smem);
+  const uint64_t cap = (uint64_t)sm_count() * std::min<uint64_t>(per_sm, 8);
+  dim3 grid((unsigned)std::min<uint64_t>(a.ntiles, cap), (unsigned)batch);
+  k_tile<T, THREADS><<<grid, THREADS, smem, s>>>((cx<T>*)state, a, (const TileOp*)w,
+                                                  (const double2*)(w + moff));
+  B200Q_LAUNCH_CHECK();
+  return 0;
+}
+
 }  // namespace b200q
 
 using namespace b200q;
@@ -628,6 +680,17 @@ int b200q_sample(double* probs_dev, int m, const double* uniforms_dev, int64_t s
     B200Q_LAUNCH_CHECK();
   }
   return 0;
+}
+
+int b200q_apply_tile(void* state, int n, int dtype, int64_t batch, const int* tile_bits, int T,
+                     int L, const void* ops_host, int nops, const void* mats_host, int nmat,
+                     void* work, size_t work_bytes, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  DISPATCH(dtype,
+           tile_t<float>(state, n, batch, tile_bits, T, L, (const TileOp*)ops_host, nops,
+                         (const double2*)mats_host, nmat, work, work_bytes, s),
+           tile_t<double>(state, n, batch, tile_bits, T, L, (const TileOp*)ops_host, nops,
+                          (const double2*)mats_host, nmat, work, work_bytes, s));
 }
 
 int b200q_adjoint_step(void* vecs, int n, int dtype, int n_bras, const int* tgt_bits, int k,

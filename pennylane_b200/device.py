@@ -158,6 +158,9 @@ class B200Qubit:
         c_dtype: ``np.complex128`` (default) or ``np.complex64``.
         exact_sampling (bool): build the CDF in numpy's summation order (bit-exact shots) or
             with the parallel scan.
+        fusion (int): 0 = one kernel per gate (rounding-stable parity mode); 1 = host fusion
+            pass with single-qubit block merging + tile kernel (default); 2 = also two-qubit
+            dense blocks.
         device: torch CUDA device.
     """
 
@@ -166,10 +169,10 @@ class B200Qubit:
     pennylane_requires = ">=0.44"
     version = "0.1.0"
     author = "b200-qubit"
-    _device_options = ("rng", "c_dtype", "exact_sampling")
+    _device_options = ("rng", "c_dtype", "exact_sampling", "fusion")
 
     def __init__(self, wires=None, shots=None, seed="global", c_dtype=np.complex128,
-                 exact_sampling: bool = True, device=None, max_workers=None):
+                 exact_sampling: bool = True, device=None, max_workers=None, fusion: int = 1):
         if max_workers is not None:
             raise DeviceError("b200.qubit owns a CUDA context and does not support max_workers "
                               "(process pools); run one device per GPU instead.")
@@ -185,6 +188,7 @@ class B200Qubit:
         self._rng = np.random.default_rng(seed)
         self._c_dtype = np.dtype(c_dtype)
         self._exact_sampling = bool(exact_sampling)
+        self._fusion = int(fusion)
         self._torch_device = device
         self._debugger = None
         self._state_cache = None
@@ -230,6 +234,7 @@ class B200Qubit:
         opts.setdefault("rng", self._rng)
         opts.setdefault("c_dtype", self._c_dtype)
         opts.setdefault("exact_sampling", self._exact_sampling)
+        opts.setdefault("fusion", self._fusion)
         updated["device_options"] = opts
         return replace(config, **updated)
 
@@ -311,7 +316,7 @@ class B200Qubit:
         return _sim.simulate(
             circuit, rng=opts.get("rng", self._rng), dtype=opts.get("c_dtype", self._c_dtype),
             device=self._torch_device, exact_sampling=opts.get("exact_sampling", self._exact_sampling),
-            state_cache=self._state_cache)
+            state_cache=self._state_cache, fusion=opts.get("fusion", self._fusion))
 
     def execute(self, circuits, execution_config: ExecutionConfig | None = None):
         batch, single = self._as_batch(circuits)
@@ -329,7 +334,8 @@ class B200Qubit:
         batch, single = self._as_batch(circuits)
         self._track(batch, "derivative_batches")
         res = tuple(_adjoint.adjoint_jacobian(c, dtype=self._dtype(execution_config),
-                                              device=self._torch_device) for c in batch)
+                                              device=self._torch_device, fusion=self._fusion)
+                    for c in batch)
         return res[0] if single else res
 
     def execute_and_compute_derivatives(self, circuits, execution_config=None):
@@ -339,7 +345,8 @@ class B200Qubit:
         for c in batch:
             c = c.map_to_standard_wires()
             jac, final = _adjoint.adjoint_jacobian(c, dtype=self._dtype(execution_config),
-                                                   device=self._torch_device, return_state=True)
+                                                   device=self._torch_device, return_state=True,
+                                                   fusion=self._fusion)
             results.append(_sim.measure_final_state(c, final, False))
             jacs.append(jac)
         if single:

@@ -19,7 +19,7 @@ def _is_prep(op) -> bool:
     return hasattr(op, "state_vector")
 
 
-def get_final_state(circuit, dtype=np.complex128, device=None, buffer=None):
+def get_final_state(circuit, dtype=np.complex128, device=None, buffer=None, fusion: int = 0):
     """Run the gate loop (simulate.py:214-235).  ``circuit`` must be in standard wire order.
 
     Returns ``(StateVector, is_state_batched)``.  Measurement-only wires are simply extra
@@ -35,8 +35,13 @@ def get_final_state(circuit, dtype=np.complex128, device=None, buffer=None):
         vec = np.asarray(prep.state_vector(wire_order=list(range(n))))
         # single-precision StatePrep gives a complex64 simulation (initialize_state.py:47-51)
         sv.set_state(vec)
-    for op in ops_[bool(prep):]:
-        sv.apply_operation(op)
+    gates = ops_[bool(prep):]
+    if fusion and gates:
+        # host fusion pass + tile kernel: one state sweep per segment (compiler.py)
+        sv.apply_operations_fused(gates, level=fusion)
+    else:
+        for op in gates:
+            sv.apply_operation(op)
     return sv, sv.batch > 1
 
 
@@ -262,10 +267,10 @@ def measure_final_state(circuit, sv: StateVector, is_state_batched: bool, rng=No
 
 
 def simulate(circuit, rng=None, dtype=np.complex128, device=None, exact_sampling: bool = True,
-             state_cache=None):
+             state_cache=None, fusion: int = 0):
     """simulate.py:308-393 (without native mid-circuit measurements)."""
     circuit = circuit.map_to_standard_wires()
-    sv, batched = get_final_state(circuit, dtype=dtype, device=device)
+    sv, batched = get_final_state(circuit, dtype=dtype, device=device, fusion=fusion)
     if state_cache is not None:
         state_cache[circuit.hash] = sv
     return measure_final_state(circuit, sv, batched, rng=rng, exact_sampling=exact_sampling)

@@ -315,6 +315,47 @@ class StateVector:
             raise B200QError(f"operator {name} has no matrix and no dedicated kernel")
         self._apply_matrix_auto(np.asarray(op.matrix()), wires, (), None)
 
+    # ---- fused execution (host fusion pass + tile kernel) ---------------------------------------
+    def default_tile(self):
+        """(T, L): tile bits / contiguous low bits.  64 KiB tiles -> 3 CTAs per SM."""
+        import os
+
+        T = int(os.environ.get("B200Q_TILE_T", 12 if self.dtype_code else 13))
+        L = int(os.environ.get("B200Q_TILE_L", 5 if self.dtype_code else 6))
+        return T, L
+
+    def apply_operations_fused(self, ops_, level: int = 1, T: int | None = None,
+                               L: int | None = None, bit_of=None):
+        """Apply a list of operators through the fusion pass (compiler.py): returns the number of
+        state sweeps (kernel launches over the full state) that were issued."""
+        from .compiler import compile_ops
+
+        dT, dL = self.default_tile()
+        segs = compile_ops(ops_, self.n, bit_of=bit_of, level=level, T=T or dT, L=L if L is not None else dL)
+        for seg in segs:
+            self.run_segment(seg)
+        return len(segs)
+
+    def run_segment(self, seg):
+        from .compiler import DIAG, encode_segment
+
+        if seg.tile_bits is None:
+            p = seg.prims[0]
+            if p.op is not None:
+                self.apply_operation(p.op)
+            elif p.kind == DIAG:
+                self.apply_diag(np.asarray(p.mat), [self.n - 1 - b for b in p.other])
+            else:  # pragma: no cover
+                raise B200QError("unexpected generic primitive")
+            return
+        ops_arr, table = encode_segment(seg)
+        w, wb = self.workspace()
+        check(self.lib.b200q_apply_tile(
+            self.ptr, self.n, self.dtype_code, self.batch, int_array(seg.tile_bits),
+            len(seg.tile_bits), _low_run(seg.tile_bits),
+            C.cast(ops_arr, C.c_void_p), len(seg.prims), table.ctypes.data_as(C.c_void_p),
+            int(table.size), w, wb, self.stream))
+
     def _apply_matrix_auto(self, mat, wires, cw, cvals):
         if _is_diagonal(mat) and not cw:
             idx = np.arange(mat.shape[-1])
@@ -403,3 +444,13 @@ class StateVector:
 
 
 _XMAT = np.array([[0, 1], [1, 0]], dtype=np.complex128)
+
+
+def _low_run(tile_bits) -> int:
+    """Number of leading tile bits that are contiguous from bit 0 (the kernel's L)."""
+    run = 0
+    for i, b in enumerate(tile_bits):
+        if b != i:
+            break
+        run += 1
+    return run

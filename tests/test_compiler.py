@@ -1,0 +1,134 @@
+"""CPU: the host fusion pass (lowering -> block merging -> segment packing) preserves the
+circuit.  A small numpy interpreter of the tile primitives (test-only) replays the compiled
+segments and is compared with the oracle's gate-by-gate result."""
+import numpy as np
+import pytest
+
+from conftest import random_state
+from oracle.apply_operation import apply_operation
+from pennylane_b200 import ops as q
+from pennylane_b200.compiler import (CX, DENSE1, DENSE2, DIAG, GENERIC, PARITY, SWAP, TileOp,
+                                     compile_ops, encode_segment)
+
+
+def _apply_prim(p, psi, n):
+    """psi: flat array indexed by the integer whose bit b is `bit position b`."""
+    N = 1 << n
+    idx = np.arange(N)
+    sel = np.ones(N, dtype=bool)
+    for b, v in p.ctrl.items():
+        sel &= ((idx >> b) & 1) == v
+    out = psi.copy()
+    if p.kind == PARITY:
+        par = np.zeros(N, dtype=int)
+        for b in p.other:
+            par ^= (idx >> b) & 1
+        ph = np.where(par == 1, p.mat[1], p.mat[0])
+        out[sel] = psi[sel] * ph[sel]
+    elif p.kind == DIAG:
+        k = len(p.other)
+        t = np.zeros(N, dtype=int)
+        for j, b in enumerate(p.other):
+            t |= ((idx >> b) & 1) << (k - 1 - j)
+        out[sel] = psi[sel] * np.asarray(p.mat)[t[sel]]
+    elif p.kind in (CX, DENSE1):
+        m = np.array([[0, 1], [1, 0]], dtype=complex) if p.kind == CX else p.mat
+        b = p.targets[0]
+        i0 = idx[sel & (((idx >> b) & 1) == 0)]
+        i1 = i0 | (1 << b)
+        out[i0] = m[0, 0] * psi[i0] + m[0, 1] * psi[i1]
+        out[i1] = m[1, 0] * psi[i0] + m[1, 1] * psi[i1]
+    elif p.kind in (DENSE2, SWAP):
+        m = p.mat if p.kind == DENSE2 else np.eye(4)[[0, 2, 1, 3]].astype(complex)
+        b0, b1 = p.targets
+        base = idx[sel & (((idx >> b0) & 1) == 0) & (((idx >> b1) & 1) == 0)]
+        ii = [base, base | (1 << b1), base | (1 << b0), base | (1 << b0) | (1 << b1)]
+        x = [psi[i] for i in ii]
+        for r in range(4):
+            out[ii[r]] = sum(m[r, c] * x[c] for c in range(4))
+    else:
+        raise AssertionError(p.kind)
+    return out
+
+
+def _replay(segs, state, n):
+    psi = state.reshape(-1).copy()
+    for seg in segs:
+        for p in seg.prims:
+            if seg.tile_bits is not None:
+                assert set(p.targets) <= set(seg.tile_bits), "target outside the tile"
+            if p.kind == GENERIC:
+                psi = apply_operation(p.op, psi.reshape((2,) * n)).reshape(-1)
+            else:
+                psi = _apply_prim(p, psi, n)
+    return psi.reshape((2,) * n)
+
+
+def _random_circuit(n, depth, seed):
+    rng = np.random.default_rng(seed)
+    ops_ = []
+    for _ in range(depth):
+        w = [int(x) for x in rng.permutation(n)]
+        a, b, c = w[0], w[1], w[2]
+        th = rng.uniform(0, 6)
+        choices = [
+            q.RX(th, wires=a), q.RY(th, wires=a), q.RZ(th, wires=a), q.Hadamard(wires=a),
+            q.PauliX(wires=a), q.PauliY(wires=a), q.PauliZ(wires=a), q.S(wires=a), q.T(wires=a),
+            q.SX(wires=a), q.PhaseShift(th, wires=a), q.Rot(th, 0.3, -th, wires=a),
+            q.GlobalPhase(th, wires=a), q.CNOT(wires=[a, b]), q.CZ(wires=[a, b]),
+            q.CY(wires=[a, b]), q.SWAP(wires=[a, b]), q.ISWAP(wires=[a, b]),
+            q.CRX(th, wires=[a, b]), q.CRZ(th, wires=[a, b]), q.CRot(th, .1, .2, wires=[a, b]),
+            q.ControlledPhaseShift(th, wires=[a, b]), q.IsingXX(th, wires=[a, b]),
+            q.IsingZZ(th, wires=[a, b]), q.IsingXY(th, wires=[a, b]),
+            q.PauliRot(th, "XY", wires=[a, b]), q.PauliRot(th, "ZIZ", wires=[a, b, c]),
+            q.PauliRot(th, "XYZ", wires=[a, b, c]), q.MultiRZ(th, wires=[a, b, c]),
+            q.Toffoli(wires=[a, b, c]), q.CSWAP(wires=[a, b, c]), q.CCZ(wires=[a, b, c]),
+            q.MultiControlledX(wires=[a, b, c], control_values=[0, 1]),
+            q.ctrl(q.RY(th, wires=a), [b, c], [1, 0]), q.ctrl(q.IsingXX(th, wires=[a, b]), c),
+            q.adjoint(q.S(wires=a)), q.DiagonalQubitUnitary(np.exp(1j * rng.normal(size=8)), wires=[a, b, c]),
+            q.QubitUnitary(np.linalg.qr(rng.normal(size=(8, 8)) + 1j * rng.normal(size=(8, 8)))[0], wires=[a, b, c]),
+        ]
+        ops_.append(choices[int(rng.integers(len(choices)))])
+    return ops_
+
+
+@pytest.mark.parametrize("level", [0, 1, 2])
+@pytest.mark.parametrize("n,T,L", [(6, 4, 2), (7, 5, 3), (8, 12, 5), (9, 6, 0)])
+def test_compiled_segments_reproduce_circuit(level, n, T, L):
+    ops_ = _random_circuit(n, 120, seed=n * 10 + level)
+    state = random_state(n, seed=n)
+    ref = state
+    for op in ops_:
+        ref = apply_operation(op, ref)
+    segs = compile_ops(ops_, n, level=level, T=T, L=L)
+    assert sum(s.ngates for s in segs) == sum(1 for o in ops_ if o.name != "Identity")
+    for s in segs:
+        if s.tile_bits is not None:
+            assert len(s.tile_bits) == min(T, n) and s.tile_bits == sorted(s.tile_bits)
+            assert s.tile_bits[:min(L, n)] == list(range(min(L, n)))
+    got = _replay(segs, state, n)
+    assert np.max(np.abs(got - ref)) < 1e-12
+
+
+def test_hea_packing_and_encoding():
+    import bench
+
+    n = 30
+    ops_ = bench.hea_ops(n)
+    segs = compile_ops(ops_, n, level=1, T=12, L=5)
+    assert sum(s.ngates for s in segs) == 720 and len(segs) <= 40
+    for s in segs:
+        arr, table = encode_segment(s)
+        assert len(arr) == len(s.prims) and table.dtype == np.complex128
+        assert isinstance(arr[0], TileOp)
+        for o in arr:
+            assert 0 <= o.t0 < 12 and 0 <= o.t1 < 12 and o.mat_off + 2 <= table.size + 2
+
+
+def test_merging_reduces_primitives():
+    ops_ = [q.RZ(.1, wires=0), q.RY(.2, wires=0), q.RZ(.3, wires=0), q.Hadamard(wires=1),
+            q.CNOT(wires=[0, 1]), q.T(wires=1), q.S(wires=1)]
+    l0 = compile_ops(ops_, 2, level=0)
+    l1 = compile_ops(ops_, 2, level=1)
+    assert sum(len(s.prims) for s in l0) == 7 and sum(len(s.prims) for s in l1) == 4
+    assert sum(s.ngates for s in l1) == 7
