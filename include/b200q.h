@@ -143,6 +143,25 @@ int b200q_apply_tile(void* state, int n, int dtype, int64_t batch, const int* ti
                      int L, const void* ops_host, int nops, const void* mats_host, int nmat,
                      void* work, size_t work_bytes, void* stream);
 
+/* Register-tiled fused segment (the production fused path; b200q_apply_tile is the small-state
+ * fallback).  ONE read + ONE write of vec0 (and of vec1 when given) applies `nops` records:
+ * every thread keeps 2^RB amplitudes in registers, a segment is a sequence of ROUNDS (which tile
+ * positions are register bits), gates on register bits cost no memory traffic, rounds are
+ * separated by one swizzled shared-memory transpose.  (T, RB, threads) are fixed per
+ * (dtype, nvec): query them with b200q_rtile_geometry.  ops_host: 64-byte records
+ * (pennylane_b200/csrc/rtile.cuh `RtOp`, mirrored by pennylane_b200/compiler.py `RtOp`); the
+ * first record must be a ROUND.  base_hi is OR-ed into the tile base index when evaluating
+ * controls / parities on bits outside the tile: a sharded state passes its rank bits there.
+ * vec1 != NULL selects adjoint mode: gates act on both vectors, GEN records accumulate
+ * coef * Im<vec1| P |vec0> into slot q0; out_dev[batch][nslots] = scale * sums (deterministic
+ * order); write0 = 0 leaves vec0 untouched (extra bras re-use the ket).
+ * Replaces simulate.py:214-235 (gate loop) and adjoint_jacobian.py:121-137 (reverse sweep). */
+int b200q_rtile_geometry(int dtype, int nvec, int* T_out, int* RB_out, int* threads_out);
+int b200q_apply_rtile(void* vec0, void* vec1, int n, int dtype, int64_t batch, const int* tile_bits,
+                      int T, int L, const void* ops_host, int nops, const void* mats_host, int nmat,
+                      int nslots, int write0, uint64_t base_hi, double scale, double* out_dev,
+                      void* work, size_t work_bytes, void* stream);
+
 /* One reverse-sweep step of adjoint differentiation on vecs = [1 + n_bras][2^n] (row 0 = ket):
  *   z_b = <bra_b| G |ket>,  ket <- A ket,  bra_b <- A bra_b      (A = U^dagger, k <= 3)
  * out_dev[b] = -Im z_b  (= Re <bra_b| i G |ket>, the Jacobian entry when bras carry the factor

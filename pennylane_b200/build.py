@@ -14,7 +14,7 @@ CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(CSRC, "libb200q.so")
 SOURCES = ["api.cu"]
 HEADERS = ["common.cuh", "gates.cuh", "measure.cuh", "sample.cuh", "adjoint.cuh", "tile.cuh",
-           "program.cuh", os.path.join("..", "..", "include", "b200q.h")]
+           "rtile.cuh", os.path.join("..", "..", "include", "b200q.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -49,12 +49,18 @@ class Prim:
     ctrl: dict = field(default_factory=dict)         # bit -> required value (may be outside)
     other: list = field(default_factory=list)        # parity / diagonal-table bits (may be outside)
     mat: np.ndarray | None = None                    # dense matrix / (p0, p1) / table
+    mat0: np.ndarray | None = None                   # DENSE1: matrix where the control FAILS
+                                                     # (None: identity, i.e. a plain controlled gate)
     ngates: int = 1
     op: object = None                                # GENERIC: the original operator
+    slot: int = 0                                    # GEN: output slot (trainable-parameter index)
+    ny: int = 0                                      # GEN: number of Y factors
+    coef: float = 0.0                                # GEN: real coefficient of the Pauli term
+    zbits: list = field(default_factory=list)        # GEN: bits carrying Z or Y
 
     @property
     def bits(self):
-        return set(self.targets) | set(self.ctrl) | set(self.other)
+        return set(self.targets) | set(self.ctrl) | set(self.other) | set(self.zbits)
 
 
 _X = np.array([[0, 1], [1, 0]], dtype=complex)
@@ -182,41 +188,77 @@ def _embed(m1, pos):
 
 
 def merge_blocks(prims: list[Prim], level: int = 1) -> list[Prim]:
-    """level 0: nothing; 1: products of single-qubit runs; 2: also absorb single-qubit blocks
-    into adjacent dense two-qubit gates and merge consecutive dense gates on the same pair."""
+    """level 0: nothing; 1: products of single-qubit runs, with singly-controlled X gates on
+    the same target folded in as *controlled-select* blocks (``mat`` where the control holds,
+    ``mat0`` where it does not: CNOT next to a single-qubit block costs no extra pass and no
+    data movement); 2: also absorb single-qubit blocks into adjacent dense two-qubit gates and
+    merge consecutive dense gates on the same pair."""
     if level <= 0:
         return list(prims)
     out: list[Prim] = []
-    pending: dict[int, Prim] = {}            # bit -> accumulated 1q block (not yet emitted)
+    pending: dict[int, Prim] = {}            # target bit -> accumulated block (not yet emitted)
 
     def flush(bits):
-        for b in sorted(bits):
-            if b in pending:
+        """Emit every pending block that shares a bit (target or control) with ``bits``."""
+        bits = set(bits)
+        for b in sorted(pending):
+            if pending[b].bits & bits:
                 out.append(pending.pop(b))
 
+    def flush_controlled_by(b):
+        for t in sorted(pending):
+            if b in pending[t].ctrl:
+                out.append(pending.pop(t))
+
     for p in prims:
-        one = _as_1q_matrix(p) if p.kind != GENERIC else None
+        one = _as_1q_matrix(p) if p.kind not in (GENERIC, GEN) else None
         if one is not None:
             b, m = one
+            flush_controlled_by(b)               # blocks that read b as a control come first
             if b in pending:
                 q = pending[b]
                 q.mat = np.asarray(m) @ q.mat
+                if q.mat0 is not None:
+                    q.mat0 = np.asarray(m) @ q.mat0
                 q.ngates += p.ngates
             else:
                 pending[b] = Prim(DENSE1, targets=[b], mat=np.asarray(m, dtype=complex),
                                   ngates=p.ngates)
             continue
+        if p.kind == CX and len(p.ctrl) == 1:
+            t = p.targets[0]
+            (c, v), = p.ctrl.items()
+            flush_controlled_by(t)               # they read t before it is flipped
+            if c in pending:
+                out.append(pending.pop(c))       # the control's own block acts first
+            q = pending.get(t)
+            if q is not None and q.ctrl and q.ctrl != {c: v}:
+                out.append(pending.pop(t))
+                q = None
+            if q is None:
+                pending[t] = Prim(DENSE1, targets=[t], ctrl={c: v}, mat=_X.copy(),
+                                  mat0=np.eye(2, dtype=complex), ngates=p.ngates)
+            else:
+                if not q.ctrl:
+                    q.ctrl = {c: v}
+                    q.mat0 = q.mat
+                q.mat = _X @ q.mat
+                q.ngates += p.ngates
+            continue
         if level >= 2 and p.kind == DENSE2 and not p.ctrl:
-            # absorb pending single-qubit blocks that precede this gate on its two bits
+            # absorb pending (uncontrolled) single-qubit blocks that precede this gate
+            for b in p.targets:
+                flush_controlled_by(b)
             m = p.mat
             for pos, b in enumerate(p.targets):
-                if b in pending:
+                if b in pending and not pending[b].ctrl:
                     q = pending.pop(b)
                     m = m @ _embed(q.mat, pos)
                     p.ngates += q.ngates
             p.mat = m
             # merge with an immediately preceding dense gate on the same ordered pair
-            if out and out[-1].kind == DENSE2 and not out[-1].ctrl and out[-1].targets == p.targets:
+            if (out and out[-1].kind == DENSE2 and not out[-1].ctrl and out[-1].targets == p.targets
+                    and not any(q.bits & p.bits for q in pending.values())):
                 out[-1].mat = p.mat @ out[-1].mat
                 out[-1].ngates += p.ngates
             else:
@@ -224,9 +266,11 @@ def merge_blocks(prims: list[Prim], level: int = 1) -> list[Prim]:
                 out.append(p)
             continue
         flush(p.bits)
+        if not p.bits:
+            flush(list(pending))                 # global phases keep their place trivially
         out.append(p)
-    flush(list(pending))
-    # normalise accumulated 1q blocks (a product may have become diagonal / X / identity)
+    flush([b for q in pending.values() for b in q.bits])
+    # normalise accumulated blocks (a product may have become diagonal / X / identity)
     norm = []
     for p in out:
         if p.kind == DENSE1 and not p.ctrl:
@@ -235,6 +279,11 @@ def merge_blocks(prims: list[Prim], level: int = 1) -> list[Prim]:
             if q.kind == DIAG and np.allclose(q.mat, 1.0):
                 q = Prim(PARITY, mat=np.array([1.0 + 0j, 1.0 + 0j]), ngates=p.ngates)
             norm.append(q)
+        elif p.kind == DENSE1 and p.mat0 is not None and np.array_equal(p.mat0, np.eye(2)):
+            p.mat0 = None                        # plain controlled gate: skip where control fails
+            if np.array_equal(p.mat, _X):
+                p = Prim(CX, targets=p.targets, ctrl=p.ctrl, ngates=p.ngates)
+            norm.append(p)
         else:
             norm.append(p)
     return norm
@@ -291,7 +340,8 @@ def pack_segments(prims: list[Prim], n: int, T: int = 12, L: int = 5, max_ops: i
                 keep.append(p)
                 continue
             need = {b for b in p.targets if b >= L and b not in hi}
-            msize = 0 if p.mat is None else int(np.size(p.mat))
+            msize = (0 if p.mat is None else int(np.size(p.mat))) + \
+                (0 if p.mat0 is None else int(np.size(p.mat0)))
             if len(hi) + len(need) <= free and nmat + msize <= max_mat:
                 hi |= need
                 nmat += msize
@@ -321,12 +371,27 @@ def compile_ops(ops_, n: int, bit_of=None, level: int = 1, T: int = 12, L: int =
     return pack_segments(prims, n, T=T, L=L)
 
 
+def _expand_select(prims):
+    """Controlled-select block -> two controlled records (the shared-memory kernel has no
+    select): ``mat`` on control == v, ``mat0`` on control == not v."""
+    out = []
+    for p in prims:
+        if p.kind == DENSE1 and p.mat0 is not None:
+            (c, v), = p.ctrl.items()
+            out.append(Prim(DENSE1, targets=p.targets, ctrl={c: v}, mat=p.mat, ngates=p.ngates))
+            out.append(Prim(DENSE1, targets=p.targets, ctrl={c: 1 - v}, mat=p.mat0, ngates=0))
+        else:
+            out.append(p)
+    return out
+
+
 def encode_segment(seg: Segment):
-    """Segment -> (ctypes TileOp array, complex128 matrix table)."""
+    """Segment -> (ctypes TileOp array, complex128 matrix table) for ``b200q_apply_tile``."""
     pos = {b: i for i, b in enumerate(seg.tile_bits)}
-    ops_arr = (TileOp * len(seg.prims))()
+    prims = _expand_select(seg.prims)
+    ops_arr = (TileOp * len(prims))()
     mats: list[complex] = []
-    for i, p in enumerate(seg.prims):
+    for i, p in enumerate(prims):
         o = ops_arr[i]
         o.kind = p.kind
         cml = cvl = cme = cve = 0
@@ -365,3 +430,242 @@ def encode_segment(seg: Segment):
             mats.append(0j)
     table = np.ascontiguousarray(np.array(mats if mats else [0j, 0j], dtype=np.complex128))
     return ops_arr, table
+
+
+# ---------------------------------------------------------------------------------------------
+# register-tiled kernel (rtile.cuh): round scheduling + record encoding
+# ---------------------------------------------------------------------------------------------
+RT_ROUND, RT_GEN = 6, 7
+GEN = 7            # Prim kind: generator Pauli term of a trainable gate (adjoint sweeps)
+_IO_LANES = 5      # tile positions 0..4 stay on the lanes in the first / last round
+
+
+class _RtGate(C.Structure):
+    _fields_ = [("ctrl_r", C.c_uint32), ("cval_r", C.c_uint32), ("ctrl_t", C.c_uint32),
+                ("cval_t", C.c_uint32), ("ctrl_e", C.c_uint64), ("cval_e", C.c_uint64),
+                ("par_r", C.c_uint32), ("par_t", C.c_uint32), ("par_e", C.c_uint64)]
+
+
+class _RtDiag(C.Structure):
+    _fields_ = [("src", C.c_int8 * 16), ("pad", C.c_int32 * 8)]
+
+
+class _RtRound(C.Structure):
+    _fields_ = [("rbits", C.c_int8 * 8), ("tbits", C.c_int8 * 16), ("pad", C.c_int32 * 6)]
+
+
+class _RtGen(C.Structure):
+    _fields_ = [("xr", C.c_uint32), ("zr", C.c_uint32), ("zt", C.c_uint32), ("pad", C.c_uint32),
+                ("ze", C.c_uint64), ("coef", C.c_double), ("pad2", C.c_int32 * 4)]
+
+
+class _RtU(C.Union):
+    _fields_ = [("g", _RtGate), ("d", _RtDiag), ("r", _RtRound), ("p", _RtGen)]
+
+
+class RtOp(C.Structure):
+    """Mirror of ``struct RtOp`` (pennylane_b200/csrc/rtile.cuh)."""
+    _fields_ = [("kind", C.c_int32), ("q0", C.c_int32), ("q1", C.c_int32), ("mat_off", C.c_int32),
+                ("u", _RtU)]
+
+
+assert C.sizeof(RtOp) == 64
+
+
+@dataclass
+class Round:
+    rpos: list                 # tile positions held by register bits 0..RB-1
+    tpos: list                 # tile positions held by thread bits 0..TB-1
+    prims: list = field(default_factory=list)
+
+
+def _expand_swaps(prims):
+    """SWAP(a, b) = CX(a<-b) CX(b<-a) CX(a<-b): the register kernel has no swap record."""
+    out = []
+    for p in prims:
+        if p.kind == SWAP:
+            a, b = p.targets
+            for t, c in ((a, b), (b, a), (a, b)):
+                ctrl = dict(p.ctrl)
+                ctrl[c] = 1
+                out.append(Prim(CX, targets=[t], ctrl=ctrl, ngates=0))
+            out[-1].ngates = p.ngates
+        else:
+            out.append(p)
+    return out
+
+
+def _thread_positions(free, sww, io):
+    """Order the non-register tile positions over the thread bits.  IO rounds keep positions
+    0..4 on the lanes (coalesced global access); inner rounds put positions that are distinct
+    modulo the swizzle width on the lowest lane bits (conflict-free shared-memory phases)."""
+    free = sorted(free)
+    if io:
+        return free
+    chosen, seen = [], set()
+    for p in free:
+        if p % sww not in seen:
+            chosen.append(p)
+            seen.add(p % sww)
+        if len(chosen) == sww:
+            break
+    rest = [p for p in free if p not in chosen]
+    return chosen + rest
+
+
+def schedule_rounds(prims, tile_bits, RB: int, sww: int = 3):
+    """Assign the primitives of one segment to rounds.  Returns a list of :class:`Round`.
+
+    A primitive can run in a round when all its targets are register bits of that round and no
+    earlier unscheduled primitive shares a bit with it.  The first and last rounds are "IO
+    rounds": their register bits avoid tile positions 0..4, which stay on the lanes."""
+    T = len(tile_bits)
+    pos = {b: i for i, b in enumerate(tile_bits)}
+    lanes = min(_IO_LANES, T - RB)
+    io_allowed = set(range(lanes, T))
+    remaining = _expand_swaps(prims)
+    rounds: list[Round] = []
+
+    def greedy(allowed, rem):
+        R, run, keep, blocked = [], [], [], set()
+        for p in rem:
+            pb = p.bits
+            tp = [pos[b] for b in p.targets]
+            if blocked & pb:
+                blocked |= pb
+                keep.append(p)
+                continue
+            need = [t for t in tp if t not in R]
+            if all(t in allowed for t in tp) and len(R) + len(need) <= RB:
+                R += need
+                run.append(p)
+            else:
+                blocked |= pb
+                keep.append(p)
+        return R, run, keep
+
+    def finish(R, io):
+        pool = [p for p in (sorted(io_allowed, reverse=True) if io else range(T - 1, -1, -1))
+                if p not in R]
+        R = list(R) + pool[: RB - len(R)]
+        free = [p for p in range(T) if p not in R]
+        return R, _thread_positions(free, sww, io)
+
+    first = True
+    while remaining or first:
+        if first:
+            R, run, keep = greedy(io_allowed, remaining)
+            io = True
+        else:
+            # prefer a round that is IO-compatible when it finishes the segment
+            R, run, keep = greedy(io_allowed, remaining)
+            io = True
+            if keep:
+                R, run, keep = greedy(set(range(T)), remaining)
+                io = all(r in io_allowed for r in R)
+        if not run and not first:
+            raise RuntimeError("round scheduling made no progress")   # pragma: no cover
+        R, tpos = finish(R, io)
+        rounds.append(Round(R, tpos, run))
+        remaining = keep
+        first = False
+    last = rounds[-1]
+    if any(r not in io_allowed for r in last.rpos) or last.tpos[:lanes] != list(range(lanes)):
+        R, tpos = finish([], True)
+        rounds.append(Round(R, tpos, []))
+    return rounds
+
+
+def _swap_2q(m):
+    """4x4 matrix with the roles of its two index bits exchanged."""
+    perm = [0, 2, 1, 3]
+    return np.asarray(m)[np.ix_(perm, perm)]
+
+
+def encode_rt_segment(seg: Segment, RB: int, sww: int = 3, rounds=None):
+    """Segment -> (ctypes RtOp array, complex128 table, n_records).  ``rounds`` can be passed
+    when the caller already scheduled them."""
+    tile_bits = seg.tile_bits
+    pos = {b: i for i, b in enumerate(tile_bits)}
+    if rounds is None:
+        rounds = schedule_rounds(seg.prims, tile_bits, RB, sww)
+    nrec = sum(1 + len(r.prims) for r in rounds)
+    ops_arr = (RtOp * nrec)()
+    mats: list[complex] = []
+    i = 0
+    for rnd in rounds:
+        o = ops_arr[i]; i += 1
+        o.kind = RT_ROUND
+        for b, p in enumerate(rnd.rpos):
+            o.u.r.rbits[b] = p
+        for b, p in enumerate(rnd.tpos):
+            o.u.r.tbits[b] = p
+        rbit = {p: b for b, p in enumerate(rnd.rpos)}
+        tbit = {p: b for b, p in enumerate(rnd.tpos)}
+
+        def split_mask(bits_vals):
+            """{global bit: value} -> (mask_r, val_r, mask_t, val_t, mask_e, val_e)."""
+            mr = vr = mt = vt = me = ve = 0
+            for b, v in bits_vals.items():
+                if b in pos:
+                    p = pos[b]
+                    if p in rbit:
+                        mr |= 1 << rbit[p]; vr |= (1 << rbit[p]) if v else 0
+                    else:
+                        mt |= 1 << tbit[p]; vt |= (1 << tbit[p]) if v else 0
+                else:
+                    me |= 1 << b; ve |= (1 << b) if v else 0
+            return mr, vr, mt, vt, me, ve
+
+        for p in rnd.prims:
+            o = ops_arr[i]; i += 1
+            o.mat_off = len(mats)
+            if p.kind == GEN:
+                o.kind = RT_GEN
+                o.q0 = int(p.slot)
+                o.q1 = int(p.ny) & 3
+                xr = 0
+                for b in p.targets:
+                    xr |= 1 << rbit[pos[b]]
+                zr, _, zt, _, ze, _ = split_mask({b: 1 for b in p.zbits})
+                o.u.p.xr, o.u.p.zr, o.u.p.zt, o.u.p.ze = xr, zr, zt, ze
+                o.u.p.coef = float(p.coef)
+                continue
+            if p.kind == DIAG:
+                o.kind = DIAG
+                o.q0 = len(p.other)
+                for j, b in enumerate(p.other):
+                    if b in pos:
+                        pp = pos[b]
+                        o.u.d.src[j] = rbit[pp] if pp in rbit else 32 + tbit[pp]
+                    else:
+                        o.u.d.src[j] = 64 + b
+                mats.extend(np.asarray(p.mat, dtype=complex).reshape(-1))
+            else:
+                o.kind = p.kind
+                g = o.u.g
+                g.ctrl_r, g.cval_r, g.ctrl_t, g.cval_t, g.ctrl_e, g.cval_e = split_mask(p.ctrl)
+                if p.kind == DENSE1:
+                    o.q0 = rbit[pos[p.targets[0]]]
+                    mats.extend(np.asarray(p.mat, dtype=complex).reshape(-1))
+                    if p.mat0 is not None:
+                        o.kind = DENSE1 | 0x100
+                        mats.extend(np.asarray(p.mat0, dtype=complex).reshape(-1))
+                elif p.kind == DENSE2:
+                    q0, q1 = rbit[pos[p.targets[0]]], rbit[pos[p.targets[1]]]
+                    m = np.asarray(p.mat, dtype=complex)
+                    if q0 < q1:
+                        q0, q1, m = q1, q0, _swap_2q(m)
+                    o.q0, o.q1 = q0, q1
+                    mats.extend(m.reshape(-1))
+                elif p.kind == CX:
+                    o.q0 = rbit[pos[p.targets[0]]]
+                elif p.kind == PARITY:
+                    g.par_r, _, g.par_t, _, g.par_e, _ = split_mask({b: 1 for b in p.other})
+                    mats.extend(np.asarray(p.mat, dtype=complex).reshape(-1)[:2])
+                else:  # pragma: no cover
+                    raise ValueError(f"primitive kind {p.kind} has no register-kernel record")
+            if len(mats) % 2:
+                mats.append(0j)
+    table = np.ascontiguousarray(np.array(mats if mats else [0j, 0j], dtype=np.complex128))
+    return ops_arr, table, nrec

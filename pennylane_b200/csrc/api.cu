@@ -1,5 +1,6 @@
 // b200q — extern "C" entry points (see include/b200q.h for the contract of each function).
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <vector>
@@ -11,6 +12,7 @@
 #include "measure.cuh"
 #include "sample.cuh"
 #include "tile.cuh"
+#include "rtile.cuh"
 
 namespace b200q {
 
@@ -474,6 +476,112 @@ static int tile_t(void* state, int n, int64_t batch, const int* tile_bits, int T
   return 0;
 }
 
+// geometry of the register-tiled kernel: (dtype, nvec) -> (T, RB, THREADS)
+static void rtile_geom(int dtype, int nvec, int& T, int& RB, int& threads) {
+  if (nvec <= 1) { threads = 256; RB = dtype == B200Q_C128 ? 4 : 5; }
+  else { threads = 512; RB = dtype == B200Q_C128 ? 3 : 4; }
+  T = (threads == 256 ? 8 : 9) + RB;
+}
+
+template <typename T, int RB, int NV, int THREADS, int MINB>
+static int rtile_launch(void* v0, void* v1, const RtArgs& a, int64_t batch, const RtOp* ops_dev,
+                        const double2* mats_dev, int nslots, double scale, double* out_dev,
+                        double* partials, size_t partial_cap, cudaStream_t s) {
+  const size_t smem = ((size_t)NV * sizeof(cx<T>) << a.T) + sizeof(cx<T>) * ((a.nmat + 1) & ~1) +
+                      (size_t)a.nops * sizeof(RtOp) + (size_t)((2 << RB) + 2 * THREADS) * sizeof(unsigned long long) +
+                      (size_t)nslots * (THREADS / 32) * sizeof(double);
+  B200Q_REQUIRE(smem <= 227 * 1024, "rtile: %zu bytes of shared memory needed (%d ops, %d slots)",
+                smem, a.nops, nslots);
+  static bool attr_set = false;
+  if (!attr_set) {
+    B200Q_CHECK(cudaFuncSetAttribute(k_rtile<T, RB, NV, THREADS, MINB>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  uint64_t per_sm = std::max<uint64_t>(1, std::min<uint64_t>(MINB, (227 * 1024) / smem));
+  if (const char* e = getenv("B200Q_RT_CTAS")) per_sm = std::max(1, atoi(e));   // tuning knob
+  const uint64_t cap = (uint64_t)sm_count() * per_sm;
+  dim3 grid((unsigned)std::min<uint64_t>(a.ntiles, cap), (unsigned)batch);
+  if (nslots > 0)
+    B200Q_REQUIRE((size_t)batch * nslots * grid.x <= partial_cap, "rtile: workspace too small for %d slots",
+                  nslots);
+  k_rtile<T, RB, NV, THREADS, MINB><<<grid, THREADS, smem, s>>>(a, (cx<T>*)v0, (cx<T>*)v1, ops_dev,
+                                                                 mats_dev, 0, partials);
+  B200Q_LAUNCH_CHECK();
+  if (nslots > 0) {
+    k_final_reduce<<<(unsigned)(batch * nslots), 256, 0, s>>>(partials, out_dev, (int)grid.x, 1,
+                                                                (int)(batch * nslots), scale);
+    B200Q_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+static int rtile_dispatch(void* v0, void* v1, int n, int dtype, int64_t batch, const int* tile_bits,
+                          int Tn, int L, const RtOp* ops_host, int nops, const double2* mats_host,
+                          int nmat, int nslots, int write0, uint64_t base_hi, double scale,
+                          double* out_dev, void* work, size_t work_bytes, cudaStream_t s) {
+  int gT, gRB, gTh;
+  rtile_geom(dtype, v1 ? 2 : 1, gT, gRB, gTh);
+  B200Q_REQUIRE(Tn == gT && Tn <= n && L >= 0 && L <= Tn, "rtile: T=%d (need %d) L=%d n=%d", Tn, gT, L, n);
+  B200Q_REQUIRE(nops >= 1 && nops <= 2048 && nmat >= 0 && nslots >= 0, "rtile: bad nops=%d nmat=%d", nops, nmat);
+  B200Q_REQUIRE(ops_host[0].kind == RT_ROUND, "rtile: the first record must be a round");
+  B200Q_REQUIRE(nslots == 0 || (v1 && out_dev), "rtile: generator slots need a bra and an output");
+  RtArgs a;
+  memset(&a, 0, sizeof(a));
+  a.n = n; a.T = Tn; a.L = L; a.nops = nops; a.nmat = nmat; a.nslots = nslots; a.write0 = write0;
+  a.base_hi = base_hi;
+  {
+    static int pf = -1;                      // tuning knob, read once
+    if (pf < 0) { const char* e = getenv("B200Q_RT_PREFETCH"); pf = e ? atoi(e) : 0; }
+    a.prefetch = pf;
+  }
+  for (int i = 0; i < nops; ++i) {
+    if (ops_host[i].kind == RT_ROUND) {
+      a.last_round = i;
+      uint32_t seen = 0;
+      const int tb = Tn - gRB;
+      for (int b = 0; b < gRB; ++b) seen |= 1u << ops_host[i].u.r.rbits[b];
+      for (int b = 0; b < tb; ++b) seen |= 1u << ops_host[i].u.r.tbits[b];
+      B200Q_REQUIRE(seen == (1u << Tn) - 1u, "rtile: round %d is not a permutation of the tile bits", i);
+    }
+  }
+  uint64_t inmask = 0;
+  for (int i = 0; i < Tn; ++i) {
+    const int b = tile_bits[i];
+    B200Q_REQUIRE(b >= 0 && b < n && !((inmask >> b) & 1), "rtile: bad tile bit %d", b);
+    B200Q_REQUIRE(i < L ? b == i : (i == 0 || b > tile_bits[i - 1]),
+                  "rtile: bits must be ascending with the first L equal to 0..L-1");
+    inmask |= 1ull << b;
+    if (i >= L) a.hi_bits[i - L] = (int8_t)b;
+  }
+  int no = 0;
+  for (int b = 0; b < n; ++b)
+    if (!((inmask >> b) & 1)) a.out_bits[no++] = (int8_t)b;
+  a.ntiles = 1ull << (n - Tn);
+  const size_t ops_bytes = (size_t)nops * sizeof(RtOp);
+  const size_t mat_bytes = (size_t)nmat * sizeof(double2);
+  B200Q_REQUIRE(work && ops_bytes + mat_bytes + 512 <= kTermRegion && work_bytes >= kWorkBytes,
+                "rtile: segment tables too large for the workspace");
+  char* w = (char*)work;
+  B200Q_CHECK(cudaMemcpyAsync(w, ops_host, ops_bytes, cudaMemcpyHostToDevice, s));
+  const size_t moff = (ops_bytes + 255) & ~(size_t)255;
+  if (nmat) B200Q_CHECK(cudaMemcpyAsync(w + moff, mats_host, mat_bytes, cudaMemcpyHostToDevice, s));
+  double* partials = (double*)(w + kTermRegion);
+  const size_t pcap = (work_bytes - kTermRegion) / sizeof(double);
+  const RtOp* od = (const RtOp*)w;
+  const double2* md = (const double2*)(w + moff);
+  if (dtype == B200Q_C128) {
+    if (!v1) return rtile_launch<double, 4, 1, 256, 2>(v0, v1, a, batch, od, md, nslots, scale, out_dev, partials, pcap, s);
+    return rtile_launch<double, 3, 2, 512, 1>(v0, v1, a, batch, od, md, nslots, scale, out_dev, partials, pcap, s);
+  }
+  if (dtype == B200Q_C64) {
+    if (!v1) return rtile_launch<float, 5, 1, 256, 2>(v0, v1, a, batch, od, md, nslots, scale, out_dev, partials, pcap, s);
+    return rtile_launch<float, 4, 2, 512, 1>(v0, v1, a, batch, od, md, nslots, scale, out_dev, partials, pcap, s);
+  }
+  set_error("unknown dtype %d", dtype);
+  return 2;
+}
+
 }  // namespace b200q
 
 using namespace b200q;
@@ -691,6 +799,25 @@ int b200q_apply_tile(void* state, int n, int dtype, int64_t batch, const int* ti
                          (const double2*)mats_host, nmat, work, work_bytes, s),
            tile_t<double>(state, n, batch, tile_bits, T, L, (const TileOp*)ops_host, nops,
                           (const double2*)mats_host, nmat, work, work_bytes, s));
+}
+
+int b200q_rtile_geometry(int dtype, int nvec, int* T_out, int* RB_out, int* threads_out) {
+  B200Q_REQUIRE(dtype == B200Q_C64 || dtype == B200Q_C128, "rtile_geometry: unknown dtype %d", dtype);
+  int T, RB, th;
+  rtile_geom(dtype, nvec, T, RB, th);
+  if (T_out) *T_out = T;
+  if (RB_out) *RB_out = RB;
+  if (threads_out) *threads_out = th;
+  return 0;
+}
+
+int b200q_apply_rtile(void* vec0, void* vec1, int n, int dtype, int64_t batch, const int* tile_bits,
+                      int T, int L, const void* ops_host, int nops, const void* mats_host, int nmat,
+                      int nslots, int write0, uint64_t base_hi, double scale, double* out_dev,
+                      void* work, size_t work_bytes, void* stream) {
+  return rtile_dispatch(vec0, vec1, n, dtype, batch, tile_bits, T, L, (const RtOp*)ops_host, nops,
+                        (const double2*)mats_host, nmat, nslots, write0, base_hi, scale, out_dev,
+                        work, work_bytes, (cudaStream_t)stream);
 }
 
 int b200q_adjoint_step(void* vecs, int n, int dtype, int n_bras, const int* tgt_bits, int k,

@@ -1,0 +1,509 @@
+// b200q — register-tiled fused segment kernel (K5 + K8 of SURVEY.md section 2c).
+//
+// One launch = ONE read and ONE write of the state (forward), or of the ket and one bra
+// (adjoint reverse sweep), applying a whole *segment* of gates.  A CTA owns a tile of 2^T
+// amplitudes (T = log2(THREADS) + RB tile positions: the L lowest index bits plus T-L
+// arbitrary higher bits chosen by the host).  Unlike k_tile (tile.cuh), which makes one
+// shared-memory pass per gate and is therefore bound by the 128 B/clk shared-memory crossbar
+// (measured: 18 % of HBM peak on the 30-qubit ansatz), here every thread keeps 2^RB
+// amplitudes in REGISTERS.  The segment is a sequence of *rounds*; a round names the RB tile
+// positions that are held in registers ("register bits"); every gate whose targets are
+// register bits is applied with no memory traffic at all (controls / parity bits may sit on
+// thread bits or outside the tile — they are predicates, not data).  Between rounds the tile
+// is transposed through an XOR-swizzled shared-memory buffer (one conflict-free store + load
+// of the tile), so the shared-memory traffic per tile is 2 * (rounds-1) tile copies instead
+// of 2 per gate.  The first round loads straight from global memory and the last stores
+// straight back; the host makes those two rounds keep tile positions 0..4 on the lanes so
+// every warp access covers whole 128-byte lines.  The next tile of the CTA's grid-stride loop
+// is prefetched into L2 while the current one is being computed.
+//
+// Adjoint mode (NV = 2): vector 0 is the ket, vector 1 a bra; gates are applied to both, and
+// RT_GEN records accumulate coef * Im <bra| P |ket> for a Pauli term P of the generator of a
+// trainable gate (adjoint_jacobian.py:121-137 fused: no ket_temp, no separate inner-product
+// sweep).  Sums are kept per (slot, warp) in shared memory and reduced in a fixed order.
+//
+// Reference analogue: none (default.qubit sweeps the state once per gate,
+// simulate.py:214-235).  Algorithmic bytes per launch: 2*S*NV.
+#pragma once
+#include "common.cuh"
+
+namespace b200q {
+
+enum RtKind : int {
+  RT_DENSE1 = 0,   // 2x2 on register bit q0
+  RT_DENSE2 = 1,   // 4x4 on register bits q0 (matrix MSB) > q1 (matrix LSB)
+  RT_CX = 2,       // X on register bit q0
+  RT_PARITY = 3,   // amp *= parity ? mat[1] : mat[0]
+  RT_DIAG = 4,     // amp *= tab[idx]
+  RT_ROUND = 6,    // new register/thread bit assignment (first op of every program)
+  RT_GEN = 7,      // adjoint: acc[slot] += coef * Im <bra| P |ket>
+};
+
+struct RtGate {     // DENSE1 / DENSE2 / CX / PARITY
+  unsigned ctrl_r, cval_r;                 // controls on register bits
+  unsigned ctrl_t, cval_t;                 // controls on thread bits
+  unsigned long long ctrl_e, cval_e;       // controls outside the tile (global bit positions)
+  unsigned par_r, par_t;                   // PARITY: register / thread bits in the parity
+  unsigned long long par_e;                // PARITY: bits outside the tile
+};
+struct RtDiag {     // table index bit b (MSB first): src < 32 register bit, < 64 thread bit
+  signed char src[16];                     // (src-32), else external global bit (src-64)
+  int pad[8];
+};
+struct RtRound {
+  signed char rbits[8];                    // tile position held by register bit b
+  signed char tbits[16];                   // tile position held by thread bit b
+  int pad[6];
+};
+struct RtGen {      // Pauli term: x part on register bits only
+  unsigned xr, zr, zt, pad;
+  unsigned long long ze;
+  double coef;
+  int pad2[4];
+};
+struct __align__(16) RtOp {
+  int kind;
+  int q0, q1;       // DIAG: q0 = number of index bits.  GEN: q0 = slot, q1 = number of Y factors
+  int mat_off;
+  union {
+    RtGate g;
+    RtDiag d;
+    RtRound r;
+    RtGen p;
+  } u;
+};
+static_assert(sizeof(RtOp) == 64, "RtOp must be 64 bytes (mirrored by ctypes in compiler.py)");
+
+struct RtArgs {
+  int n, T, L, nops, nmat, nslots;
+  int write0;                    // write vector 0 back (adjoint passes over several bras)
+  int last_round;                // index of the last RT_ROUND record
+  int prefetch;                  // issue L2 prefetches for the CTA's next tile
+  int8_t hi_bits[16];            // global positions of tile positions L..T-1 (ascending)
+  int8_t out_bits[B200Q_MAX_BITS];   // ascending global positions of the n-T non-tile bits
+  unsigned long long ntiles;     // 2^(n-T)
+  unsigned long long base_hi;    // OR-ed into the tile base for "external" predicates
+                                 // (the rank's global-qubit bits when the state is sharded)
+};
+
+template <int W> __device__ __forceinline__ unsigned rt_sw(unsigned j) {
+  unsigned s = 0;
+#pragma unroll
+  for (int sh = W; sh < 16; sh += W) s ^= (j >> sh);
+  return s & ((1u << W) - 1u);
+}
+
+__device__ __forceinline__ unsigned long long rt_gscatter(unsigned j, const RtArgs& a) {
+  unsigned long long off = j & ((1u << a.L) - 1u);
+  const unsigned hi = j >> a.L;
+  for (int b = 0; b < a.T - a.L; ++b) off |= (unsigned long long)((hi >> b) & 1u) << a.hi_bits[b];
+  return off;
+}
+
+template <typename T_, int RB, int NV, int THREADS>
+struct RtKernel {
+  static constexpr int NA = 1 << RB;
+  static constexpr int TB = (THREADS == 128) ? 7 : (THREADS == 256) ? 8 : (THREADS == 512) ? 9 : 10;
+  static constexpr int SWW = (sizeof(T_) == 8) ? 3 : 4;    // swizzle width: 16-byte / 8-byte elements
+  static constexpr int NW = THREADS / 32;
+  using C = cx<T_>;
+
+  // XOR of the per-register-bit constants selected by k (k is a compile-time constant at
+  // every call site after unrolling)
+  template <typename V> static __device__ __forceinline__ V sel_xor(const V (&c)[RB], int k) {
+    V r = 0;
+#pragma unroll
+    for (int b = 0; b < RB; ++b)
+      if ((k >> b) & 1) r ^= c[b];
+    return r;
+  }
+
+  // In-place complex mat-vec on D amplitudes of one vector.  Every output component is formed
+  // as (partial sum over the OTHER inputs) and then ONE final FMA that reads the input it
+  // overwrites:  x_r.re <- m_rr.re * x_r.re + t.  The result is born in the register it lives
+  // in, so no register moves are needed at the control-flow merges of the record interpreter
+  // (the naive "y = M x; x = y" form costs one MOV per FMA, measured with ncu: 47 % of all
+  // issued instructions).
+  template <int D>
+  static __device__ __forceinline__ void matvec_inplace(C (&A)[NA], const int (&ix)[D],
+                                                        const C* __restrict__ m) {
+    T_ tx[D], ty[D];
+#pragma unroll
+    for (int r = 0; r < D; ++r) {
+      const C mrr = m[r * D + r];
+      tx[r] = -mrr.y * A[ix[r]].y;
+      ty[r] = mrr.y * A[ix[r]].x;
+#pragma unroll
+      for (int c = 0; c < D; ++c) {
+        if (c == r) continue;
+        const C mrc = m[r * D + c];
+        tx[r] = fma(mrc.x, A[ix[c]].x, tx[r]);
+        tx[r] = fma(-mrc.y, A[ix[c]].y, tx[r]);
+        ty[r] = fma(mrc.y, A[ix[c]].x, ty[r]);
+        ty[r] = fma(mrc.x, A[ix[c]].y, ty[r]);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < D; ++r) {
+      const T_ d = m[r * D + r].x;
+      A[ix[r]].x = fma(d, A[ix[r]].x, tx[r]);
+      A[ix[r]].y = fma(d, A[ix[r]].y, ty[r]);
+    }
+  }
+
+  // Controlled-select dense gates.  For every group of amplitudes the matrix is chosen by the
+  // control predicate: `m` (controls satisfied) or `m + D*D` (controls not satisfied; only when
+  // HAS0, otherwise the group is left untouched).  A CNOT next to a single-qubit block on its
+  // target is folded by the host into ONE such record (M1 = X*U or U*X, M0 = U), so the ansatz'
+  // CNOT ring costs no data movement at all.  `tsel` is the thread/external part of the
+  // predicate; (cr, cv) the register-bit part, uniform over the warp.  The matrix is re-read
+  // from shared memory (broadcast) per group: 64 data registers leave no room to pin it.
+  template <int Q, bool HAS0>
+  static __device__ __forceinline__ void dense1(C (&A)[NV][NA], const C* __restrict__ m,
+                                                const bool tsel, const unsigned cr,
+                                                const unsigned cv) {
+#pragma unroll
+    for (int k = 0; k < NA; ++k) {
+      if ((k >> Q) & 1) continue;
+      const bool sel = tsel && ((k & cr) == cv);
+      if (!HAS0 && !sel) continue;
+      const C* mm = (HAS0 && !sel) ? m + 4 : m;
+      const int ix[2] = {k, k | (1 << Q)};
+#pragma unroll
+      for (int v = 0; v < NV; ++v) matvec_inplace<2>(A[v], ix, mm);
+    }
+  }
+
+  template <int Q0, int Q1, bool HAS0>   // Q0 > Q1; Q0 is the matrix MSB
+  static __device__ __forceinline__ void dense2(C (&A)[NV][NA], const C* __restrict__ m,
+                                                const bool tsel, const unsigned cr,
+                                                const unsigned cv) {
+#pragma unroll
+    for (int k = 0; k < NA; ++k) {
+      if (((k >> Q0) & 1) || ((k >> Q1) & 1)) continue;
+      const bool sel = tsel && ((k & cr) == cv);
+      if (!HAS0 && !sel) continue;
+      const C* mm = (HAS0 && !sel) ? m + 16 : m;
+      const int ix[4] = {k, k | (1 << Q1), k | (1 << Q0), k | (1 << Q0) | (1 << Q1)};
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        asm volatile("" ::: "memory");     // do not hoist the 16 matrix entries out of the quads
+        matvec_inplace<4>(A[v], ix, mm);
+      }
+    }
+  }
+
+  template <int Q>
+  static __device__ __forceinline__ void cx_gate(C (&A)[NV][NA], unsigned cr, unsigned cv) {
+#pragma unroll
+    for (int k = 0; k < NA; ++k) {
+      if ((k >> Q) & 1) continue;
+      if ((k & cr) != cv) continue;
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        const C x0 = A[v][k];
+        A[v][k] = A[v][k | (1 << Q)];
+        A[v][k | (1 << Q)] = x0;
+      }
+    }
+  }
+
+  // a <- p * a, both components formed by a final FMA on the overwritten input
+  static __device__ __forceinline__ void cmul_inplace(C& a, const C p) {
+    const T_ tx = -p.y * a.y, ty = p.y * a.x;
+    a.x = fma(p.x, a.x, tx);
+    a.y = fma(p.x, a.y, ty);
+  }
+
+  // acc += sign * {Re, Im}(conj(bra_k) * ket_{k ^ XR})
+  template <int XR>
+  static __device__ __forceinline__ double gen_term(const C (&A)[NV][NA], unsigned zr,
+                                                    unsigned tpar, bool odd) {
+    double acc = 0.0;
+#pragma unroll
+    for (int k = 0; k < NA; ++k) {
+      const C b = A[NV - 1][k], x = A[0][k ^ XR];
+      const unsigned par = (__popc((unsigned)(k ^ XR) & zr) & 1u) ^ tpar;
+      double val;
+      if (odd) val = (double)b.x * (double)x.x + (double)b.y * (double)x.y;   // Re
+      else val = (double)b.x * (double)x.y - (double)b.y * (double)x.x;       // Im
+      acc += par ? -val : val;
+    }
+    return acc;
+  }
+
+  static __device__ __forceinline__ void run(const RtArgs& __restrict__ a, C* __restrict__ v0,
+                                             C* __restrict__ v1, const RtOp* __restrict__ ops_g,
+                                             const double2* __restrict__ mats_g,
+                                             const long long mat_bstride,
+                                             double* __restrict__ partials) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const unsigned tsize = 1u << a.T;
+    C* tile = reinterpret_cast<C*>(smem_raw);                                  // NV * 2^T
+    C* mats = tile + (size_t)NV * tsize;                                        // nmat (padded even)
+    RtOp* ops = reinterpret_cast<RtOp*>(mats + ((a.nmat + 1) & ~1));            // nops
+    unsigned long long* koff = reinterpret_cast<unsigned long long*>(ops + a.nops);  // 2 * NA
+    unsigned long long* toff = koff + 2 * NA;                                   // 2 * THREADS
+    double* accs = reinterpret_cast<double*>(toff + 2 * THREADS);               // nslots * NW
+    const unsigned tid = threadIdx.x;
+
+    const double2* mg = mats_g + (long long)blockIdx.y * mat_bstride;
+    for (int i = tid; i < a.nmat; i += THREADS) mats[i] = make_cx<T_>((T_)mg[i].x, (T_)mg[i].y);
+    for (int i = tid; i < a.nops; i += THREADS) ops[i] = ops_g[i];
+    for (int i = tid; i < a.nslots * NW; i += THREADS) accs[i] = 0.0;
+    __syncthreads();
+
+    C* vec[2] = {v0 + ((unsigned long long)blockIdx.y << a.n),
+                 NV > 1 ? v1 + ((unsigned long long)blockIdx.y << a.n) : nullptr};
+
+    // global offsets of the first (load) and last (store) round layouts are tile independent:
+    // the per-thread parts live in shared memory (toff), the per-register-index parts too (koff)
+    {
+      const RtOp& f = ops[0];
+      const RtOp& l = ops[a.last_round];
+      unsigned tj = 0, tl = 0;
+      for (int b = 0; b < TB; ++b) {
+        tj |= ((tid >> b) & 1u) << f.u.r.tbits[b];
+        tl |= ((tid >> b) & 1u) << l.u.r.tbits[b];
+      }
+      toff[tid] = rt_gscatter(tj, a);
+      toff[THREADS + tid] = rt_gscatter(tl, a);
+      if (tid < 2 * NA) {
+        const RtOp& r = tid < NA ? f : l;
+        const unsigned k = tid & (NA - 1);
+        unsigned j = 0;
+        for (int b = 0; b < RB; ++b) j |= ((k >> b) & 1u) << r.u.r.rbits[b];
+        koff[tid] = rt_gscatter(j, a);
+      }
+    }
+    __syncthreads();
+    // L2 prefetch granule: one 128-byte line when the contiguous run allows it
+    const unsigned line_amps = 128u / sizeof(C);
+    const unsigned pf_unit = (1u << a.L) < line_amps ? (1u << a.L) : line_amps;
+
+    for (unsigned t = blockIdx.x; t < (unsigned)a.ntiles; t += gridDim.x) {
+      unsigned long long base = 0;
+      for (int b = 0; b < a.n - a.T; ++b) base |= (unsigned long long)((t >> b) & 1u) << a.out_bits[b];
+
+      // ---- optional: prefetch the CTA's next tile into L2 --------------------------------
+      if (a.prefetch && t + gridDim.x < (unsigned)a.ntiles) {
+        const unsigned tn = t + gridDim.x;
+        unsigned long long bn = 0;
+        for (int b = 0; b < a.n - a.T; ++b) bn |= (unsigned long long)((tn >> b) & 1u) << a.out_bits[b];
+        for (unsigned u = tid * pf_unit; u < tsize; u += THREADS * pf_unit) {
+          const unsigned long long g = bn | rt_gscatter(u, a);
+#pragma unroll
+          for (int v = 0; v < NV; ++v) asm volatile("prefetch.global.L2 [%0];" ::"l"(vec[v] + g));
+        }
+      }
+
+      C A[NV][NA];
+      // ---- load (round 0 layout) ------------------------------------------------------------
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        const C* src = vec[v] + base + toff[tid];
+#pragma unroll
+        for (int k = 0; k < NA; ++k) A[v][k] = src[koff[k]];
+      }
+      int cur = 0;                     // index of the current round's record
+
+      for (int o = 1; o < a.nops; ++o) {
+        const RtOp& op = ops[o];
+        const int kind = op.kind & 0xff;
+        if (kind <= RT_CX) {
+          // ---- gates on register bits, with controls anywhere --------------------------------
+          const RtGate& g = op.u.g;
+          const bool tsel = ((tid & g.ctrl_t) == g.cval_t) &&
+                            (((base | a.base_hi) & g.ctrl_e) == g.cval_e);
+          const unsigned cr = g.ctrl_r, cv = g.cval_r;
+          const bool has0 = (op.kind >> 8) & 1;
+          const C* m = mats + op.mat_off;
+          if (kind == RT_DENSE1) {
+            if (has0) {
+              switch (op.q0) {
+                case 0: dense1<0, true>(A, m, tsel, cr, cv); break;
+                case 1: if constexpr (RB > 1) dense1<1, true>(A, m, tsel, cr, cv); break;
+                case 2: if constexpr (RB > 2) dense1<2, true>(A, m, tsel, cr, cv); break;
+                case 3: if constexpr (RB > 3) dense1<3, true>(A, m, tsel, cr, cv); break;
+                case 4: if constexpr (RB > 4) dense1<4, true>(A, m, tsel, cr, cv); break;
+                default: break;
+              }
+            } else if (tsel) {
+              switch (op.q0) {
+                case 0: dense1<0, false>(A, m, true, cr, cv); break;
+                case 1: if constexpr (RB > 1) dense1<1, false>(A, m, true, cr, cv); break;
+                case 2: if constexpr (RB > 2) dense1<2, false>(A, m, true, cr, cv); break;
+                case 3: if constexpr (RB > 3) dense1<3, false>(A, m, true, cr, cv); break;
+                case 4: if constexpr (RB > 4) dense1<4, false>(A, m, true, cr, cv); break;
+                default: break;
+              }
+            }
+          } else if (kind == RT_CX) {
+            if (tsel) {
+              switch (op.q0) {
+                case 0: cx_gate<0>(A, cr, cv); break;
+                case 1: if constexpr (RB > 1) cx_gate<1>(A, cr, cv); break;
+                case 2: if constexpr (RB > 2) cx_gate<2>(A, cr, cv); break;
+                case 3: if constexpr (RB > 3) cx_gate<3>(A, cr, cv); break;
+                case 4: if constexpr (RB > 4) cx_gate<4>(A, cr, cv); break;
+                default: break;
+              }
+            }
+          } else {   // RT_DENSE2
+            switch (op.q0 * 8 + op.q1) {
+#define RT_D2_CASE(Q0, Q1)                                                     \
+  case Q0 * 8 + Q1:                                                            \
+    if constexpr (Q0 < RB) {                                                   \
+      if (has0) dense2<Q0, Q1, true>(A, m, tsel, cr, cv);                      \
+      else if (tsel) dense2<Q0, Q1, false>(A, m, true, cr, cv);                \
+    }                                                                          \
+    break;
+              RT_D2_CASE(1, 0)
+              RT_D2_CASE(2, 0) RT_D2_CASE(2, 1)
+              RT_D2_CASE(3, 0) RT_D2_CASE(3, 1) RT_D2_CASE(3, 2)
+              RT_D2_CASE(4, 0) RT_D2_CASE(4, 1) RT_D2_CASE(4, 2) RT_D2_CASE(4, 3)
+#undef RT_D2_CASE
+              default: break;
+            }
+          }
+          continue;
+        }
+        if (kind == RT_ROUND) {
+          // transpose through shared memory: store in the old layout, load in the new one.
+          // Both layouts are recomputed here from their records (nothing layout-related is
+          // kept in registers between rounds).
+          unsigned tslot, rsl[RB];
+          {
+            const RtOp& old = ops[cur];
+            unsigned tj = 0;
+            for (int b = 0; b < TB; ++b) tj |= ((tid >> b) & 1u) << old.u.r.tbits[b];
+            tslot = tj ^ rt_sw<SWW>(tj);
+#pragma unroll
+            for (int b = 0; b < RB; ++b) {
+              const unsigned rj = 1u << old.u.r.rbits[b];
+              rsl[b] = rj ^ rt_sw<SWW>(rj);
+            }
+          }
+          __syncthreads();
+#pragma unroll
+          for (int v = 0; v < NV; ++v)
+#pragma unroll
+            for (int k = 0; k < NA; ++k) tile[v * tsize + (tslot ^ sel_xor(rsl, k))] = A[v][k];
+          {
+            unsigned tj = 0;
+            for (int b = 0; b < TB; ++b) tj |= ((tid >> b) & 1u) << op.u.r.tbits[b];
+            tslot = tj ^ rt_sw<SWW>(tj);
+#pragma unroll
+            for (int b = 0; b < RB; ++b) {
+              const unsigned rj = 1u << op.u.r.rbits[b];
+              rsl[b] = rj ^ rt_sw<SWW>(rj);
+            }
+          }
+          __syncthreads();
+#pragma unroll
+          for (int v = 0; v < NV; ++v)
+#pragma unroll
+            for (int k = 0; k < NA; ++k) A[v][k] = tile[v * tsize + (tslot ^ sel_xor(rsl, k))];
+          cur = o;
+          continue;
+        }
+        const unsigned long long baseE = base | a.base_hi;
+        if (kind == RT_PARITY) {
+          const RtGate& g = op.u.g;
+          if (((tid & g.ctrl_t) != g.cval_t) || ((baseE & g.ctrl_e) != g.cval_e)) continue;
+          const unsigned cr = g.ctrl_r, cv = g.cval_r;
+          const unsigned tpar = (__popc(tid & g.par_t) + __popcll(baseE & g.par_e)) & 1u;
+          // the thread's own parity decides which phase is "even" for it
+          const C pe = mats[op.mat_off + tpar], po = mats[op.mat_off + (tpar ^ 1u)];
+          const unsigned pr = g.par_r;
+#pragma unroll
+          for (int k = 0; k < NA; ++k) {
+            if ((k & cr) != cv) continue;
+            const bool odd = __popc((unsigned)k & pr) & 1u;       // uniform over the warp
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+              if (odd) cmul_inplace(A[v][k], po);
+              else cmul_inplace(A[v][k], pe);
+            }
+          }
+          continue;
+        }
+        if (kind == RT_DIAG) {
+          const C* tab = mats + op.mat_off;
+          const int nd = op.q0;
+          unsigned idx0 = 0;
+          for (int b = 0; b < nd; ++b) {
+            const int s = op.u.d.src[b];
+            const int pos = nd - 1 - b;
+            if (s >= 64) idx0 |= (unsigned)((baseE >> (s - 64)) & 1ull) << pos;
+            else if (s >= 32) idx0 |= ((tid >> (s - 32)) & 1u) << pos;
+          }
+#pragma unroll
+          for (int k = 0; k < NA; ++k) {
+            unsigned idx = idx0;
+            for (int b = 0; b < nd; ++b) {
+              const int s = op.u.d.src[b];
+              if (s < 32) idx |= (((unsigned)k >> s) & 1u) << (nd - 1 - b);
+            }
+            const C d = tab[idx];
+#pragma unroll
+            for (int v = 0; v < NV; ++v) cmul_inplace(A[v][k], d);
+          }
+          continue;
+        }
+        if (kind == RT_GEN) {
+          if constexpr (NV > 1) {
+            const unsigned tpar0 = (__popc(tid & op.u.p.zt) + __popcll(baseE & op.u.p.ze)) & 1u;
+            const int ny = op.q1;
+            const unsigned tpar = tpar0 ^ (unsigned)((ny >> 1) & 1);      // i^2 = -1, i^3 = -i
+            const bool odd = ny & 1;
+            const unsigned zr = op.u.p.zr;
+            double s = 0.0;
+            switch (op.u.p.xr) {
+#define RT_GEN_CASE(X) \
+  case X: if constexpr (X < NA) s = gen_term<X>(A, zr, tpar, odd); break;
+              RT_GEN_CASE(0) RT_GEN_CASE(1) RT_GEN_CASE(2) RT_GEN_CASE(3)
+              RT_GEN_CASE(4) RT_GEN_CASE(5) RT_GEN_CASE(6) RT_GEN_CASE(7)
+              RT_GEN_CASE(8) RT_GEN_CASE(9) RT_GEN_CASE(10) RT_GEN_CASE(11)
+              RT_GEN_CASE(12) RT_GEN_CASE(13) RT_GEN_CASE(14) RT_GEN_CASE(15)
+#undef RT_GEN_CASE
+              default: break;
+            }
+            s *= op.u.p.coef;
+            s = warp_sum(s);
+            if ((tid & 31u) == 0) accs[op.q0 * NW + (tid >> 5)] += s;
+          }
+          continue;
+        }
+      }
+
+      // ---- store (last round layout) -----------------------------------------------------
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        if (v == 0 && !a.write0) continue;
+        C* dst = vec[v] + base + toff[THREADS + tid];
+#pragma unroll
+        for (int k = 0; k < NA; ++k) dst[koff[NA + k]] = A[v][k];
+      }
+    }
+
+    if (a.nslots > 0) {
+      __syncthreads();
+      for (int s = tid; s < a.nslots; s += THREADS) {
+        double acc = 0.0;
+        for (int w = 0; w < NW; ++w) acc += accs[s * NW + w];
+        partials[((size_t)blockIdx.y * a.nslots + s) * gridDim.x + blockIdx.x] = acc;
+      }
+    }
+  }
+};
+
+template <typename T_, int RB, int NV, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
+k_rtile(const __grid_constant__ RtArgs a, cx<T_>* __restrict__ v0, cx<T_>* __restrict__ v1,
+        const RtOp* __restrict__ ops_g, const double2* __restrict__ mats_g,
+        const long long mat_bstride, double* __restrict__ partials) {
+  RtKernel<T_, RB, NV, THREADS>::run(a, v0, v1, ops_g, mats_g, mat_bstride, partials);
+}
+
+}  // namespace b200q

@@ -315,14 +315,27 @@ class StateVector:
             raise B200QError(f"operator {name} has no matrix and no dedicated kernel")
         self._apply_matrix_auto(np.asarray(op.matrix()), wires, (), None)
 
-    # ---- fused execution (host fusion pass + tile kernel) ---------------------------------------
-    def default_tile(self):
-        """(T, L): tile bits / contiguous low bits.  64 KiB tiles -> 3 CTAs per SM."""
+    # ---- fused execution (host fusion pass + tile kernels) ------------------------------------
+    def rt_geometry(self, nvec: int = 1):
+        """(T, RB, threads) of the register-tiled kernel for this dtype (b200q_rtile_geometry)."""
+        key = (self.dtype_code, nvec)
+        if key not in _RT_GEOM:
+            T, RB, th = C.c_int(), C.c_int(), C.c_int()
+            check(self.lib.b200q_rtile_geometry(self.dtype_code, nvec, C.byref(T), C.byref(RB),
+                                                C.byref(th)))
+            _RT_GEOM[key] = (T.value, RB.value, th.value)
+        return _RT_GEOM[key]
+
+    def default_tile(self, nvec: int = 1):
+        """(T, L): tile bits / contiguous low bits.  States with at least T qubits use the
+        register-tiled kernel (T fixed by its geometry); smaller states the shared-memory one."""
         import os
 
-        T = int(os.environ.get("B200Q_TILE_T", 12 if self.dtype_code else 13))
-        L = int(os.environ.get("B200Q_TILE_L", 5 if self.dtype_code else 6))
-        return T, L
+        T, _, _ = self.rt_geometry(nvec)
+        if self.n < T:
+            T = min(self.n, 12 if self.dtype_code else 13)
+        L = int(os.environ.get("B200Q_TILE_L", 5))
+        return T, min(L, T)
 
     def apply_operations_fused(self, ops_, level: int = 1, T: int | None = None,
                                L: int | None = None, bit_of=None):
@@ -336,8 +349,8 @@ class StateVector:
             self.run_segment(seg)
         return len(segs)
 
-    def run_segment(self, seg):
-        from .compiler import DIAG, encode_segment
+    def run_segment(self, seg, base_hi: int = 0):
+        from .compiler import DIAG, encode_rt_segment, encode_segment
 
         if seg.tile_bits is None:
             p = seg.prims[0]
@@ -348,12 +361,25 @@ class StateVector:
             else:  # pragma: no cover
                 raise B200QError("unexpected generic primitive")
             return
-        ops_arr, table = encode_segment(seg)
         w, wb = self.workspace()
+        rtT, rtRB, _ = self.rt_geometry(1)
+        if len(seg.tile_bits) == rtT:
+            enc = getattr(seg, "_rt_enc", None)
+            if enc is None:
+                enc = encode_rt_segment(seg, rtRB, 3 if self.dtype_code else 4)
+                seg._rt_enc = enc
+            ops_arr, table, nrec = enc
+            check(self.lib.b200q_apply_rtile(
+                self.ptr, None, self.n, self.dtype_code, self.batch, int_array(seg.tile_bits),
+                rtT, _low_run(seg.tile_bits), C.cast(ops_arr, C.c_void_p), nrec,
+                table.ctypes.data_as(C.c_void_p), int(table.size), 0, 1, int(base_hi), 1.0, None,
+                w, wb, self.stream))
+            return
+        ops_arr, table = encode_segment(seg)
         check(self.lib.b200q_apply_tile(
             self.ptr, self.n, self.dtype_code, self.batch, int_array(seg.tile_bits),
             len(seg.tile_bits), _low_run(seg.tile_bits),
-            C.cast(ops_arr, C.c_void_p), len(seg.prims), table.ctypes.data_as(C.c_void_p),
+            C.cast(ops_arr, C.c_void_p), len(ops_arr), table.ctypes.data_as(C.c_void_p),
             int(table.size), w, wb, self.stream))
 
     def _apply_matrix_auto(self, mat, wires, cw, cvals):
@@ -444,6 +470,7 @@ class StateVector:
 
 
 _XMAT = np.array([[0, 1], [1, 0]], dtype=np.complex128)
+_RT_GEOM: dict = {}
 
 
 def _low_run(tile_bits) -> int:

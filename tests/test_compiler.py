@@ -32,12 +32,15 @@ def _apply_prim(p, psi, n):
             t |= ((idx >> b) & 1) << (k - 1 - j)
         out[sel] = psi[sel] * np.asarray(p.mat)[t[sel]]
     elif p.kind in (CX, DENSE1):
-        m = np.array([[0, 1], [1, 0]], dtype=complex) if p.kind == CX else p.mat
         b = p.targets[0]
-        i0 = idx[sel & (((idx >> b) & 1) == 0)]
-        i1 = i0 | (1 << b)
-        out[i0] = m[0, 0] * psi[i0] + m[0, 1] * psi[i1]
-        out[i1] = m[1, 0] * psi[i0] + m[1, 1] * psi[i1]
+        variants = [(sel, np.array([[0, 1], [1, 0]], dtype=complex) if p.kind == CX else p.mat)]
+        if p.kind == DENSE1 and p.mat0 is not None:
+            variants.append((~sel, p.mat0))          # controlled-select block
+        for s_, m in variants:
+            i0 = idx[s_ & (((idx >> b) & 1) == 0)]
+            i1 = i0 | (1 << b)
+            out[i0] = m[0, 0] * psi[i0] + m[0, 1] * psi[i1]
+            out[i1] = m[1, 0] * psi[i0] + m[1, 1] * psi[i1]
     elif p.kind in (DENSE2, SWAP):
         m = p.mat if p.kind == DENSE2 else np.eye(4)[[0, 2, 1, 3]].astype(complex)
         b0, b1 = p.targets
@@ -119,7 +122,7 @@ def test_hea_packing_and_encoding():
     assert sum(s.ngates for s in segs) == 720 and len(segs) <= 40
     for s in segs:
         arr, table = encode_segment(s)
-        assert len(arr) == len(s.prims) and table.dtype == np.complex128
+        assert len(arr) >= len(s.prims) and table.dtype == np.complex128
         assert isinstance(arr[0], TileOp)
         for o in arr:
             assert 0 <= o.t0 < 12 and 0 <= o.t1 < 12 and o.mat_off + 2 <= table.size + 2
@@ -130,5 +133,52 @@ def test_merging_reduces_primitives():
             q.CNOT(wires=[0, 1]), q.T(wires=1), q.S(wires=1)]
     l0 = compile_ops(ops_, 2, level=0)
     l1 = compile_ops(ops_, 2, level=1)
-    assert sum(len(s.prims) for s in l0) == 7 and sum(len(s.prims) for s in l1) == 4
+    assert sum(len(s.prims) for s in l0) == 7 and sum(len(s.prims) for s in l1) == 2
     assert sum(s.ngates for s in l1) == 7
+
+
+# ---- register-tiled kernel: round scheduling + record encoding (CPU, via tests/rt_emulator) ----
+@pytest.mark.parametrize("level", [0, 1, 2])
+@pytest.mark.parametrize("n,T,L,RB,sww", [(9, 7, 3, 3, 3), (10, 8, 5, 3, 3), (12, 12, 5, 4, 3),
+                                          (13, 12, 4, 4, 3), (13, 13, 5, 5, 4), (13, 12, 5, 3, 3)])
+def test_round_schedule_reproduces_circuit(level, n, T, L, RB, sww):
+    from pennylane_b200.compiler import RT_ROUND, encode_rt_segment, schedule_rounds
+    from rt_emulator import run_records
+
+    ops_ = _random_circuit(n, 100, seed=n * 7 + level + RB)
+    state = random_state(n, seed=n + 1)
+    ref = state
+    for op in ops_:
+        ref = apply_operation(op, ref)
+    segs = compile_ops(ops_, n, level=level, T=T, L=L)
+    psi = state.reshape(-1).copy()
+    lanes = min(5, T - RB)
+    for seg in segs:
+        if seg.tile_bits is None:
+            p = seg.prims[0]
+            if p.kind == GENERIC:
+                psi = apply_operation(p.op, psi.reshape((2,) * n)).reshape(-1)
+            else:
+                psi = _apply_prim(p, psi, n)
+            continue
+        rounds = schedule_rounds(seg.prims, seg.tile_bits, RB, sww)
+        # IO rounds keep tile positions 0..lanes-1 on the lanes
+        for r in (rounds[0], rounds[-1]):
+            assert r.tpos[:lanes] == list(range(lanes))
+            assert all(p >= lanes for p in r.rpos)
+        for r in rounds:
+            assert sorted(r.rpos + r.tpos) == list(range(T))
+        arr, table, nrec = encode_rt_segment(seg, RB, sww, rounds=rounds)
+        assert arr[0].kind == RT_ROUND and nrec == len(arr)
+        psi = run_records(psi, n, seg.tile_bits, arr, table, RB)
+    assert np.max(np.abs(psi.reshape((2,) * n) - ref)) < 1e-12
+
+
+def test_round_schedule_hea_round_count():
+    """The 30-qubit ansatz needs few shared-memory transposes per segment."""
+    import bench
+    from pennylane_b200.compiler import schedule_rounds
+
+    segs = compile_ops(bench.hea_ops(30), 30, level=1, T=12, L=5)
+    nrounds = [len(schedule_rounds(s.prims, s.tile_bits, 4)) for s in segs]
+    assert max(nrounds) <= 6 and sum(nrounds) <= 4 * len(segs)

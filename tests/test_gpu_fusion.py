@@ -107,3 +107,54 @@ def test_device_results_identical_with_and_without_fusion():
         qb.QuantumScript(tape.operations, [qb.sample(wires=range(n))], shots=2000))
     assert np.mean(np.any(s0 != s1, axis=1)) < 5e-3     # rounding may move boundary shots
     del q
+
+
+# ---- register-tiled kernel (b200q_apply_rtile) ----------------------------------------------
+@pytest.mark.parametrize("level", [0, 1, 2])
+@pytest.mark.parametrize("dtype,n,L", [(np.complex128, 12, 5), (np.complex128, 14, 5),
+                                       (np.complex128, 15, 3), (np.complex128, 16, 6),
+                                       (np.complex64, 13, 5), (np.complex64, 15, 4),
+                                       (np.complex64, 16, 7)])
+def test_rtile_random_circuits(level, dtype, n, L):
+    """Every primitive kind through the register-tiled kernel (the tile geometry is the
+    kernel's own: T = 12 for complex128, 13 for complex64)."""
+    from pennylane_b200 import StateVector
+    from test_compiler import _random_circuit
+
+    ops_ = _random_circuit(n, 160, seed=300 + n + level)
+    state = random_state(n, seed=n)
+    sv = StateVector(n, dtype=dtype)
+    T = sv.rt_geometry(1)[0]
+    sv.set_state(state.astype(dtype))
+    nseg = sv.apply_operations_fused(ops_, level=level, T=T, L=L)
+    ref = _oracle(ops_, state)
+    assert np.max(np.abs(sv.to_numpy() - ref)) < TOL[np.dtype(dtype)] * (1 if dtype == np.complex128 else 3)
+    assert nseg < len(ops_)
+
+
+def test_rtile_batched_states_share_the_program():
+    from pennylane_b200 import StateVector
+    from test_compiler import _random_circuit
+
+    n, B = 13, 3
+    ops_ = _random_circuit(n, 60, seed=11)
+    state = random_state(n, seed=5, batch=B)
+    sv = StateVector(n, batch=B)
+    sv.set_state(state)
+    sv.apply_operations_fused(ops_, level=1)
+    ref = _oracle(ops_, state, batched=True)
+    assert np.max(np.abs(sv.to_numpy() - ref)) < 1e-12
+
+
+def test_rtile_hea_matches_unfused_at_20_qubits():
+    import bench
+    from pennylane_b200 import StateVector
+
+    n = 20
+    ops_ = bench.hea_ops(n, layers=2)
+    a = StateVector(n)
+    a.apply_operations_fused(ops_, level=1)
+    b = StateVector(n)
+    for op in ops_:
+        b.apply_operation(op)
+    assert np.max(np.abs(a.to_numpy() - b.to_numpy())) < 1e-13
