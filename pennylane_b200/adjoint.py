@@ -44,9 +44,10 @@ class _Sweep:
     """Reverse sweep state: ``vecs`` buffer, a batched view for plain gate application and the
     device-side accumulator for inner products."""
 
-    def __init__(self, tape, dtype, device, n_bras):
+    def __init__(self, tape, dtype, device, n_bras, fusion: int = 0):
         torch = _torch()
         self.tape = tape
+        self.fusion = int(fusion)
         self.n = tape.num_wires
         self.n_bras = n_bras
         np_dtype = np.dtype(dtype)
@@ -138,6 +139,146 @@ class _Sweep:
         acc[offset: offset + self.n_bras].copy_(torch.from_numpy(vals))
 
 
+# ---------------------------------------------------------------------------------------------
+# fused reverse sweep: whole segments of U^dagger + generator inner products per launch
+# ---------------------------------------------------------------------------------------------
+def _generator_terms(op, bit_of, max_x_bits):
+    """Pauli terms of the generator of ``op`` as GEN primitives (without slot), or None when the
+    generator has no Pauli representation the register kernel can take."""
+    from .compiler import GEN, Prim
+
+    try:
+        gen = op.generator()
+    except Exception:
+        return None
+    if isinstance(gen, tuple):
+        gen = _ops.SProd(gen[1], gen[0])
+    ps = _pauli_rep(gen)
+    if ps is None and getattr(gen, "name", "") == "Projector" and len(gen.wires) == 1 \
+            and getattr(gen, "_basis", False):
+        # |b><b| = (I + (-1)^b Z) / 2   (PhaseShift / U1 / ControlledPhaseShift targets)
+        from .pauli import PauliSentence, PauliWord
+        b = int(np.asarray(gen.data[0]).ravel()[0])
+        ps = PauliSentence({PauliWord({}): 0.5, PauliWord({gen.wires[0]: "Z"}): 0.5 * (-1) ** b})
+    if ps is None:
+        return None
+    terms = []
+    for word, coef in ps.items():
+        if abs(np.imag(coef)) > 1e-14:
+            return None
+        xb, zb, ny = [], [], 0
+        for wire, ch in word.items():
+            b = bit_of(wire)
+            if ch in "XY":
+                xb.append(b)
+            if ch in "ZY":
+                zb.append(b)
+            ny += ch == "Y"
+        if len(xb) > max_x_bits:
+            return None
+        terms.append(Prim(GEN, targets=xb, zbits=zb, ny=ny, coef=float(np.real(coef)), ngates=0))
+    return terms
+
+
+def _fused_reverse_program(tape, n, RB, level):
+    """Primitives of the whole reverse sweep (adjoint_jacobian.py:121-137) in sweep order, or
+    None if some trainable gate cannot be expressed for the register kernel."""
+    from .compiler import GEN, GENERIC, lower
+
+    bit_of = lambda w: n - 1 - int(w)                     # noqa: E731
+    n_op_params, trainable = _param_bookkeeping(tape)
+    param_number = n_op_params - 1
+    t_number = len(trainable) - 1
+    while t_number >= 0 and trainable[t_number] > param_number:
+        t_number -= 1
+    prims, filled = [], []
+    for op in reversed(tape.operations[tape.num_preps:]):
+        if op.name == "Snapshot":
+            continue
+        npar = len(op.data)
+        is_trainable = npar == 1 and param_number in trainable
+        if npar > 1 and any((param_number - j) in trainable for j in range(npar)):
+            raise ValueError(
+                f"adjoint differentiation: operation {op.name} has {npar} parameters; it must "
+                "be decomposed into one-parameter gates first (default_qubit.py:286-292)")
+        adj_prims = lower(_op_adjoint(op), bit_of)
+        if is_trainable:
+            if getattr(op, "batch_size", None) is not None:
+                return None
+            terms = _generator_terms(op, bit_of, RB)
+            if terms is None or any(p.kind == GENERIC for p in adj_prims):
+                return None
+            for t in terms:
+                t.param = t_number
+            prims.extend(terms)
+            filled.append(t_number)
+            t_number -= 1
+        prims.extend(adj_prims)
+        param_number -= npar
+    return prims, filled, trainable
+
+
+def _reverse_sweep_fused(tape, sweep: "_Sweep", level: int = 1):
+    """Reverse sweep through ``b200q_apply_rtile`` in adjoint mode: one read + one write of the
+    ket and of each bra per SEGMENT of gates (instead of per gate), generator inner products
+    accumulated inside the same pass.  Returns (vals[n_trainable][n_bras], filled, trainable)
+    like :func:`_reverse_sweep`, or None when the tape needs the per-gate path."""
+    from .compiler import DIAG, GEN, encode_rt_segment, merge_blocks, pack_segments
+    from .statevector import _low_run
+
+    torch = _torch()
+    ket = sweep.ket
+    n = sweep.n
+    T, RB, _ = ket.rt_geometry(2)
+    if n < T:
+        return None
+    prog = _fused_reverse_program(tape, n, RB, level)
+    if prog is None:
+        return None
+    prims, filled, trainable = prog
+    prims = merge_blocks(prims, level)
+    _, L = ket.default_tile(2)
+    segs = pack_segments(prims, n, T=T, L=L, max_ops=64)
+    n_bras = sweep.n_bras
+    total_slots = sum(len({p.param for p in s.prims if p.kind == GEN}) for s in segs)
+    acc = torch.zeros(max(1, total_slots * n_bras), dtype=torch.float64, device=ket.device)
+    gather = []                                   # (offset in acc, bra, param index)
+    offset = 0
+    w, wb = ket.workspace()
+    sww = 3 if ket.dtype_code else 4
+    for seg in segs:
+        if seg.tile_bits is None:
+            p = seg.prims[0]
+            if p.op is not None:
+                sweep.all.apply_operation(p.op)
+            elif p.kind == DIAG:
+                sweep.all.apply_diag(np.asarray(p.mat), [n - 1 - b for b in p.other])
+            else:  # pragma: no cover
+                raise RuntimeError("unexpected generic primitive in the reverse sweep")
+            continue
+        local = {}
+        for p in seg.prims:
+            if p.kind == GEN:
+                p.slot = local.setdefault(p.param, len(local))
+        ops_arr, table, nrec = encode_rt_segment(seg, RB, sww)
+        nslots = len(local)
+        tb = int_array(seg.tile_bits)
+        for b in range(n_bras):
+            check(sweep.lib.b200q_apply_rtile(
+                ket.ptr, sweep.bra(b).ptr, n, ket.dtype_code, 1, tb, T, _low_run(seg.tile_bits),
+                C.cast(ops_arr, C.c_void_p), nrec, table.ctypes.data_as(C.c_void_p),
+                int(table.size), nslots, 1 if b == n_bras - 1 else 0, 0, -1.0,
+                C.c_void_p(acc.data_ptr() + 8 * offset) if nslots else None, w, wb, ket.stream))
+            for param, slot in local.items():
+                gather.append((offset + slot, b, param))
+            offset += nslots
+    raw = acc.cpu().numpy()
+    vals = np.zeros((max(1, len(trainable)), n_bras))
+    for off, b, param in gather:
+        vals[param, b] = raw[off]
+    return vals, filled, trainable
+
+
 def _param_bookkeeping(tape):
     n_op_params = sum(len(op.data) for op in tape.operations)
     trainable = list(tape.trainable_params)
@@ -149,6 +290,10 @@ def _reverse_sweep(tape, sweep: _Sweep, n_rows_out: int):
     ``vals[n_trainable_op_params][n_bras]`` of ``-Im <bra|G|ket>`` and the list of trainable
     indices (positions in ``tape.trainable_params``) it filled."""
     torch = _torch()
+    if getattr(sweep, "fusion", 0):
+        fused = _reverse_sweep_fused(tape, sweep, sweep.fusion)
+        if fused is not None:
+            return fused
     n_op_params, trainable = _param_bookkeeping(tape)
     n_bras = sweep.n_bras
     acc = torch.zeros(max(1, len(trainable)) * n_bras, dtype=torch.float64, device=sweep.ket.device)
@@ -188,7 +333,7 @@ def adjoint_jacobian(tape, dtype=np.complex128, device=None, return_state: bool 
         raise ValueError("adjoint differentiation does not support broadcasting "
                          "(default_qubit.py:348 expands broadcast tapes first)")
     n_obs = len(obs)
-    sweep = _Sweep(tape, dtype, device, n_obs)
+    sweep = _Sweep(tape, dtype, device, n_obs, fusion=fusion)
     get_final_state(tape, dtype=dtype, device=device, buffer=sweep.vecs[0:1], fusion=fusion)
     final = sweep.ket.clone() if return_state else None
     for k, o in enumerate(obs):
@@ -207,13 +352,13 @@ def adjoint_jacobian(tape, dtype=np.complex128, device=None, return_state: bool 
     return (res, final) if return_state else res
 
 
-def adjoint_jvp(tape, tangents, dtype=np.complex128, device=None):
+def adjoint_jvp(tape, tangents, dtype=np.complex128, device=None, fusion: int = 0):
     """adjoint_jacobian.py:153-223: ``tangents_out[k] = sum_p J[k, p] * tangents[p]``."""
     tape = tape.map_to_standard_wires()
     obs = [m.obs for m in tape.measurements]
     n_obs = len(obs)
-    sweep = _Sweep(tape, dtype, device, n_obs)
-    get_final_state(tape, dtype=dtype, device=device, buffer=sweep.vecs[0:1])
+    sweep = _Sweep(tape, dtype, device, n_obs, fusion=fusion)
+    get_final_state(tape, dtype=dtype, device=device, buffer=sweep.vecs[0:1], fusion=fusion)
     for k, o in enumerate(obs):
         sweep.fill_bra_from_observable(k, o, 2.0)
     vals, filled, trainable = _reverse_sweep(tape, sweep, n_obs)
@@ -226,7 +371,7 @@ def adjoint_jvp(tape, tangents, dtype=np.complex128, device=None):
     return tuple(np.array(t) for t in out)
 
 
-def adjoint_vjp(tape, cotangents, dtype=np.complex128, device=None):
+def adjoint_vjp(tape, cotangents, dtype=np.complex128, device=None, fusion: int = 0):
     """adjoint_jacobian.py:327-419 (unbatched cotangents): the cotangents are folded into one
     effective observable so a single bra is swept regardless of the number of measurements."""
     tape = tape.map_to_standard_wires()
@@ -237,8 +382,8 @@ def adjoint_vjp(tape, cotangents, dtype=np.complex128, device=None):
         return tuple(0.0 for _ in trainable)
     keep = [(c, o) for c, o in zip(cots, obs) if not np.allclose(c, 0.0)]
     new_obs = _ops.dot([c for c, _ in keep], [o for _, o in keep])
-    sweep = _Sweep(tape, dtype, device, 1)
-    get_final_state(tape, dtype=dtype, device=device, buffer=sweep.vecs[0:1])
+    sweep = _Sweep(tape, dtype, device, 1, fusion=fusion)
+    get_final_state(tape, dtype=dtype, device=device, buffer=sweep.vecs[0:1], fusion=fusion)
     sweep.fill_bra_from_observable(0, new_obs, 2.0)
     vals, filled, trainable = _reverse_sweep(tape, sweep, 1)
     out = np.zeros(len(trainable))

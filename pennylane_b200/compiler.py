@@ -53,7 +53,8 @@ class Prim:
                                                      # (None: identity, i.e. a plain controlled gate)
     ngates: int = 1
     op: object = None                                # GENERIC: the original operator
-    slot: int = 0                                    # GEN: output slot (trainable-parameter index)
+    slot: int = 0                                    # GEN: output slot inside its segment
+    param: int = -1                                  # GEN: trainable-parameter index
     ny: int = 0                                      # GEN: number of Y factors
     coef: float = 0.0                                # GEN: real coefficient of the Pauli term
     zbits: list = field(default_factory=list)        # GEN: bits carrying Z or Y

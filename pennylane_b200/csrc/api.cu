@@ -477,13 +477,23 @@ static int tile_t(void* state, int n, int64_t batch, const int* tile_bits, int T
 }
 
 // geometry of the register-tiled kernel: (dtype, nvec) -> (T, RB, THREADS)
+static int rtile_variant() {
+  // tuning knob, read once: 0 = 256 threads x 2 CTAs/SM (default: measured 2120 gates/s on the
+  // 30-qubit ansatz), 1 = register-pipelined 1 CTA/SM (1550 gates/s: 8 warps cannot hide the
+  // FP64 latency)
+  static int variant = -1;
+  if (variant < 0) { const char* e = getenv("B200Q_RT_VARIANT"); variant = e ? atoi(e) : 0; }
+  return variant;
+}
+
 static void rtile_geom(int dtype, int nvec, int& T, int& RB, int& threads) {
-  if (nvec <= 1) { threads = 256; RB = dtype == B200Q_C128 ? 4 : 5; }
-  else { threads = 512; RB = dtype == B200Q_C128 ? 3 : 4; }
+  if (nvec <= 1) {
+    threads = 256; RB = dtype == B200Q_C128 ? 4 : 5;
+  } else { threads = 512; RB = dtype == B200Q_C128 ? 3 : 4; }
   T = (threads == 256 ? 8 : 9) + RB;
 }
 
-template <typename T, int RB, int NV, int THREADS, int MINB>
+template <typename T, int RB, int NV, int THREADS, int MINB, bool PFREG = false>
 static int rtile_launch(void* v0, void* v1, const RtArgs& a, int64_t batch, const RtOp* ops_dev,
                         const double2* mats_dev, int nslots, double scale, double* out_dev,
                         double* partials, size_t partial_cap, cudaStream_t s) {
@@ -494,7 +504,7 @@ static int rtile_launch(void* v0, void* v1, const RtArgs& a, int64_t batch, cons
                 smem, a.nops, nslots);
   static bool attr_set = false;
   if (!attr_set) {
-    B200Q_CHECK(cudaFuncSetAttribute(k_rtile<T, RB, NV, THREADS, MINB>,
+    B200Q_CHECK(cudaFuncSetAttribute(k_rtile<T, RB, NV, THREADS, MINB, PFREG>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
@@ -505,8 +515,8 @@ static int rtile_launch(void* v0, void* v1, const RtArgs& a, int64_t batch, cons
   if (nslots > 0)
     B200Q_REQUIRE((size_t)batch * nslots * grid.x <= partial_cap, "rtile: workspace too small for %d slots",
                   nslots);
-  k_rtile<T, RB, NV, THREADS, MINB><<<grid, THREADS, smem, s>>>(a, (cx<T>*)v0, (cx<T>*)v1, ops_dev,
-                                                                 mats_dev, 0, partials);
+  k_rtile<T, RB, NV, THREADS, MINB, PFREG><<<grid, THREADS, smem, s>>>(
+      a, (cx<T>*)v0, (cx<T>*)v1, ops_dev, mats_dev, 0, partials);
   B200Q_LAUNCH_CHECK();
   if (nslots > 0) {
     k_final_reduce<<<(unsigned)(batch * nslots), 256, 0, s>>>(partials, out_dev, (int)grid.x, 1,
@@ -570,11 +580,16 @@ static int rtile_dispatch(void* v0, void* v1, int n, int dtype, int64_t batch, c
   const size_t pcap = (work_bytes - kTermRegion) / sizeof(double);
   const RtOp* od = (const RtOp*)w;
   const double2* md = (const double2*)(w + moff);
+  const int variant = rtile_variant();
   if (dtype == B200Q_C128) {
+    if (!v1 && variant == 1)
+      return rtile_launch<double, 4, 1, 256, 1, true>(v0, v1, a, batch, od, md, nslots, scale, out_dev, partials, pcap, s);
     if (!v1) return rtile_launch<double, 4, 1, 256, 2>(v0, v1, a, batch, od, md, nslots, scale, out_dev, partials, pcap, s);
     return rtile_launch<double, 3, 2, 512, 1>(v0, v1, a, batch, od, md, nslots, scale, out_dev, partials, pcap, s);
   }
   if (dtype == B200Q_C64) {
+    if (!v1 && variant == 1)
+      return rtile_launch<float, 5, 1, 256, 1, true>(v0, v1, a, batch, od, md, nslots, scale, out_dev, partials, pcap, s);
     if (!v1) return rtile_launch<float, 5, 1, 256, 2>(v0, v1, a, batch, od, md, nslots, scale, out_dev, partials, pcap, s);
     return rtile_launch<float, 4, 2, 512, 1>(v0, v1, a, batch, od, md, nslots, scale, out_dev, partials, pcap, s);
   }

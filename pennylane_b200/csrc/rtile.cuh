@@ -78,7 +78,8 @@ struct RtArgs {
   int n, T, L, nops, nmat, nslots;
   int write0;                    // write vector 0 back (adjoint passes over several bras)
   int last_round;                // index of the last RT_ROUND record
-  int prefetch;                  // issue L2 prefetches for the CTA's next tile
+  int prefetch;                  // L2 prefetch of the CTA's next tile: bytes per prefetch
+                                 // instruction (0 = off)
   int8_t hi_bits[16];            // global positions of tile positions L..T-1 (ascending)
   int8_t out_bits[B200Q_MAX_BITS];   // ascending global positions of the n-T non-tile bits
   unsigned long long ntiles;     // 2^(n-T)
@@ -100,7 +101,10 @@ __device__ __forceinline__ unsigned long long rt_gscatter(unsigned j, const RtAr
   return off;
 }
 
-template <typename T_, int RB, int NV, int THREADS>
+// PFREG: software pipelining through registers — the loads of the CTA's NEXT tile are issued
+// (into a second register set) before the gates of the current tile run, so HBM latency hides
+// behind the FP64 work of the same CTA (one CTA per SM, up to 255 registers per thread).
+template <typename T_, int RB, int NV, int THREADS, bool PFREG = false>
 struct RtKernel {
   static constexpr int NA = 1 << RB;
   static constexpr int TB = (THREADS == 128) ? 7 : (THREADS == 256) ? 8 : (THREADS == 512) ? 9 : 10;
@@ -277,9 +281,23 @@ struct RtKernel {
       }
     }
     __syncthreads();
-    // L2 prefetch granule: one 128-byte line when the contiguous run allows it
-    const unsigned line_amps = 128u / sizeof(C);
+    // L2 prefetch granule (amplitudes), never longer than the contiguous run
+    const unsigned line_amps = (a.prefetch > 0 ? (unsigned)a.prefetch : 128u) / sizeof(C);
     const unsigned pf_unit = (1u << a.L) < line_amps ? (1u << a.L) : line_amps;
+
+    C A[NV][NA];
+    C B[PFREG ? NV : 1][PFREG ? NA : 1];
+    if (PFREG && blockIdx.x < (unsigned)a.ntiles) {
+      unsigned long long b0 = 0;
+      for (int b = 0; b < a.n - a.T; ++b)
+        b0 |= (unsigned long long)((blockIdx.x >> b) & 1u) << a.out_bits[b];
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        const C* src = vec[v] + b0 + toff[tid];
+#pragma unroll
+        for (int k = 0; k < NA; ++k) A[v][k] = src[koff[k]];
+      }
+    }
 
     for (unsigned t = blockIdx.x; t < (unsigned)a.ntiles; t += gridDim.x) {
       unsigned long long base = 0;
@@ -297,13 +315,28 @@ struct RtKernel {
         }
       }
 
-      C A[NV][NA];
       // ---- load (round 0 layout) ------------------------------------------------------------
+      if (PFREG) {
+        // issue the NEXT tile's loads now; they complete while this tile's gates run
+        if (t + gridDim.x < (unsigned)a.ntiles) {
+          const unsigned tn = t + gridDim.x;
+          unsigned long long bn = 0;
+          for (int b = 0; b < a.n - a.T; ++b)
+            bn |= (unsigned long long)((tn >> b) & 1u) << a.out_bits[b];
 #pragma unroll
-      for (int v = 0; v < NV; ++v) {
-        const C* src = vec[v] + base + toff[tid];
+          for (int v = 0; v < (PFREG ? NV : 1); ++v) {
+            const C* src = vec[v] + bn + toff[tid];
 #pragma unroll
-        for (int k = 0; k < NA; ++k) A[v][k] = src[koff[k]];
+            for (int k = 0; k < (PFREG ? NA : 1); ++k) B[v][k] = src[koff[k]];
+          }
+        }
+      } else {
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+          const C* src = vec[v] + base + toff[tid];
+#pragma unroll
+          for (int k = 0; k < NA; ++k) A[v][k] = src[koff[k]];
+        }
       }
       int cur = 0;                     // index of the current round's record
 
@@ -485,6 +518,12 @@ struct RtKernel {
 #pragma unroll
         for (int k = 0; k < NA; ++k) dst[koff[NA + k]] = A[v][k];
       }
+      if (PFREG) {
+#pragma unroll
+        for (int v = 0; v < (PFREG ? NV : 1); ++v)
+#pragma unroll
+          for (int k = 0; k < (PFREG ? NA : 1); ++k) A[v][k] = B[v][k];
+      }
     }
 
     if (a.nslots > 0) {
@@ -498,12 +537,12 @@ struct RtKernel {
   }
 };
 
-template <typename T_, int RB, int NV, int THREADS, int MINB>
+template <typename T_, int RB, int NV, int THREADS, int MINB, bool PFREG = false>
 __global__ void __launch_bounds__(THREADS, MINB)
 k_rtile(const __grid_constant__ RtArgs a, cx<T_>* __restrict__ v0, cx<T_>* __restrict__ v1,
         const RtOp* __restrict__ ops_g, const double2* __restrict__ mats_g,
         const long long mat_bstride, double* __restrict__ partials) {
-  RtKernel<T_, RB, NV, THREADS>::run(a, v0, v1, ops_g, mats_g, mat_bstride, partials);
+  RtKernel<T_, RB, NV, THREADS, PFREG>::run(a, v0, v1, ops_g, mats_g, mat_bstride, partials);
 }
 
 }  // namespace b200q

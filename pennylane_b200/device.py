@@ -358,7 +358,8 @@ class B200Qubit:
         tangents = (tangents,) if single else tuple(tangents)
         self._track(batch, "jvp_batches")
         res = tuple(_adjoint.adjoint_jvp(c, t, dtype=self._dtype(execution_config),
-                                         device=self._torch_device) for c, t in zip(batch, tangents))
+                                         device=self._torch_device, fusion=self._fusion)
+                    for c, t in zip(batch, tangents))
         return res[0] if single else res
 
     def execute_and_compute_jvp(self, circuits, tangents, execution_config=None):
@@ -370,7 +371,8 @@ class B200Qubit:
         cotangents = (cotangents,) if single else tuple(cotangents)
         self._track(batch, "vjp_batches")
         res = tuple(_adjoint.adjoint_vjp(c, t, dtype=self._dtype(execution_config),
-                                         device=self._torch_device) for c, t in zip(batch, cotangents))
+                                         device=self._torch_device, fusion=self._fusion)
+                    for c, t in zip(batch, cotangents))
         return res[0] if single else res
 
     def execute_and_compute_vjp(self, circuits, cotangents, execution_config=None):

@@ -182,3 +182,57 @@ def test_round_schedule_hea_round_count():
     segs = compile_ops(bench.hea_ops(30), 30, level=1, T=12, L=5)
     nrounds = [len(schedule_rounds(s.prims, s.tile_bits, 4)) for s in segs]
     assert max(nrounds) <= 6 and sum(nrounds) <= 4 * len(segs)
+
+
+# ---- fused adjoint reverse sweep: program construction + GEN records (CPU, emulated) -----------
+def _trainable_circuit(n, depth, seed):
+    rng = np.random.default_rng(seed)
+    ops_ = []
+    for _ in range(depth):
+        w = [int(x) for x in rng.permutation(n)]
+        a, b, c = w[0], w[1], w[2]
+        th = rng.uniform(0, 6)
+        choices = [q.RX(th, wires=a), q.RY(th, wires=a), q.RZ(th, wires=a), q.PhaseShift(th, wires=a),
+                   q.IsingXX(th, wires=[a, b]), q.IsingYY(th, wires=[a, b]), q.IsingZZ(th, wires=[a, b]),
+                   q.PauliRot(th, "XY", wires=[a, b]), q.PauliRot(th, "ZZ", wires=[a, b]),
+                   q.MultiRZ(th, wires=[a, b, c]), q.CNOT(wires=[a, b]), q.Hadamard(wires=a),
+                   q.CZ(wires=[a, b]), q.Toffoli(wires=[a, b, c]), q.S(wires=a), q.SWAP(wires=[a, b])]
+        ops_.append(choices[int(rng.integers(len(choices)))])
+    return ops_
+
+
+@pytest.mark.parametrize("level", [0, 1])
+@pytest.mark.parametrize("n,T,L,RB", [(8, 7, 3, 3), (9, 8, 4, 3), (10, 9, 5, 4)])
+def test_fused_reverse_sweep_program(level, n, T, L, RB):
+    import pennylane_b200 as qb
+    from oracle import adjoint_jacobian as o_adj
+    from oracle import simulate as o_sim
+    from pennylane_b200.adjoint import _fused_reverse_program
+    from pennylane_b200.compiler import GEN, encode_rt_segment, merge_blocks, pack_segments
+    from rt_emulator import run_records
+
+    ops_ = _trainable_circuit(n, 60, seed=n + level)
+    obs = q.PauliZ(wires=0) @ q.PauliX(wires=2)
+    tape = qb.QuantumScript(ops_, [qb.expval(obs)])
+    state, _ = o_sim.get_final_state(tape)
+    ref = np.array(o_adj.adjoint_jacobian(tape, state), dtype=float)
+    prog = _fused_reverse_program(tape, n, RB, level)
+    assert prog is not None
+    prims, filled, trainable = prog
+    segs = pack_segments(merge_blocks(prims, level), n, T=T, L=L, max_ops=64)
+    ket = state.reshape(-1).copy()
+    from oracle.apply_operation import apply_operation as o_apply
+    bra = 2.0 * o_apply(obs, state).reshape(-1)
+    jac = np.zeros(len(trainable))
+    for seg in segs:
+        assert seg.tile_bits is not None
+        local = {}
+        for p in seg.prims:
+            if p.kind == GEN:
+                p.slot = local.setdefault(p.param, len(local))
+        arr, table, nrec = encode_rt_segment(seg, RB)
+        ket, bra, sums = run_records(ket, n, seg.tile_bits, arr, table, RB, bra=bra, nslots=len(local))
+        for param, slot in local.items():
+            jac[param] += -sums[slot]
+    assert sorted(filled) == list(range(len(trainable)))
+    assert np.max(np.abs(jac - ref)) < 1e-12

@@ -166,3 +166,59 @@ def test_single_precision_adjoint():
     tape = _layered_tape(n, 2, 5, [q.PauliZ(wires=0)])
     jac = np.array(adjoint_jacobian(tape, dtype=np.complex64), dtype=float)
     assert np.max(np.abs(jac - _oracle_jac(tape))) < 1e-5
+
+
+# ---- fused reverse sweep (b200q_apply_rtile in adjoint mode) -------------------------------------
+@pytest.mark.parametrize("dtype,n,tol", [(np.complex128, 12, 1e-12), (np.complex128, 14, 1e-12),
+                                         (np.complex64, 13, 2e-5), (np.complex64, 14, 2e-5)])
+@pytest.mark.parametrize("fusion", [1, 2])
+def test_fused_reverse_sweep_layered(dtype, n, tol, fusion):
+    """Three observables (three bras sharing one ket) through the fused sweep."""
+    from pennylane_b200 import ops as q
+    from pennylane_b200.adjoint import adjoint_jacobian
+
+    obs = [q.PauliZ(wires=0), q.PauliX(wires=n - 1) @ q.PauliY(wires=0),
+           q.LinearCombination([0.5, -1.5], [q.PauliZ(wires=1) @ q.PauliZ(wires=0), q.PauliX(wires=1)])]
+    tape = _layered_tape(n, 2, n, obs)
+    jac = np.array(adjoint_jacobian(tape, dtype=dtype, fusion=fusion), dtype=float)
+    assert jac.shape == (3, 6 * n)
+    assert np.max(np.abs(jac - _oracle_jac(tape))) < tol
+
+
+@pytest.mark.parametrize("n", [12, 13])
+def test_fused_reverse_sweep_mixed_gates(n):
+    """Every generator shape the register kernel takes (X/Y/Z words, two-term projector
+    generators, three-wire Z strings) next to non-trainable gates of all kinds, with only a
+    subset of the parameters trainable."""
+    import pennylane_b200 as qb
+    from pennylane_b200 import ops as q
+    from pennylane_b200.adjoint import _Sweep, _reverse_sweep_fused, adjoint_jacobian
+    from test_compiler import _trainable_circuit
+
+    ops_ = _trainable_circuit(n, 90, seed=40 + n)
+    npar = sum(len(o.data) for o in ops_)
+    trainable = [i for i in range(npar) if i % 3 != 1]
+    tape = qb.QuantumScript(ops_, [qb.expval(q.PauliZ(wires=0) @ q.PauliX(wires=2)),
+                                   qb.expval(q.PauliY(wires=n - 1))], trainable_params=trainable)
+    jac = np.array(adjoint_jacobian(tape, fusion=1), dtype=float)
+    assert np.max(np.abs(jac - _oracle_jac(tape))) < 1e-12
+    # the fused path really ran (it returns None when it has to fall back)
+    sw = _Sweep(tape.map_to_standard_wires(), np.complex128, None, 2, fusion=1)
+    assert _reverse_sweep_fused(tape.map_to_standard_wires(), sw, 1) is not None
+
+
+def test_fused_vjp_and_jvp_match_oracle():
+    from pennylane_b200 import ops as q
+    from pennylane_b200.adjoint import adjoint_jvp, adjoint_vjp
+
+    n = 12
+    obs = [q.PauliZ(wires=0), q.PauliX(wires=3)]
+    tape = _layered_tape(n, 1, 5, obs)
+    ref = _oracle_jac(tape)
+    rng = np.random.default_rng(0)
+    cot = rng.normal(size=2)
+    tan = rng.normal(size=ref.shape[1])
+    vjp = np.array(adjoint_vjp(tape, cot, fusion=1), dtype=float)
+    jvp = np.array(adjoint_jvp(tape, tan, fusion=1), dtype=float)
+    assert np.max(np.abs(vjp - cot @ ref)) < 1e-12
+    assert np.max(np.abs(jvp - ref @ tan)) < 1e-12
