@@ -219,21 +219,45 @@ struct RtKernel {
     a.y = fma(p.x, a.y, ty);
   }
 
-  // acc += sign * {Re, Im}(conj(bra_k) * ket_{k ^ XR})
-  template <int XR>
-  static __device__ __forceinline__ double gen_term(const C (&A)[NV][NA], unsigned zr,
-                                                    unsigned tpar, bool odd) {
+  // sum_k sign_k * {Re, Im}(conj(bra_k) * ket_{k ^ PM}),  sign_k = (-1)^(popc((k ^ xr) & zr) + tpar).
+  // Only PM = 0 is instantiated: the X part of a generator term is applied to the ket in
+  // registers first (flip_ket_mask, pure register moves) and undone afterwards.  A switch over
+  // compile-time partner masks looked cheaper on paper but made ptxas spill ~4-12 KB per thread
+  // at the 128-register cap of the 512-thread adjoint kernel (checked with -Xptxas -v).
+  template <int PM>
+  static __device__ __forceinline__ double gen_term(const C (&A)[NV][NA], const unsigned xr,
+                                                    const unsigned zr, const unsigned tpar,
+                                                    const bool odd) {
     double acc = 0.0;
 #pragma unroll
     for (int k = 0; k < NA; ++k) {
-      const C b = A[NV - 1][k], x = A[0][k ^ XR];
-      const unsigned par = (__popc((unsigned)(k ^ XR) & zr) & 1u) ^ tpar;
+      const C b = A[NV - 1][k], x = A[0][k ^ PM];
+      const unsigned par = (__popc(((unsigned)k ^ xr) & zr) & 1u) ^ tpar;
       double val;
       if (odd) val = (double)b.x * (double)x.x + (double)b.y * (double)x.y;   // Re
       else val = (double)b.x * (double)x.y - (double)b.y * (double)x.x;       // Im
       acc += par ? -val : val;
     }
     return acc;
+  }
+
+  template <int Q> static __device__ __forceinline__ void flip_ket(C (&A)[NV][NA]) {
+#pragma unroll
+    for (int k = 0; k < NA; ++k) {
+      if ((k >> Q) & 1) continue;
+      const C x0 = A[0][k];
+      A[0][k] = A[0][k | (1 << Q)];
+      A[0][k | (1 << Q)] = x0;
+    }
+  }
+
+  // flip the ket on every register bit of `mask` (a permutation; applying it twice undoes it)
+  static __device__ __forceinline__ void flip_ket_mask(C (&A)[NV][NA], const unsigned mask) {
+    if (mask & 1u) flip_ket<0>(A);
+    if constexpr (RB > 1) { if (mask & 2u) flip_ket<1>(A); }
+    if constexpr (RB > 2) { if (mask & 4u) flip_ket<2>(A); }
+    if constexpr (RB > 3) { if (mask & 8u) flip_ket<3>(A); }
+    if constexpr (RB > 4) { if (mask & 16u) flip_ket<4>(A); }
   }
 
   static __device__ __forceinline__ void run(const RtArgs& __restrict__ a, C* __restrict__ v0,
@@ -464,21 +488,24 @@ struct RtKernel {
         if (kind == RT_DIAG) {
           const C* tab = mats + op.mat_off;
           const int nd = op.q0;
-          unsigned idx0 = 0;
+          // table index = thread/external part | OR of per-register-bit contributions
+          unsigned idx0 = 0, rc[RB];
+#pragma unroll
+          for (int b = 0; b < RB; ++b) rc[b] = 0;
           for (int b = 0; b < nd; ++b) {
             const int s = op.u.d.src[b];
-            const int pos = nd - 1 - b;
-            if (s >= 64) idx0 |= (unsigned)((baseE >> (s - 64)) & 1ull) << pos;
-            else if (s >= 32) idx0 |= ((tid >> (s - 32)) & 1u) << pos;
+            const unsigned bit = 1u << (nd - 1 - b);
+            if (s >= 64) idx0 |= ((baseE >> (s - 64)) & 1ull) ? bit : 0u;
+            else if (s >= 32) idx0 |= ((tid >> (s - 32)) & 1u) ? bit : 0u;
+            else {
+#pragma unroll
+              for (int r = 0; r < RB; ++r)
+                if (s == r) rc[r] |= bit;
+            }
           }
 #pragma unroll
           for (int k = 0; k < NA; ++k) {
-            unsigned idx = idx0;
-            for (int b = 0; b < nd; ++b) {
-              const int s = op.u.d.src[b];
-              if (s < 32) idx |= (((unsigned)k >> s) & 1u) << (nd - 1 - b);
-            }
-            const C d = tab[idx];
+            const C d = tab[idx0 | sel_xor(rc, k)];
 #pragma unroll
             for (int v = 0; v < NV; ++v) cmul_inplace(A[v][k], d);
           }
@@ -491,17 +518,10 @@ struct RtKernel {
             const unsigned tpar = tpar0 ^ (unsigned)((ny >> 1) & 1);      // i^2 = -1, i^3 = -i
             const bool odd = ny & 1;
             const unsigned zr = op.u.p.zr;
-            double s = 0.0;
-            switch (op.u.p.xr) {
-#define RT_GEN_CASE(X) \
-  case X: if constexpr (X < NA) s = gen_term<X>(A, zr, tpar, odd); break;
-              RT_GEN_CASE(0) RT_GEN_CASE(1) RT_GEN_CASE(2) RT_GEN_CASE(3)
-              RT_GEN_CASE(4) RT_GEN_CASE(5) RT_GEN_CASE(6) RT_GEN_CASE(7)
-              RT_GEN_CASE(8) RT_GEN_CASE(9) RT_GEN_CASE(10) RT_GEN_CASE(11)
-              RT_GEN_CASE(12) RT_GEN_CASE(13) RT_GEN_CASE(14) RT_GEN_CASE(15)
-#undef RT_GEN_CASE
-              default: break;
-            }
+            const unsigned xr = op.u.p.xr;
+            if (xr) flip_ket_mask(A, xr);
+            double s = gen_term<0>(A, xr, zr, tpar, odd);
+            if (xr) flip_ket_mask(A, xr);
             s *= op.u.p.coef;
             s = warp_sum(s);
             if ((tid & 31u) == 0) accs[op.q0 * NW + (tid >> 5)] += s;

@@ -31,3 +31,16 @@ b.record(); torch.cuda.synchronize()
 print(json.dumps({"env": {k: v for k, v in os.environ.items() if k.startswith("B200Q_")},
                   "segments": len(segs), "total_ms": round(ms, 1), "gates_per_s": round(720 / ms * 1e3),
                   "empty_gbps": round(2 * 16 * (1 << n) * 5 / (a.elapsed_time(b) * 1e-3) / 1e9)}))
+
+if "--adjoint" in sys.argv:
+    import time
+    import pennylane_b200 as qb
+    del sv
+    torch.cuda.empty_cache()
+    tape = bench.hea_tape(n)
+    dev = qb.B200Qubit(wires=n, fusion=1)
+    for i in range(2):
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        res, jac = dev.execute_and_compute_derivatives(tape)
+        torch.cuda.synchronize(); dt = time.perf_counter() - t0
+        print(json.dumps({"adjoint_s": round(dt, 3), "grad_norm": float((sum(float(j) ** 2 for j in jac)) ** 0.5)}))
