@@ -120,6 +120,23 @@ int b200q_sample(double* probs_dev, int m, const double* uniforms_dev, int64_t s
                  int64_t* idx_out_dev, int64_t* bits_out_dev, double* norm_out_dev,
                  int* flags_dev, void* work, size_t work_bytes, void* stream);
 
+/* Sampler building blocks: b200q_sample == has_nan, np_sum, div_by, cumsum, div_by(last), search,
+ * unpack_bits.  A sharded probability vector (rank r holds entries [r 2^m, (r+1) 2^m)) composes
+ * them around its collectives: np_sum per rank + numpy's pairwise tree over ranks; cumsum with
+ * carry_in_dev = the previous rank's last CDF entry (NULL on rank 0); search returns the number
+ * of LOCAL cdf entries <= u, and the global index is the sum of those counts over ranks.
+ * All vectors have 2^m entries.  sampling.py:500-531. */
+int b200q_has_nan(const double* p_dev, int m, int* flag_dev, void* stream);
+int b200q_np_sum(const double* p_dev, int m, double* out_dev, void* work, size_t work_bytes,
+                 void* stream);
+int b200q_div_by(double* p_dev, int m, const double* divisor_dev, void* stream);
+int b200q_cumsum(double* p_dev, int m, int mode, const double* carry_in_dev, void* work,
+                 size_t work_bytes, void* stream);
+int b200q_search(const double* cdf_dev, int m, const double* uniforms_dev, int64_t shots,
+                 int64_t* idx_out_dev, void* stream);
+int b200q_unpack_bits(const int64_t* idx_dev, int64_t shots, int m, int64_t* bits_out_dev,
+                      void* stream);
+
 /* Fused gate segment: ONE read + ONE write of the state applies `nops` gates through a
  * shared-memory tile spanning `tile_bits` (T ascending bit positions, the first L equal to
  * 0..L-1).  ops_host: array of 64-byte b200q_tile_op records (layout below); mats_host: the

@@ -45,6 +45,12 @@ SIGNATURES = {
         _i, [_p, _p, _i, _i, _i64, _u64p, _u64p, _ip, _dp, _dp, _i, _d, _p, _sz, _p]),
     "b200q_pauli_braket": (_i, [_p, _p, _i, _i, _u64, _u64, _i, _p, _p, _sz, _p]),
     "b200q_sample": (_i, [_p, _i, _p, _i64, _i, _p, _p, _p, _p, _p, _sz, _p]),
+    "b200q_has_nan": (_i, [_p, _i, _p, _p]),
+    "b200q_np_sum": (_i, [_p, _i, _p, _p, _sz, _p]),
+    "b200q_div_by": (_i, [_p, _i, _p, _p]),
+    "b200q_cumsum": (_i, [_p, _i, _i, _p, _p, _sz, _p]),
+    "b200q_search": (_i, [_p, _i, _p, _i64, _p, _p]),
+    "b200q_unpack_bits": (_i, [_p, _i64, _i, _p, _p]),
     "b200q_apply_tile": (_i, [_p, _i, _i, _i64, _ip, _i, _i, _p, _i, _p, _i, _p, _sz, _p]),
     "b200q_rtile_geometry": (_i, [_i, _i, _ip, _ip, _ip]),
     "b200q_apply_rtile": (_i, [_p, _p, _i, _i, _i64, _ip, _i, _i, _p, _i, _p, _i, _i, _i, _u64, _d,

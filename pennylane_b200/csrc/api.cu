@@ -805,6 +805,88 @@ int b200q_sample(double* probs_dev, int m, const double* uniforms_dev, int64_t s
   return 0;
 }
 
+// ---- sampler building blocks (the sharded sampler composes them around collectives) -------
+int b200q_has_nan(const double* p_dev, int m, int* flag_dev, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  B200Q_REQUIRE(m >= 0 && m <= 40 && p_dev && flag_dev, "has_nan: bad arguments");
+  const uint64_t count = 1ull << m;
+  B200Q_CHECK(cudaMemsetAsync(flag_dev, 0, sizeof(int), s));
+  k_has_nan<<<grid_for(count, 256, 8), 256, 0, s>>>(p_dev, count, flag_dev);
+  B200Q_LAUNCH_CHECK();
+  return 0;
+}
+
+int b200q_np_sum(const double* p_dev, int m, double* out_dev, void* work, size_t work_bytes,
+                 void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  B200Q_REQUIRE(m >= 0 && m <= 40 && p_dev && out_dev, "np_sum: bad arguments");
+  const uint64_t count = 1ull << m;
+  B200Q_REQUIRE(work && work_bytes >= kWorkBytes &&
+                    (count / 128 + count / (128 * 2047) + 64) * sizeof(double) <=
+                        work_bytes - kTermRegion,
+                "np_sum: workspace too small for 2^%d values", m);
+  double* scratch = (double*)((char*)work + kTermRegion);
+  return np_sum(p_dev, count, out_dev, scratch + 8, s);
+}
+
+int b200q_div_by(double* p_dev, int m, const double* divisor_dev, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  B200Q_REQUIRE(m >= 0 && m <= 40 && p_dev && divisor_dev, "div_by: bad arguments");
+  const uint64_t count = 1ull << m;
+  k_div_by<<<grid_for(count, 256, 8), 256, 0, s>>>(p_dev, divisor_dev, count);
+  B200Q_LAUNCH_CHECK();
+  return 0;
+}
+
+int b200q_cumsum(double* p_dev, int m, int mode, const double* carry_in_dev, void* work,
+                 size_t work_bytes, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  B200Q_REQUIRE(m >= 0 && m <= 40 && p_dev, "cumsum: bad arguments");
+  const uint64_t count = 1ull << m;
+  if (mode == B200Q_CDF_EXACT) {
+    k_cumsum_serial<1024><<<1, 64, 0, s>>>(p_dev, p_dev, count, carry_in_dev);
+    B200Q_LAUNCH_CHECK();
+    return 0;
+  }
+  B200Q_REQUIRE(mode == B200Q_CDF_FAST, "cumsum: unknown mode %d", mode);
+  const uint64_t nblocks = (count + 2047) / 2048;
+  B200Q_REQUIRE(work && work_bytes >= kWorkBytes &&
+                    (nblocks + 64) * sizeof(double) <= work_bytes - kTermRegion,
+                "cumsum: workspace too small for 2^%d values", m);
+  double* tree = (double*)((char*)work + kTermRegion) + 8;
+  k_scan_block_totals<<<(unsigned)nblocks, 256, 0, s>>>(p_dev, tree, count);
+  B200Q_LAUNCH_CHECK();
+  k_scan_totals<<<1, 1024, 0, s>>>(tree, nblocks, carry_in_dev);
+  B200Q_LAUNCH_CHECK();
+  k_scan_apply<<<(unsigned)nblocks, 256, 0, s>>>(p_dev, tree, p_dev, count);
+  B200Q_LAUNCH_CHECK();
+  return 0;
+}
+
+int b200q_search(const double* cdf_dev, int m, const double* uniforms_dev, int64_t shots,
+                 int64_t* idx_out_dev, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  B200Q_REQUIRE(m >= 0 && m <= 40 && cdf_dev && uniforms_dev && idx_out_dev && shots >= 0,
+                "search: bad arguments");
+  if (shots == 0) return 0;
+  k_search<<<(unsigned)((shots + 255) / 256), 256, 0, s>>>(
+      cdf_dev, 1ull << m, uniforms_dev, (uint64_t)shots, (long long*)idx_out_dev, nullptr, m);
+  B200Q_LAUNCH_CHECK();
+  return 0;
+}
+
+int b200q_unpack_bits(const int64_t* idx_dev, int64_t shots, int m, int64_t* bits_out_dev,
+                      void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  B200Q_REQUIRE(m >= 0 && m <= 62 && idx_dev && bits_out_dev && shots >= 0,
+                "unpack_bits: bad arguments");
+  if (shots == 0 || m == 0) return 0;
+  k_unpack_bits<<<(unsigned)((shots + 255) / 256), 256, 0, s>>>(
+      (const long long*)idx_dev, (uint64_t)shots, m, (long long*)bits_out_dev);
+  B200Q_LAUNCH_CHECK();
+  return 0;
+}
+
 int b200q_apply_tile(void* state, int n, int dtype, int64_t batch, const int* tile_bits, int T,
                      int L, const void* ops_host, int nops, const void* mats_host, int nmat,
                      void* work, size_t work_bytes, void* stream) {

@@ -96,9 +96,12 @@ __global__ void k_copy_last(const double* __restrict__ cdf, double* __restrict__
 // finished chunks back; lane 0 of warp 0 runs the dependent chain of rounded additions
 // (numpy's DOUBLE_add.accumulate: out[0] = p[0]; out[i] = out[i-1] + p[i]).  Triple buffered so
 // global traffic overlaps the chain.  In place allowed (cdf may alias p).
+// carry_in (nullable): running sum of everything that precedes p[0] in the global vector (the
+// previous rank's last CDF entry when the probability vector is sharded): out[0] = carry + p[0].
 template <int CHUNK>
 __global__ void __launch_bounds__(64)
-k_cumsum_serial(const double* p, double* cdf, const uint64_t count) {
+k_cumsum_serial(const double* p, double* cdf, const uint64_t count,
+                const double* __restrict__ carry_in = nullptr) {
   __shared__ double buf[3][CHUNK];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   double run = 0.0;
@@ -128,7 +131,7 @@ k_cumsum_serial(const double* p, double* cdf, const uint64_t count) {
     } else if (lane == 0) {
       double* b = buf[cur];
       int i0 = 0;
-      if (c == 0) { run = b[0]; i0 = 1; }
+      if (c == 0) { run = carry_in ? __dadd_rn(*carry_in, b[0]) : b[0]; b[0] = run; i0 = 1; }
 #pragma unroll 8
       for (int i = i0; i < CHUNK; ++i) { run = __dadd_rn(run, b[i]); b[i] = run; }
     }
@@ -162,11 +165,12 @@ k_scan_block_totals(const double* __restrict__ p, double* __restrict__ totals, c
 }
 
 __global__ void __launch_bounds__(1024)
-k_scan_totals(double* __restrict__ totals, const uint64_t nblocks) {
+k_scan_totals(double* __restrict__ totals, const uint64_t nblocks,
+              const double* __restrict__ carry_in = nullptr) {
   // exclusive scan in place, single CTA, processes 1024 entries per round
   __shared__ double s[1024];
   __shared__ double carry;
-  if (threadIdx.x == 0) carry = 0.0;
+  if (threadIdx.x == 0) carry = carry_in ? *carry_in : 0.0;
   __syncthreads();
   for (uint64_t base = 0; base < nblocks; base += 1024) {
     const uint64_t g = base + threadIdx.x;
@@ -242,6 +246,17 @@ k_search(const double* __restrict__ cdf, const uint64_t count, const double* __r
     long long* row = bits + s * (uint64_t)m;
     for (int j = 0; j < m; ++j) row[j] = (long long)((lo >> (m - 1 - j)) & 1ull);
   }
+}
+
+// idx -> (shots, m) int64 bit rows, column 0 = most significant bit (sampling.py:529-531)
+__global__ void __launch_bounds__(256)
+k_unpack_bits(const long long* __restrict__ idx, const uint64_t shots, const int m,
+              long long* __restrict__ bits) {
+  const uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= shots) return;
+  const unsigned long long v = (unsigned long long)idx[s];
+  long long* row = bits + s * (uint64_t)m;
+  for (int j = 0; j < m; ++j) row[j] = (long long)((v >> (m - 1 - j)) & 1ull);
 }
 
 // NaN scan (sampling.py:322-325: NaN probabilities -> all-zero samples, no exception)

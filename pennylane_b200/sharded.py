@@ -1,0 +1,917 @@
+"""Statevector sharded over ``G = 2**g`` ranks (one process per GPU) — SURVEY.md section 8(e).
+
+north_star: "the statevector is partitioned across the GPUs by the high-order qubit bits, and
+gates on global qubits trigger qubit-remapping swaps via NCCL send/recv over NVLink".  The
+reference has no analogue (default.qubit holds one numpy array; its only multi-worker mode is a
+process pool over independent tapes, default_qubit.py:810-829).
+
+Layout.  The flat index of default.qubit's state (initialize_state.py:43-44) has one bit per
+wire: *logical* bit ``b = n-1-wire``.  A host-side permutation ``phys[b]`` sends logical bits to
+*physical* bits; physical bits ``0..nl-1`` (``nl = n-g``) index the rank's shard, physical bits
+``nl..n-1`` are the rank id.  Every rank holds ``2**nl`` amplitudes per batch element.
+
+Gates.  A gate needs no communication when every wire it acts on *non-diagonally* is local:
+controls and diagonal factors on rank bits are resolved on the host (``specialise``): the rank
+either skips the gate, drops the control, or flips the sign of the angle — the shard then sees an
+ordinary gate on ``nl`` wires and the single-GPU engine (fused segments included) runs it
+unchanged.  When a non-diagonal target sits on a rank bit the planner (``plan``) inserts a
+*remap*: ``k`` rank bits are exchanged with the top ``k`` local bits.  With that choice the data
+a rank sends to each of its ``2**k - 1`` partners is one contiguous slice of its shard and what
+it receives lands in the very same slice, so the exchange is in place: grouped
+``isend``/``irecv`` (``ncclSend``/``ncclRecv`` under ``torch.distributed``) through a bounded
+staging buffer; nothing the size of a second shard is allocated.  Victims are chosen Belady-style
+(the local bits whose next non-diagonal use is furthest away) and moved to the top local
+positions with ordinary SWAP gates that ride in the preceding fused segment.
+
+Reductions.  Pauli-sum expectation values: every rank evaluates the terms whose X/Y factors are
+local (Z factors on rank bits are signs), partial sums are all-gathered and added in rank order
+(bit-identical run to run); terms that flip a rank bit are measured after one more remap.
+Marginal probabilities: local marginals placed by rank bits, same ordered sum.  Sampling: the map
+is first restored to the identity, so rank ``r`` holds the logical indices
+``[r 2**nl, (r+1) 2**nl)``; numpy's pairwise ``sum`` is the same tree over ranks, the sequential
+``cumsum`` carries its running value from rank to rank, and ``searchsorted`` is the sum over
+ranks of local counts — samples stay bit-identical to sampling.py:500-531 under a fixed seed.
+
+The numerical work is done by a *local engine* (``CudaEngine`` below: a ``StateVector`` and the
+C ABI).  The class is written against the small engine interface so that the host logic (plan,
+maps, exchanges, reductions) is testable under ``gloo`` on CPU with a test-only engine; the
+product constructs ``CudaEngine`` only and never falls back.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import ops as _ops
+
+# ---------------------------------------------------------------------------------------------
+# which wires of an operator must be local?
+# ---------------------------------------------------------------------------------------------
+_DIAG_NAMES = {"PauliZ", "S", "T", "CZ", "CCZ", "PhaseShift", "U1", "ControlledPhaseShift", "RZ",
+               "MultiRZ", "IsingZZ", "CRZ", "GlobalPhase", "Identity", "Barrier", "Snapshot",
+               "WireCut", "DiagonalQubitUnitary"}
+_FIXED_PHASE = {"PauliZ": -1.0 + 0j, "S": 1j, "T": np.exp(0.25j * np.pi), "CZ": -1.0 + 0j,
+                "CCZ": -1.0 + 0j}
+_CTRL_FIXED = {"CNOT": (1, "PauliX"), "Toffoli": (2, "PauliX"), "CY": (1, "PauliY"),
+               "CH": (1, "Hadamard"), "CSWAP": (1, "SWAP")}
+_CTRL_PARAM = {"CRX": "RX", "CRY": "RY", "CRot": "Rot"}
+
+
+def _is_generic_controlled(op) -> bool:
+    return (getattr(op, "base", None) is not None and len(getattr(op, "control_wires", ()) or ())
+            and (op.name.startswith("C(") or op.name == "ControlledQubitUnitary"))
+
+
+def op_locality(op):
+    """(must_local, may_be_global): wires the operator acts on non-diagonally / only as a
+    control or a diagonal factor."""
+    name = op.name
+    wires = list(op.wires)
+    if name in _DIAG_NAMES:
+        return [], wires
+    if name == "PauliRot":
+        word = op.hyperparameters["pauli_word"]
+        must = [w for w, c in zip(wires, word) if c in "XY"]
+        return must, [w for w in wires if w not in must]
+    if name in _CTRL_FIXED:
+        nc = _CTRL_FIXED[name][0]
+        return wires[nc:], wires[:nc]
+    if name in _CTRL_PARAM:
+        return wires[1:], wires[:1]
+    if name == "MultiControlledX":
+        return wires[-1:], wires[:-1]
+    if _is_generic_controlled(op):
+        cw = list(op.control_wires)
+        return [w for w in wires if w not in cw], cw
+    return wires, []
+
+
+def _phase_on_ones(phase, local_wires, spare_wire):
+    """Multiply the subspace where all ``local_wires`` are 1 by ``phase`` (scalar or (B,))."""
+    phase = np.asarray(phase, dtype=complex)
+    one = np.ones_like(phase)
+    if not local_wires:
+        return _ops.DiagonalQubitUnitary(np.stack([phase, phase], axis=-1), wires=[spare_wire])
+    d = _ops.DiagonalQubitUnitary(np.stack([one, phase], axis=-1), wires=[local_wires[-1]])
+    if len(local_wires) == 1:
+        return d
+    return _ops.Controlled(d, list(local_wires[:-1]))
+
+
+def specialise(op, gvals: dict, wmap: dict, spare_wire=0):
+    """The operator a rank applies to its shard: ``gvals`` maps the operator's wires that sit on
+    rank bits to this rank's bit value, ``wmap`` maps the others to local wire labels.  Returns
+    ``None`` when the gate is the identity on this rank."""
+    name = op.name
+    wires = list(op.wires)
+    if name in ("Identity", "Barrier", "Snapshot", "WireCut"):
+        return None
+    if not any(w in gvals for w in wires):
+        return op.map_wires(wmap)
+    loc = [wmap[w] for w in wires if w not in gvals]
+    if name == "GlobalPhase":
+        new = op.map_wires(wmap)
+        new.wires = tuple(loc)
+        return new
+    if name in _FIXED_PHASE or name in ("PhaseShift", "U1", "ControlledPhaseShift"):
+        if any(gvals[w] == 0 for w in wires if w in gvals):
+            return None
+        ph = _FIXED_PHASE[name] if name in _FIXED_PHASE else np.exp(1j * np.asarray(op.data[0], dtype=float))
+        return _phase_on_ones(ph, loc, spare_wire)
+    if name in ("RZ", "MultiRZ", "IsingZZ"):
+        sign = -1.0 if sum(gvals[w] for w in wires if w in gvals) & 1 else 1.0
+        th = sign * np.asarray(op.data[0], dtype=float)
+        if not loc:
+            return _phase_on_ones(np.exp(-0.5j * th), [], spare_wire)
+        return _ops.RZ(th, wires=loc[0]) if len(loc) == 1 else _ops.MultiRZ(th, wires=loc)
+    if name == "CRZ":
+        c, t = wires
+        th = np.asarray(op.data[0], dtype=float)
+        if c in gvals:
+            if gvals[c] == 0:
+                return None
+            return specialise(_ops.RZ(th, wires=t), gvals, wmap, spare_wire)
+        sign = -1.0 if gvals[t] else 1.0
+        return _phase_on_ones(np.exp(-0.5j * sign * th), [wmap[c]], spare_wire)
+    if name == "PauliRot":
+        word = op.hyperparameters["pauli_word"]
+        sign, lw, lword = 1.0, [], ""
+        for w, ch in zip(wires, word):
+            if w in gvals:
+                if ch in "XY":
+                    raise ValueError("PauliRot with an X/Y factor on a rank bit needs a remap")
+                if ch == "Z" and gvals[w]:
+                    sign = -sign
+            else:
+                lw.append(wmap[w]); lword += ch
+        th = sign * np.asarray(op.data[0], dtype=float)
+        if not lw or all(ch == "I" for ch in lword):
+            return _phase_on_ones(np.exp(-0.5j * th), [], spare_wire)
+        return _ops.PauliRot(th, lword, wires=lw)
+    if name == "DiagonalQubitUnitary":
+        D = np.asarray(op.data[0], dtype=complex)
+        k = len(wires)
+        batched = D.ndim == 2
+        sub = D.reshape((D.shape[0],) * batched + (2,) * k)
+        # index the rank-bit axes, highest axis first so the remaining positions stay valid
+        for ax in reversed(range(k)):
+            if wires[ax] in gvals:
+                sub = np.take(sub, gvals[wires[ax]], axis=ax + batched)
+        if not loc:
+            ph = sub.reshape(-1) if batched else sub.reshape(())
+            return _phase_on_ones(ph, [], spare_wire)
+        return _ops.DiagonalQubitUnitary(sub.reshape((D.shape[0], -1) if batched else (-1,)), wires=loc)
+    if name in _CTRL_FIXED or name in _CTRL_PARAM:
+        nc = _CTRL_FIXED[name][0] if name in _CTRL_FIXED else 1
+        cw, tw = wires[:nc], wires[nc:]
+        if any(gvals.get(w, 1) == 0 for w in cw):
+            return None
+        rem = [wmap[w] for w in cw if w not in gvals]
+        base_cls = getattr(_ops, _CTRL_FIXED[name][1] if name in _CTRL_FIXED else _CTRL_PARAM[name])
+        base = base_cls(*op.data, wires=[wmap[w] for w in tw])
+        if not rem:
+            return base
+        if name == "Toffoli" and len(rem) == 1:
+            return _ops.CNOT(wires=rem + [wmap[tw[0]]])
+        return _ops.Controlled(base, rem)
+    if name == "MultiControlledX":
+        cw, cv = wires[:-1], [int(bool(v)) for v in op.control_values]
+        if any(w in gvals and gvals[w] != v for w, v in zip(cw, cv)):
+            return None
+        rem = [(wmap[w], v) for w, v in zip(cw, cv) if w not in gvals]
+        t = wmap[wires[-1]]
+        if not rem:
+            return _ops.PauliX(wires=t)
+        return _ops.MultiControlledX(wires=[w for w, _ in rem] + [t], control_values=[v for _, v in rem])
+    if _is_generic_controlled(op):
+        cw = list(op.control_wires)
+        cv = [int(bool(v)) for v in op.control_values]
+        if any(w in gvals and gvals[w] != v for w, v in zip(cw, cv)):
+            return None
+        base = op.base.map_wires(wmap)
+        rem = [(wmap[w], v) for w, v in zip(cw, cv) if w not in gvals]
+        if not rem:
+            return base
+        return _ops.Controlled(base, [w for w, _ in rem], [v for _, v in rem])
+    raise ValueError(f"{name} acts non-diagonally on a rank bit: the planner must remap first")
+
+
+# ---------------------------------------------------------------------------------------------
+# planner
+# ---------------------------------------------------------------------------------------------
+@dataclass
+class RunStep:
+    ops: list                      # original operators (wire labels of the circuit)
+    phys: list                     # logical bit -> physical bit while these run
+    swaps: list = field(default_factory=list)   # (pa, pb): local physical-bit swaps AFTER the ops
+
+
+@dataclass
+class ExchangeStep:
+    rank_bits: list                # rank-bit indices (physical bit - nl), ascending
+    k: int                         # exchanged with local physical bits nl-k .. nl-1, in order
+
+
+def _next_use(ops_, start, n, bit_of):
+    """For every logical bit: index of the first operator at or after ``start`` that needs it
+    local (len(ops_) + something if never)."""
+    nxt = [len(ops_) + 1 + b for b in range(n)]         # stable tie-break
+    seen = set()
+    for i in range(start, len(ops_)):
+        must, _ = op_locality(ops_[i])
+        for w in must:
+            b = bit_of(w)
+            if b not in seen:
+                seen.add(b)
+                nxt[b] = i
+        if len(seen) == n:
+            break
+    return nxt
+
+
+def plan_remap(phys, nl, want_local, nxt):
+    """Choose the bits to exchange: returns (local swaps, ExchangeStep, new phys).
+
+    ``want_local``: logical bits that must become local now.  Every other rank-resident bit
+    whose next use precedes that of the best remaining victim comes along (one exchange of k
+    bits moves ``1 - 2**-k`` of the shard; k exchanges of one bit move ``k/2``)."""
+    n = len(phys)
+    phys = list(phys)
+    glob = [b for b in range(n) if phys[b] >= nl]
+    local = [b for b in range(n) if phys[b] < nl]
+    need = [b for b in want_local if phys[b] >= nl]
+    cand = sorted((b for b in local if b not in want_local), key=lambda b: -nxt[b])
+    incoming = list(need)
+    victims = cand[: len(incoming)]
+    if len(victims) < len(incoming):
+        raise ValueError("not enough local qubits to remap (gate wider than the shard?)")
+    rest_g = sorted((b for b in glob if b not in incoming), key=lambda b: nxt[b])
+    ci = len(victims)
+    for b in rest_g:
+        if ci < len(cand) and nxt[cand[ci]] > nxt[b]:
+            incoming.append(b); victims.append(cand[ci]); ci += 1
+    k = len(incoming)
+    # move the victims to the top k local positions
+    swaps = []
+    at = {phys[b]: b for b in range(n)}
+    top = list(range(nl - k, nl))
+    vict_set = set(victims)
+    free_top = [p for p in top if at[p] not in vict_set]
+    for v in victims:
+        if phys[v] >= nl - k:
+            continue
+        p, t = phys[v], free_top.pop()
+        other = at[t]
+        swaps.append((p, t))
+        phys[v], phys[other] = t, p
+        at[t], at[p] = v, other
+    incoming.sort(key=lambda b: phys[b])
+    rank_bits = [phys[b] - nl for b in incoming]
+    for i, b in enumerate(incoming):
+        slot = nl - k + i
+        v = at[slot]
+        phys[v], phys[b] = phys[b], slot
+    return swaps, ExchangeStep(rank_bits, k), phys
+
+
+def plan(ops_, n, g, phys=None, bit_of=None):
+    """Cut an operator list into run steps separated by exchanges.  Returns (steps, final phys).
+
+    List scheduling over the circuit's dependency order: a run step takes every operator that
+    is executable under the current map and not behind a blocked operator on any of its wires
+    (operators on disjoint wires commute), so one exchange is amortised over as many gates as
+    the dependencies allow — a layered ansatz costs about one exchange per layer, not one per
+    gate on a rank bit."""
+    nl = n - g
+    if bit_of is None:
+        bit_of = lambda w: n - 1 - int(w)            # noqa: E731
+    phys = list(range(n)) if phys is None else list(phys)
+    steps = []
+    remaining = list(ops_)
+    while remaining:
+        run, keep, blocked = [], [], set()
+        for op in remaining:
+            must, _ = op_locality(op)
+            allb = {bit_of(w) for w in op.wires}
+            if len(must) > nl:
+                raise ValueError(f"{op.name} acts on more qubits than one shard holds")
+            if (blocked & allb) or any(phys[bit_of(w)] >= nl for w in must):
+                blocked |= allb
+                keep.append(op)
+            else:
+                run.append(op)
+        if not keep:
+            steps.append(RunStep(run, list(phys)))
+            break
+        first_must = [bit_of(w) for w in op_locality(keep[0])[0]]
+        if not any(phys[b] >= nl for b in first_must):      # pragma: no cover - defensive
+            raise RuntimeError("sharded planner made no progress")
+        nxt = _next_use(keep, 0, n, bit_of)
+        swaps, ex, new_phys = plan_remap(phys, nl, first_must, nxt)
+        steps.append(RunStep(run, list(phys), swaps))
+        steps.append(ex)
+        phys, remaining = new_phys, keep
+    return steps, phys
+
+
+# ---------------------------------------------------------------------------------------------
+# the CUDA local engine
+# ---------------------------------------------------------------------------------------------
+class CudaEngine:
+    """Local engine over a :class:`~pennylane_b200.statevector.StateVector` (the product path)."""
+
+    def __init__(self, nl, dtype=np.complex128, batch=1, device=None, fusion=1):
+        from .statevector import StateVector
+
+        self.sv = StateVector(nl, dtype=dtype, batch=batch, device=device)
+        self.fusion = fusion
+
+    # -- state ---------------------------------------------------------------------------
+    n = property(lambda self: self.sv.n)
+    batch = property(lambda self: self.sv.batch)
+    data = property(lambda self: self.sv.data)
+    device = property(lambda self: self.sv.device)
+
+    def reset(self, index=None):
+        """|0..0> restricted to this shard: ``index`` = local index of the single 1 or None."""
+        self.sv.data.zero_()
+        if index is not None:
+            self.sv.reset(int(index))
+
+    def set_local_state(self, arr):
+        self.sv.set_state(arr)
+
+    def resize_batch(self, batch):
+        self.sv._resize_batch(batch)
+
+    # -- gates ---------------------------------------------------------------------------
+    def compile(self, local_ops):
+        if not self.fusion:
+            return ("ops", list(local_ops))
+        from .compiler import compile_ops
+
+        T, L = self.sv.default_tile()
+        return ("segs", compile_ops(local_ops, self.sv.n, level=self.fusion, T=T, L=L))
+
+    def run(self, handle):
+        kind, items = handle
+        if kind == "ops":
+            for op in items:
+                self.sv.apply_operation(op)
+            return len(items)
+        for seg in items:
+            self.sv.run_segment(seg)
+        return len(items)
+
+    # -- reductions ------------------------------------------------------------------------
+    def expval_terms(self, xs, zs, ys, cs):
+        """sum_t cs[t] <psi_local| P_t |psi_local> per batch element -> (B,) float64."""
+        from ._lib import check, f64_array, int_array, u64_array
+
+        sv = self.sv
+        w, wb = sv.workspace()
+        check(sv.lib.b200q_expval_pauli_sum(
+            sv.ptr, sv.n, sv.dtype_code, sv.batch, u64_array(xs), u64_array(zs),
+            int_array(ys) if ys else None, f64_array(cs), len(cs),
+            C.c_void_p(sv._scal.data_ptr()), w, wb, sv.stream))
+        return sv._scal[: sv.batch].cpu().numpy().copy()
+
+    def probs(self, local_wires):
+        """(B, 2**m) float64 marginal over local wires (host array)."""
+        return self.sv.probs_device(local_wires).cpu().numpy()
+
+    def probs_device(self, local_wires):
+        return self.sv.probs_device(local_wires)
+
+    # -- sampler building blocks (all on 2**m float64 device vectors) ---------------------------
+    def _scalar(self, value):
+        import torch
+
+        return torch.tensor([float(value)], dtype=torch.float64, device=self.sv.device)
+
+    def has_nan(self, p, m):
+        import torch
+        from ._lib import check
+
+        flag = torch.zeros(1, dtype=torch.int32, device=self.sv.device)
+        check(self.sv.lib.b200q_has_nan(C.c_void_p(p.data_ptr()), m, C.c_void_p(flag.data_ptr()),
+                                        self.sv.stream))
+        return bool(flag.item())
+
+    def np_sum(self, p, m):
+        from ._lib import check
+
+        need = ((1 << m) // 128 + (1 << m) // (128 * 2047) + 128) * 8 + (4 << 20)
+        w, wb = self.sv.workspace(need)
+        out = self._scalar(0.0)
+        check(self.sv.lib.b200q_np_sum(C.c_void_p(p.data_ptr()), m, C.c_void_p(out.data_ptr()), w, wb,
+                                       self.sv.stream))
+        return float(out.item())
+
+    def div_by(self, p, m, value):
+        from ._lib import check
+
+        d = self._scalar(value)
+        check(self.sv.lib.b200q_div_by(C.c_void_p(p.data_ptr()), m, C.c_void_p(d.data_ptr()),
+                                       self.sv.stream))
+
+    def cumsum(self, p, m, exact, carry):
+        """In-place inclusive cumsum starting from ``carry`` (None: start of the vector);
+        returns the last entry."""
+        from ._lib import check
+
+        need = ((1 << m) // 2048 + 128) * 8 + (4 << 20)
+        w, wb = self.sv.workspace(need)
+        c = None if carry is None else self._scalar(carry)
+        check(self.sv.lib.b200q_cumsum(C.c_void_p(p.data_ptr()), m, 0 if exact else 1,
+                                       None if c is None else C.c_void_p(c.data_ptr()), w, wb,
+                                       self.sv.stream))
+        return float(p[-1].item())
+
+    def search(self, cdf, m, u):
+        """Number of cdf entries <= u, per uniform (device int64 tensor)."""
+        import torch
+        from ._lib import check
+
+        ud = torch.from_numpy(np.ascontiguousarray(u, dtype=np.float64)).to(self.sv.device)
+        out = torch.empty(len(u), dtype=torch.int64, device=self.sv.device)
+        check(self.sv.lib.b200q_search(C.c_void_p(cdf.data_ptr()), m, C.c_void_p(ud.data_ptr()),
+                                       len(u), C.c_void_p(out.data_ptr()), self.sv.stream))
+        return out
+
+    def unpack_bits(self, idx, m):
+        import torch
+        from ._lib import check
+
+        bits = torch.empty((idx.numel(), m), dtype=torch.int64, device=idx.device)
+        check(self.sv.lib.b200q_unpack_bits(C.c_void_p(idx.data_ptr()), idx.numel(), m,
+                                            C.c_void_p(bits.data_ptr()), self.sv.stream))
+        return bits.cpu().numpy()
+
+    def sample_replicated(self, probs_host, shots, rng, exact):
+        """Single-GPU sampler on a (small) probability vector every rank holds."""
+        import torch
+        from ._lib import check
+
+        sv = self.sv
+        m = int(np.log2(probs_host.size))
+        p = torch.from_numpy(np.ascontiguousarray(probs_host, dtype=np.float64)).to(sv.device)
+        u = torch.from_numpy(rng.random(shots)).to(sv.device)
+        bits = torch.empty((shots, m), dtype=torch.int64, device=sv.device)
+        flags = torch.zeros(1, dtype=torch.int32, device=sv.device)
+        need = ((1 << m) // 128 + (1 << m) // (128 * 2047) + 128) * 8 + (4 << 20)
+        w, wb = sv.workspace(need)
+        check(sv.lib.b200q_sample(C.c_void_p(p.data_ptr()), m, C.c_void_p(u.data_ptr()), shots,
+                                  0 if exact else 1, None, C.c_void_p(bits.data_ptr()),
+                                  C.c_void_p(sv._scal.data_ptr()), C.c_void_p(flags.data_ptr()),
+                                  w, wb, sv.stream))
+        norm = float(sv._scal[0].item())
+        if int(flags.item()):
+            return np.zeros((shots, m), dtype=np.int64)
+        if abs(norm - 1.0) > 1e-6:
+            raise ValueError("probabilities do not sum to 1")
+        return bits.cpu().numpy()
+
+    def synchronize(self):
+        import torch
+
+        torch.cuda.synchronize(self.sv.device)
+
+
+# ---------------------------------------------------------------------------------------------
+# the sharded statevector
+# ---------------------------------------------------------------------------------------------
+class ShardedStateVector:
+    """``2**n`` amplitudes over ``dist.get_world_size()`` ranks (a power of two)."""
+
+    def __init__(self, num_wires, dist, engine=None, dtype=np.complex128, batch=1, device=None,
+                 fusion=1, stage_bytes=1 << 30, group=None):
+        self.dist = dist
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        g = self.world.bit_length() - 1
+        if (1 << g) != self.world:
+            raise ValueError("the number of ranks must be a power of two")
+        self.n, self.g, self.nl = int(num_wires), g, int(num_wires) - g
+        if self.nl < 1:
+            raise ValueError("fewer than one local qubit per rank")
+        self.engine = engine if engine is not None else CudaEngine(self.nl, dtype, batch, device,
+                                                                   fusion)
+        self.phys = list(range(self.n))
+        self.stage_bytes = int(stage_bytes)
+        self._stage = None
+        self.stats = {"exchanges": 0, "exchange_bytes": 0, "run_steps": 0, "sweeps": 0}
+        self.reset()
+
+    # -- bookkeeping ---------------------------------------------------------------------------
+    def bit_of(self, wire):
+        return self.n - 1 - int(wire)
+
+    @property
+    def batch(self):
+        return self.engine.batch
+
+    def rank_bit(self, j, rank=None):
+        return ((self.rank if rank is None else rank) >> j) & 1
+
+    def _maps(self, phys, wires):
+        """(gvals, wmap) of ``wires`` under ``phys`` for this rank."""
+        gvals, wmap = {}, {}
+        for w in wires:
+            p = phys[self.bit_of(w)]
+            if p >= self.nl:
+                gvals[w] = self.rank_bit(p - self.nl)
+            else:
+                wmap[w] = self.nl - 1 - p
+        return gvals, wmap
+
+    def reset(self):
+        """|0...0>."""
+        self.phys = list(range(self.n))
+        self.engine.reset(0 if self.rank == 0 else None)
+
+    def set_state(self, full_state):
+        """Every rank passes the same full host vector ((2**n,), (2,)*n or batched)."""
+        self.phys = list(range(self.n))
+        arr = np.asarray(full_state)
+        dim = 1 << self.n
+        flat = arr.reshape(-1, dim)
+        ln = 1 << self.nl
+        self.engine.set_local_state(flat[:, self.rank * ln:(self.rank + 1) * ln])
+
+    # -- gates -------------------------------------------------------------------------------
+    def localise(self, step: RunStep):
+        """Run step -> operators on local wire labels for THIS rank."""
+        out = []
+        for op in step.ops:
+            gvals, wmap = self._maps(step.phys, op.wires)
+            loc = specialise(op, gvals, wmap, spare_wire=0)
+            if loc is not None:
+                out.append(loc)
+        for pa, pb in step.swaps:
+            out.append(_ops.SWAP(wires=[self.nl - 1 - pa, self.nl - 1 - pb]))
+        return out
+
+    def compile(self, ops_):
+        """Plan + per-rank lowering.  Returns a program to pass to :meth:`run`; the current
+        map is consumed (a program is valid for the map it was compiled from)."""
+        steps, final = plan(ops_, self.n, self.g, self.phys, self.bit_of)
+        prog = []
+        for st in steps:
+            if isinstance(st, RunStep):
+                lops = self.localise(st)
+                prog.append(("run", self.engine.compile(lops) if lops else None))
+            else:
+                prog.append(("exchange", st))
+        return {"steps": prog, "start": list(self.phys), "final": final,
+                "n_exchanges": sum(1 for k, _ in prog if k == "exchange")}
+
+    def run(self, program):
+        if program["start"] != self.phys:
+            raise ValueError("program compiled for another qubit map")
+        for kind, item in program["steps"]:
+            if kind == "run":
+                if item is not None:
+                    self.stats["sweeps"] += self.engine.run(item)
+                self.stats["run_steps"] += 1
+            else:
+                self.exchange(item)
+        self.phys = list(program["final"])
+
+    def apply_operations(self, ops_):
+        bs = [getattr(o, "batch_size", None) for o in ops_]
+        bs = [b for b in bs if b is not None]
+        if bs and self.engine.batch == 1 and bs[0] != 1:
+            self.engine.resize_batch(bs[0])
+        self.run(self.compile(list(ops_)))
+
+    # -- the exchange --------------------------------------------------------------------------
+    def exchange(self, ex: ExchangeStep):
+        """Swap rank bits ``ex.rank_bits`` with local physical bits ``nl-k .. nl-1``."""
+        import torch
+
+        dist, k = self.dist, ex.k
+        data = self.engine.data                      # (B, 2**nl)
+        B = data.shape[0]
+        chunk = 1 << (self.nl - k)
+        q = 0
+        for i, rb in enumerate(ex.rank_bits):
+            q |= self.rank_bit(rb) << i
+        partners = []
+        for j in range(1 << k):
+            if j == q:
+                continue
+            r = self.rank
+            for i, rb in enumerate(ex.rank_bits):
+                r = (r & ~(1 << rb)) | (((j >> i) & 1) << rb)
+            partners.append((j, r))
+        itemsize = data.element_size()
+        per_partner = max(1, self.stage_bytes // (itemsize * len(partners)))
+        piece = min(chunk, 1 << (per_partner.bit_length() - 1))
+        if self._stage is None or self._stage.numel() < piece * len(partners) or \
+                self._stage.dtype != data.dtype:
+            self._stage = torch.empty(piece * len(partners), dtype=data.dtype, device=data.device)
+        for b in range(B):
+            row = data[b]
+            for off in range(0, chunk, piece):
+                p2p = []
+                for s, (j, r) in enumerate(partners):
+                    mine = row[j * chunk + off: j * chunk + off + piece]
+                    stage = self._stage[s * piece:(s + 1) * piece]
+                    gr = r if self.group is None else dist.get_global_rank(self.group, r)
+                    p2p.append(dist.P2POp(dist.isend, mine, gr, self.group))
+                    p2p.append(dist.P2POp(dist.irecv, stage, gr, self.group))
+                for req in dist.batch_isend_irecv(p2p):
+                    req.wait()
+                for s, (j, r) in enumerate(partners):
+                    row[j * chunk + off: j * chunk + off + piece].copy_(
+                        self._stage[s * piece:(s + 1) * piece])
+        self.stats["exchanges"] += 1
+        self.stats["exchange_bytes"] += B * chunk * len(partners) * itemsize
+
+    def remap(self, want_local_bits, nxt=None):
+        """Make the given logical bits local (one exchange at most)."""
+        if all(self.phys[b] < self.nl for b in want_local_bits):
+            return
+        if nxt is None:
+            nxt = [2 * self.n - b for b in range(self.n)]
+            for b in want_local_bits:
+                nxt[b] = 0
+        swaps, ex, new_phys = plan_remap(self.phys, self.nl, list(want_local_bits), nxt)
+        self._run_swaps(swaps)
+        self.exchange(ex)
+        self.phys = new_phys
+
+    def _run_swaps(self, swaps):
+        if not swaps:
+            return
+        lops = [_ops.SWAP(wires=[self.nl - 1 - a, self.nl - 1 - b]) for a, b in swaps]
+        self.stats["sweeps"] += self.engine.run(self.engine.compile(lops))
+
+    def restore_identity_map(self):
+        """Bring every logical bit back to its own physical position (needed before sampling:
+        the CDF must run over logical indices).  At most two exchanges + one local permutation."""
+        n, nl = self.n, self.nl
+        for _ in range(3):
+            at = {self.phys[b]: b for b in range(n)}
+            wrong = [p for p in range(nl, n) if at[p] != p]
+            if not wrong:
+                break
+            if any(self.phys[p] >= nl for p in wrong):
+                # a rightful owner sits on another rank position: park every misplaced
+                # occupant on local bits first, the next pass brings the owners in
+                self._exchange_exact([(at[p], None) for p in wrong])
+            else:
+                self._exchange_exact([(at[p], p) for p in wrong])
+        # local permutation by transpositions
+        swaps = []
+        phys = list(self.phys)
+        at = {phys[b]: b for b in range(n)}
+        for p in range(nl):
+            if at[p] != p:
+                src = phys[p]                       # where logical p currently lives
+                other = at[p]
+                swaps.append((src, p))
+                phys[p], phys[other] = p, src
+                at[p], at[src] = p, other
+        self._run_swaps(swaps)
+        self.phys = phys
+        assert self.phys == list(range(n)), self.phys
+
+    def _exchange_exact(self, pairs):
+        """Exchange the rank-resident logical bits ``b`` of ``pairs`` = [(b, want)] with local
+        bits: ``want`` = logical bit that must take b's rank position (None: any victim)."""
+        n, nl = self.n, self.nl
+        k = len(pairs)
+        phys = list(self.phys)
+        at = {phys[b]: b for b in range(n)}
+        pairs = sorted(pairs, key=lambda t: phys[t[0]])
+        fixed = {w for _, w in pairs if w is not None}
+        spare = [b for b in range(n) if phys[b] < nl and b not in fixed and b < nl]
+        spare.sort(key=lambda b: -phys[b])
+        victims = [w if w is not None else spare.pop(0) for _, w in pairs]
+        # victims[i] must sit at local position nl-k+i
+        swaps = []
+        for i, v in enumerate(victims):
+            t = nl - k + i
+            if phys[v] != t:
+                other = at[t]
+                swaps.append((phys[v], t))
+                pv = phys[v]
+                phys[v], phys[other] = t, pv
+                at[t], at[pv] = v, other
+        self._run_swaps(swaps)
+        ex = ExchangeStep([phys[b] - nl for b, _ in pairs], k)
+        self.exchange(ex)
+        for i, (b, _) in enumerate(pairs):
+            v = victims[i]
+            phys[v], phys[b] = phys[b], nl - k + i
+        self.phys = phys
+
+    # -- reductions ----------------------------------------------------------------------------
+    def _ordered_sum(self, local):
+        """Sum of per-rank float64 arrays in rank order (deterministic)."""
+        import torch
+
+        t = torch.from_numpy(np.ascontiguousarray(local, dtype=np.float64).reshape(-1))
+        dev = self.engine.data.device
+        t = t.to(dev)
+        out = [torch.empty_like(t) for _ in range(self.world)]
+        self.dist.all_gather(out, t, group=self.group)
+        acc = out[0].cpu().numpy().copy()
+        for o in out[1:]:
+            acc = acc + o.cpu().numpy()
+        return acc.reshape(np.shape(local))
+
+    def expval_pauli_sentence(self, ps):
+        """<psi| sum_t c_t P_t |psi> (float, or (B,) when batched)."""
+        terms = []
+        for word, coeff in ps.items():
+            xb = [self.bit_of(w) for w, ch in word.items() if ch in "XY"]
+            zb = [self.bit_of(w) for w, ch in word.items() if ch in "ZY"]
+            ny = sum(1 for ch in word.values() if ch == "Y")
+            terms.append((xb, zb, ny, float(np.real(coeff))))
+        total = np.zeros(self.batch)
+        pending = terms
+        guard = 0
+        while pending:
+            now = [t for t in pending if all(self.phys[b] < self.nl for b in t[0])]
+            later = [t for t in pending if not all(self.phys[b] < self.nl for b in t[0])]
+            if now:
+                xs, zs, ys, cs = [], [], [], []
+                for xb, zb, ny, c in now:
+                    xm = zm = 0
+                    sign = 1.0
+                    for b in xb:
+                        xm |= 1 << self.phys[b]
+                    for b in zb:
+                        p = self.phys[b]
+                        if p < self.nl:
+                            zm |= 1 << p
+                        elif self.rank_bit(p - self.nl):
+                            sign = -sign
+                    xs.append(xm); zs.append(zm); ys.append(ny); cs.append(sign * c)
+                total = total + self._ordered_sum(self.engine.expval_terms(xs, zs, ys, cs))
+            if later:
+                guard += 1
+                if guard > 4 * self.n:
+                    raise RuntimeError("expval remapping made no progress")   # pragma: no cover
+                first = later[0]
+                flips = {}
+                for xb, _, _, _ in later:
+                    for b in xb:
+                        flips[b] = flips.get(b, 0) + 1
+                # victims: local bits that few pending terms flip, never one the first pending
+                # term flips (so that term is measured next pass: guaranteed progress); other
+                # rank-resident flip bits come along when a cheaper victim exists
+                nxt = [-flips.get(b, 0) for b in range(self.n)]
+                for b in first[0]:
+                    nxt[b] = -10**6
+                self.remap([b for b in first[0] if self.phys[b] >= self.nl], nxt)
+            pending = later
+        return total if self.batch > 1 else float(total[0])
+
+    def probs(self, wires=None):
+        """Marginal probabilities over ``wires`` in the given order (every rank gets the full
+        2**m vector; m is assumed small — use :meth:`sample` for all-wire sampling)."""
+        wires = list(range(self.n)) if wires is None else list(wires)
+        m = len(wires)
+        loc = [(i, w) for i, w in enumerate(wires) if self.phys[self.bit_of(w)] < self.nl]
+        glo = [(i, w) for i, w in enumerate(wires) if self.phys[self.bit_of(w)] >= self.nl]
+        lw = [self.nl - 1 - self.phys[self.bit_of(w)] for _, w in loc]
+        pl = self.engine.probs(lw) if lw else None
+        if pl is None:
+            pl = self.engine.probs([0]).sum(axis=-1, keepdims=True)
+        B = pl.shape[0]
+        full = np.zeros((B,) + (2,) * m)
+        idx = [slice(None)] * (m + 1)
+        for i, w in glo:
+            idx[i + 1] = self.rank_bit(self.phys[self.bit_of(w)] - self.nl)
+        sub = pl.reshape((B,) + (2,) * len(loc))
+        # axes of `sub` follow `loc` order, which is the order of the remaining axes of `full`
+        full[tuple(idx)] = sub
+        out = self._ordered_sum(full.reshape(B, -1))
+        return out if B > 1 else out[0]
+
+    def norm2(self):
+        xs, zs, ys, cs = [0], [0], [0], [1.0]
+        r = self._ordered_sum(self.engine.expval_terms(xs, zs, ys, cs))
+        return r if self.batch > 1 else float(r[0])
+
+    # -- sampling ------------------------------------------------------------------------------
+    def sample(self, shots, rng, wires=None, exact=True):
+        """(shots, m) int64 samples, bit-identical on every rank and to sampling.py:500-531 under
+        the same Generator state (every rank must hold an identically seeded ``rng``)."""
+        import torch
+
+        if self.batch != 1:
+            raise NotImplementedError("sharded sampling of broadcast states")
+        wires_all = list(range(self.n))
+        if wires is not None and list(wires) != wires_all:
+            p = self.probs(wires)
+            return self.engine.sample_replicated(p, shots, rng, exact)
+        self.restore_identity_map()
+        eng, dist, nl = self.engine, self.dist, self.nl
+        p = eng.probs_device(list(range(nl)))[0]
+        u = rng.random(shots)
+        nan = np.array([1.0 if eng.has_nan(p, nl) else 0.0])
+        if self._ordered_sum(nan)[0] > 0:
+            return np.zeros((shots, self.n), dtype=np.int64)       # sampling.py:322-325
+        # norm = probs.sum(): numpy's pairwise tree = same tree over the per-rank sums
+        sums = self._gather_scalar(eng.np_sum(p, nl))
+        while len(sums) > 1:
+            sums = [sums[i] + sums[i + 1] for i in range(0, len(sums), 2)]
+        norm = float(sums[0])
+        if abs(norm - 1.0) > 1e-6:                                  # sampling.py:514-519
+            raise ValueError("probabilities do not sum to 1")
+        eng.div_by(p, nl, norm)
+        # cdf = probs.cumsum(): the running value travels from rank to rank
+        dev = p.device
+        carry = None
+        if self.rank > 0:
+            t = torch.zeros(1, dtype=torch.float64, device=dev)
+            dist.recv(t, self._grank(self.rank - 1), group=self.group)
+            carry = float(t.item())
+        last = eng.cumsum(p, nl, bool(exact), carry)
+        if self.rank + 1 < self.world:
+            dist.send(torch.tensor([last], dtype=torch.float64, device=dev),
+                      self._grank(self.rank + 1), group=self.group)
+        total = self._gather_scalar(last)[-1]
+        eng.div_by(p, nl, total)                                    # cdf /= cdf[-1]
+        cnt = eng.search(p, nl, u)
+        dist.all_reduce(cnt, group=self.group)                      # int64 sum: exact
+        return eng.unpack_bits(cnt, self.n)
+
+    def _grank(self, r):
+        return r if self.group is None else self.dist.get_global_rank(self.group, r)
+
+    def _gather_scalar(self, x):
+        import torch
+
+        dev = self.engine.data.device
+        t = torch.tensor([float(x)], dtype=torch.float64, device=dev)
+        out = [torch.empty_like(t) for _ in range(self.world)]
+        self.dist.all_gather(out, t, group=self.group)
+        return [float(o.item()) for o in out]
+
+    # -- host copy (tests / small states) ---------------------------------------------------------
+    def to_numpy(self):
+        """Full state in LOGICAL order on every rank ((B, 2**n) or (2**n,)).  Small states only."""
+        import torch
+
+        data = self.engine.data
+        out = [torch.empty_like(data) for _ in range(self.world)]
+        self.dist.all_gather(out, data.contiguous(), group=self.group)
+        B = data.shape[0]
+        phys_state = torch.stack(out, dim=1).cpu().numpy().reshape(B, 1 << self.n)
+        # axis order of the physical index, MSB first: physical bit n-1 .. 0
+        arr = phys_state.reshape((B,) + (2,) * self.n)
+        # logical bit b lives on physical bit phys[b] -> numpy axis (n-1-phys[b]) + 1
+        axes = [0] + [1 + (self.n - 1 - self.phys[b]) for b in range(self.n - 1, -1, -1)]
+        logical = arr.transpose(axes).reshape(B, 1 << self.n)
+        return logical if B > 1 else logical[0]
+
+
+# ---------------------------------------------------------------------------------------------
+# circuit level
+# ---------------------------------------------------------------------------------------------
+def simulate_sharded(circuit, dist, rng=None, dtype=np.complex128, engine=None, fusion=1,
+                     exact_sampling=True, device=None, return_state=False):
+    """The sharded mirror of simulate.py:308-393 for a tape in standard wire order: gate loop,
+    then expval (Pauli observables) / probs analytically, or sample() with shots."""
+    circuit = circuit.map_to_standard_wires()
+    n = circuit.num_wires
+    ops_ = list(circuit.operations)
+    sv = ShardedStateVector(n, dist, engine=engine, dtype=dtype, device=device, fusion=fusion)
+    if ops_ and hasattr(ops_[0], "state_vector"):
+        sv.set_state(np.asarray(ops_[0].state_vector(wire_order=list(range(n)))))
+        ops_ = ops_[1:]
+    if ops_:
+        sv.apply_operations(ops_)
+    results = []
+    if circuit.shots:
+        rng = np.random.default_rng(rng)
+        # measure_with_samples (sampling.py:276-335): one all-wire sampling, then per-measurement
+        # post-processing of the sample matrix
+        if any(mp.obs is not None for mp in circuit.measurements):
+            raise NotImplementedError("sharded finite-shot measurement of an observable")
+        wires = list(range(n))
+        samples = sv.sample(circuit.shots.total_shots, rng, None, exact_sampling)
+        for mp in circuit.measurements:
+            results.append(mp.process_samples(samples, wires))
+    else:
+        for mp in circuit.measurements:
+            if mp.kind == "expval" and getattr(mp.obs, "pauli_rep", None) is not None:
+                r = sv.expval_pauli_sentence(mp.obs.pauli_rep)
+                results.append(np.float64(r) if np.ndim(r) == 0 else r)
+            elif mp.kind == "probs" and mp.obs is None:
+                results.append(sv.probs(list(mp.wires) if len(mp.wires) else None))
+            elif mp.kind == "state":
+                results.append(sv.to_numpy())
+            else:
+                raise NotImplementedError(f"sharded measurement {mp.kind} of {mp.obs}")
+    res = results[0] if len(results) == 1 else tuple(results)
+    return (res, sv) if return_state else res
