@@ -1,0 +1,150 @@
+"""Multi-GPU arm of bench.py (`--gpus N` under torchrun): the statevector sharded over N ranks.
+
+Weak scaling: `args.qubits + log2(N)` qubits, i.e. the same 16 GiB shard per GPU as the 1-GPU
+workload; the circuit is the same hardware-efficient ansatz (8 layers, expval(Z0)).  One step =
+reset + the whole circuit (fused segments on every shard + the qubit-remapping exchanges over
+NVLink) + the expectation value.  Timed on the device with CUDA events between barriers, max over
+ranks.  Besides the contract keys the line carries the split of the step into shard-local sweeps
+(HBM roofline) and exchanges (NVLink: bytes sent per GPU / time, against the 770 GB/s measured
+peer-copy figure of B200_PROFILING.md).
+"""
+from __future__ import annotations
+
+import json
+import os
+import time
+
+import numpy as np
+
+
+def run_sharded(args, dist, rank, world, local_rank):
+    import torch
+
+    import pennylane_b200 as qb
+    from bench import ROOT, ClockSampler, hea_ops, workload_config
+    from pennylane_b200 import ops as q
+    from pennylane_b200.sharded import ShardedStateVector, simulate_sharded
+
+    g = world.bit_length() - 1
+    n = args.qubits + g
+    ops_ = hea_ops(n, args.layers)
+    ngates = len(ops_)
+    obs = q.PauliZ(wires=0)
+    fusion = args.fusion_level if args.fusion == "on" else 0
+    sv = ShardedStateVector(n, dist, dtype=np.complex128, fusion=fusion)
+    program = sv.compile(ops_)
+    S_loc = 16.0 * (1 << sv.nl)
+
+    records = []
+
+    def timer(kind, fn):
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = fn()
+        e1.record()
+        records.append((kind, e0, e1, r if kind == "run" else 0))
+        return r
+
+    def step():
+        sv.reset()
+        sv.run(program)
+        return sv.expval_pauli_sentence(obs.pauli_rep)
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    dist.barrier()
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    sv.timer = timer
+    sv.stats = {k: 0 for k in sv.stats}
+    start = torch.cuda.Event(enable_timing=True); end = torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    dist.barrier()
+    start.record()
+    val = None
+    for _ in range(args.steps):
+        val = step()
+    end.record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    sv.timer = None
+    ms = torch.tensor([start.elapsed_time(end)], dtype=torch.float64, device="cuda")
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    total_ms = float(ms.item())
+    ms_per_step = total_ms / args.steps
+    clk = clocks.stop()
+
+    run_s = sum(a.elapsed_time(b) for k, a, b, _ in records if k == "run") * 1e-3
+    ex_s = sum(a.elapsed_time(b) for k, a, b, _ in records if k == "exchange") * 1e-3
+    sweeps = sum(c for k, _, _, c in records if k == "run")
+    ex_bytes = sv.stats["exchange_bytes"]
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    hbm = sweeps * 2.0 * S_loc / run_s / 1e9 if run_s > 0 else None
+
+    # e2e: the public sharded entry point, host parameters in / host scalar out, wall clock
+    par = np.random.default_rng(3).uniform(0, 2 * np.pi, (args.layers, n, 2))
+
+    def e2e_step():
+        ops2 = []
+        for l in range(args.layers):
+            for w in range(n):
+                ops2.append(q.RY(float(par[l, w, 0]), wires=w))
+                ops2.append(q.RZ(float(par[l, w, 1]), wires=w))
+            for w in range(n):
+                ops2.append(q.CNOT(wires=[w, (w + 1) % n]))
+        tape = qb.QuantumScript(ops2, [qb.expval(q.PauliZ(wires=0))])
+        return simulate_sharded(tape, dist, fusion=fusion)
+
+    del sv, program
+    torch.cuda.empty_cache()
+    e2e_step()
+    torch.cuda.synchronize(); dist.barrier()
+    k2 = max(1, min(args.steps, 2))
+    t0 = time.perf_counter()
+    for _ in range(k2):
+        r = e2e_step()
+    torch.cuda.synchronize(); dist.barrier()
+    e2e_s = torch.tensor([(time.perf_counter() - t0) / k2], dtype=torch.float64, device="cuda")
+    dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_s = float(e2e_s.item())
+    assert abs(float(r) - float(val)) < 1e-9, (r, val)
+
+    if rank == 0:
+        cfg = workload_config(args, n)
+        cfg["shard_bytes"] = int(S_loc)
+        line = {
+            "metric": "gates_per_s", "value": ngates / (ms_per_step * 1e-3), "unit": "gates/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "c128",
+            "data": "synthetic", "config": cfg, "expval": float(val),
+            "state_sweeps_per_step": sweeps // args.steps,
+            "roofline": {"bound": "hbm", "kernel": "k_rtile<double,4,1,256,2> (fused segment on each shard: 2*S_loc per launch)",
+                         "achieved": hbm, "peak": peak, "unit": "GB/s",
+                         "frac": (hbm / peak) if hbm else None, "traffic": None,
+                         "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
+                         "share_of_step": run_s / (total_ms * 1e-3)},
+            "exchange": {"per_step": sv_stats_per_step(ex_bytes, args.steps),
+                         "count_per_step": sum(1 for k, *_ in records if k == "exchange") // args.steps,
+                         "seconds_per_step": ex_s / args.steps,
+                         "sent_gbps_per_gpu": ex_bytes / ex_s / 1e9 if ex_s > 0 else None,
+                         "nvlink_peak_gbps": 770.0, "peak_source": "B200_PROFILING.md measured peer copy, per direction",
+                         "frac": (ex_bytes / ex_s / 1e9 / 770.0) if ex_s > 0 else None,
+                         "share_of_step": ex_s / (total_ms * 1e-3)},
+            "cpu_baseline": None,
+            "e2e": {"value": ngates / e2e_s, "unit": "gates/s", "seconds_per_step": e2e_s,
+                    "h2d_bytes_per_step": int(world * 64 * ngates), "d2h_bytes_per_step": 8 * world},
+            "gpu_launches": int((sweeps + 3 * args.steps) * world), "clocks": clk,
+        }
+        print(json.dumps(line))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def sv_stats_per_step(nbytes, steps):
+    return {"bytes_sent_per_gpu": int(nbytes // max(1, steps))}

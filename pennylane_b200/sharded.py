@@ -336,9 +336,10 @@ class CudaEngine:
 
     def reset(self, index=None):
         """|0..0> restricted to this shard: ``index`` = local index of the single 1 or None."""
-        self.sv.data.zero_()
         if index is not None:
             self.sv.reset(int(index))
+        else:
+            self.sv.data.zero_()           # cudaMemset: a shard that holds no basis-state 1
 
     def set_local_state(self, arr):
         self.sv.set_state(arr)
@@ -504,6 +505,7 @@ class ShardedStateVector:
         self.stage_bytes = int(stage_bytes)
         self._stage = None
         self.stats = {"exchanges": 0, "exchange_bytes": 0, "run_steps": 0, "sweeps": 0}
+        self.timer = None          # optional: callable(kind, fn) -> fn() (bench.py times steps)
         self.reset()
 
     # -- bookkeeping ---------------------------------------------------------------------------
@@ -575,8 +577,13 @@ class ShardedStateVector:
         for kind, item in program["steps"]:
             if kind == "run":
                 if item is not None:
-                    self.stats["sweeps"] += self.engine.run(item)
+                    if self.timer is not None:
+                        self.stats["sweeps"] += self.timer("run", lambda: self.engine.run(item))
+                    else:
+                        self.stats["sweeps"] += self.engine.run(item)
                 self.stats["run_steps"] += 1
+            elif self.timer is not None:
+                self.timer("exchange", lambda: self.exchange(item))
             else:
                 self.exchange(item)
         self.phys = list(program["final"])
