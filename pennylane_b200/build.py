@@ -12,13 +12,14 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(CSRC, "libb200q.so")
-SOURCES = ["api.cu"]
+SOURCES = ["api.cu", "rtile.cu"]          # compiled in parallel, one object each
 HEADERS = ["common.cuh", "gates.cuh", "measure.cuh", "sample.cuh", "adjoint.cuh", "tile.cuh",
-           "rtile.cuh", os.path.join("..", "..", "include", "b200q.h")]
+           "rtile.cuh", "rtile_host.h", os.path.join("..", "..", "include", "b200q.h")]
+OBJDIR = os.path.join(CSRC, "build")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
-    "-O3", "-lineinfo", "-std=c++17", "--shared",
+    "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC",
 ]
 
@@ -44,16 +45,42 @@ def needs_build() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return OUT
-    cmd = [_nvcc(), *NVCC_FLAGS, *[os.path.join(CSRC, s) for s in SOURCES], "-o", OUT]
+    from concurrent.futures import ThreadPoolExecutor
+
+    os.makedirs(OBJDIR, exist_ok=True)
+    nvcc = _nvcc()
+
+    def compile_one(src):
+        obj = os.path.join(OBJDIR, os.path.splitext(src)[0] + ".o")
+        srcp = os.path.join(CSRC, src)
+        deps = [srcp] + [os.path.join(CSRC, h) for h in HEADERS]
+        if not force and os.path.exists(obj) and all(
+                os.path.getmtime(d) <= os.path.getmtime(obj) for d in deps if os.path.exists(d)) \
+                and src not in _always_rebuild(obj):
+            return obj, ""
+        cmd = [nvcc, *NVCC_FLAGS, "-c", srcp, "-o", obj]
+        if verbose:
+            cmd[1:1] = ["-Xptxas", "-v"]
+        res = subprocess.run(cmd, capture_output=True, text=True, cwd=CSRC)
+        if res.returncode != 0:
+            raise RuntimeError(f"nvcc failed:\n{' '.join(cmd)}\n{res.stdout}\n{res.stderr}")
+        return obj, res.stderr
+
+    with ThreadPoolExecutor(max_workers=len(SOURCES)) as pool:
+        results = list(pool.map(compile_one, SOURCES))
     if verbose:
-        cmd.insert(1, "-Xptxas")
-        cmd.insert(2, "-v")
+        for _, log in results:
+            print(log)
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "--shared", "-Xcompiler", "-fPIC",
+           *[o for o, _ in results], "-o", OUT]
     res = subprocess.run(cmd, capture_output=True, text=True, cwd=CSRC)
     if res.returncode != 0:
-        raise RuntimeError(f"nvcc failed:\n{' '.join(cmd)}\n{res.stdout}\n{res.stderr}")
-    if verbose:
-        print(res.stderr)
+        raise RuntimeError(f"link failed:\n{' '.join(cmd)}\n{res.stdout}\n{res.stderr}")
     return OUT
+
+
+def _always_rebuild(obj):
+    return ()
 
 
 if __name__ == "__main__":

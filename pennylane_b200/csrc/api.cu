@@ -12,7 +12,7 @@
 #include "measure.cuh"
 #include "sample.cuh"
 #include "tile.cuh"
-#include "rtile.cuh"
+#include "rtile_host.h"
 
 namespace b200q {
 
@@ -37,8 +37,6 @@ int sm_count() {
   return cached;
 }
 
-static const size_t kWorkBytes = 32ull << 20;      // 32 MiB scratch
-static const size_t kTermRegion = 4ull << 20;      // first 4 MiB: uploaded term tables
 static const int kReduceCtasPerSm = 4;
 
 // every reduction kernel runs with exactly this many CTAs so partial rows have one stride
@@ -474,127 +472,6 @@ static int tile_t(void* state, int n, int64_t batch, const int* tile_bits, int T
                                                   (const double2*)(w + moff));
   B200Q_LAUNCH_CHECK();
   return 0;
-}
-
-// geometry of the register-tiled kernel: (dtype, nvec) -> (T, RB, THREADS)
-static int rtile_variant() {
-  // tuning knob, read once: 0 = 256 threads x 2 CTAs/SM (default: measured 2120 gates/s on the
-  // 30-qubit ansatz), 1 = register-pipelined 1 CTA/SM (1550 gates/s: 8 warps cannot hide the
-  // FP64 latency)
-  static int variant = -1;
-  if (variant < 0) { const char* e = getenv("B200Q_RT_VARIANT"); variant = e ? atoi(e) : 0; }
-  return variant;
-}
-
-static void rtile_geom(int dtype, int nvec, int& T, int& RB, int& threads) {
-  if (nvec <= 1) {
-    threads = 256; RB = dtype == B200Q_C128 ? 4 : 5;
-  } else { threads = 512; RB = dtype == B200Q_C128 ? 3 : 4; }
-  T = (threads == 256 ? 8 : 9) + RB;
-}
-
-template <typename T, int RB, int NV, int THREADS, int MINB, bool PFREG = false>
-static int rtile_launch(void* v0, void* v1, const RtArgs& a, int64_t batch, const RtOp* ops_dev,
-                        const double2* mats_dev, int nslots, double scale, double* out_dev,
-                        double* partials, size_t partial_cap, cudaStream_t s) {
-  const size_t smem = ((size_t)NV * sizeof(cx<T>) << a.T) + sizeof(cx<T>) * ((a.nmat + 1) & ~1) +
-                      (size_t)a.nops * sizeof(RtOp) + (size_t)((2 << RB) + 2 * THREADS) * sizeof(unsigned long long) +
-                      (size_t)nslots * (THREADS / 32) * sizeof(double);
-  B200Q_REQUIRE(smem <= 227 * 1024, "rtile: %zu bytes of shared memory needed (%d ops, %d slots)",
-                smem, a.nops, nslots);
-  static bool attr_set = false;
-  if (!attr_set) {
-    B200Q_CHECK(cudaFuncSetAttribute(k_rtile<T, RB, NV, THREADS, MINB, PFREG>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
-  }
-  uint64_t per_sm = std::max<uint64_t>(1, std::min<uint64_t>(MINB, (227 * 1024) / smem));
-  if (const char* e = getenv("B200Q_RT_CTAS")) per_sm = std::max(1, atoi(e));   // tuning knob
-  const uint64_t cap = (uint64_t)sm_count() * per_sm;
-  dim3 grid((unsigned)std::min<uint64_t>(a.ntiles, cap), (unsigned)batch);
-  if (nslots > 0)
-    B200Q_REQUIRE((size_t)batch * nslots * grid.x <= partial_cap, "rtile: workspace too small for %d slots",
-                  nslots);
-  k_rtile<T, RB, NV, THREADS, MINB, PFREG><<<grid, THREADS, smem, s>>>(
-      a, (cx<T>*)v0, (cx<T>*)v1, ops_dev, mats_dev, 0, partials);
-  B200Q_LAUNCH_CHECK();
-  if (nslots > 0) {
-    k_final_reduce<<<(unsigned)(batch * nslots), 256, 0, s>>>(partials, out_dev, (int)grid.x, 1,
-                                                                (int)(batch * nslots), scale);
-    B200Q_LAUNCH_CHECK();
-  }
-  return 0;
-}
-
-static int rtile_dispatch(void* v0, void* v1, int n, int dtype, int64_t batch, const int* tile_bits,
-                          int Tn, int L, const RtOp* ops_host, int nops, const double2* mats_host,
-                          int nmat, int nslots, int write0, uint64_t base_hi, double scale,
-                          double* out_dev, void* work, size_t work_bytes, cudaStream_t s) {
-  int gT, gRB, gTh;
-  rtile_geom(dtype, v1 ? 2 : 1, gT, gRB, gTh);
-  B200Q_REQUIRE(Tn == gT && Tn <= n && L >= 0 && L <= Tn, "rtile: T=%d (need %d) L=%d n=%d", Tn, gT, L, n);
-  B200Q_REQUIRE(nops >= 1 && nops <= 2048 && nmat >= 0 && nslots >= 0, "rtile: bad nops=%d nmat=%d", nops, nmat);
-  B200Q_REQUIRE(ops_host[0].kind == RT_ROUND, "rtile: the first record must be a round");
-  B200Q_REQUIRE(nslots == 0 || (v1 && out_dev), "rtile: generator slots need a bra and an output");
-  RtArgs a;
-  memset(&a, 0, sizeof(a));
-  a.n = n; a.T = Tn; a.L = L; a.nops = nops; a.nmat = nmat; a.nslots = nslots; a.write0 = write0;
-  a.base_hi = base_hi;
-  {
-    static int pf = -1;                      // tuning knob, read once
-    if (pf < 0) { const char* e = getenv("B200Q_RT_PREFETCH"); pf = e ? atoi(e) : 0; }
-    a.prefetch = pf;
-  }
-  for (int i = 0; i < nops; ++i) {
-    if (ops_host[i].kind == RT_ROUND) {
-      a.last_round = i;
-      uint32_t seen = 0;
-      const int tb = Tn - gRB;
-      for (int b = 0; b < gRB; ++b) seen |= 1u << ops_host[i].u.r.rbits[b];
-      for (int b = 0; b < tb; ++b) seen |= 1u << ops_host[i].u.r.tbits[b];
-      B200Q_REQUIRE(seen == (1u << Tn) - 1u, "rtile: round %d is not a permutation of the tile bits", i);
-    }
-  }
-  uint64_t inmask = 0;
-  for (int i = 0; i < Tn; ++i) {
-    const int b = tile_bits[i];
-    B200Q_REQUIRE(b >= 0 && b < n && !((inmask >> b) & 1), "rtile: bad tile bit %d", b);
-    B200Q_REQUIRE(i < L ? b == i : (i == 0 || b > tile_bits[i - 1]),
-                  "rtile: bits must be ascending with the first L equal to 0..L-1");
-    inmask |= 1ull << b;
-    if (i >= L) a.hi_bits[i - L] = (int8_t)b;
-  }
-  int no = 0;
-  for (int b = 0; b < n; ++b)
-    if (!((inmask >> b) & 1)) a.out_bits[no++] = (int8_t)b;
-  a.ntiles = 1ull << (n - Tn);
-  const size_t ops_bytes = (size_t)nops * sizeof(RtOp);
-  const size_t mat_bytes = (size_t)nmat * sizeof(double2);
-  B200Q_REQUIRE(work && ops_bytes + mat_bytes + 512 <= kTermRegion && work_bytes >= kWorkBytes,
-                "rtile: segment tables too large for the workspace");
-  char* w = (char*)work;
-  B200Q_CHECK(cudaMemcpyAsync(w, ops_host, ops_bytes, cudaMemcpyHostToDevice, s));
-  const size_t moff = (ops_bytes + 255) & ~(size_t)255;
-  if (nmat) B200Q_CHECK(cudaMemcpyAsync(w + moff, mats_host, mat_bytes, cudaMemcpyHostToDevice, s));
-  double* partials = (double*)(w + kTermRegion);
-  const size_t pcap = (work_bytes - kTermRegion) / sizeof(double);
-  const RtOp* od = (const RtOp*)w;
-  const double2* md = (const double2*)(w + moff);
-  const int variant = rtile_variant();
-  if (dtype == B200Q_C128) {
-    if (!v1 && variant == 1)
-      return rtile_launch<double, 4, 1, 256, 1, true>(v0, v1, a, batch, od, md, nslots, scale, out_dev, partials, pcap, s);
-    if (!v1) return rtile_launch<double, 4, 1, 256, 2>(v0, v1, a, batch, od, md, nslots, scale, out_dev, partials, pcap, s);
-    return rtile_launch<double, 3, 2, 512, 1>(v0, v1, a, batch, od, md, nslots, scale, out_dev, partials, pcap, s);
-  }
-  if (dtype == B200Q_C64) {
-    if (!v1 && variant == 1)
-      return rtile_launch<float, 5, 1, 256, 1, true>(v0, v1, a, batch, od, md, nslots, scale, out_dev, partials, pcap, s);
-    if (!v1) return rtile_launch<float, 5, 1, 256, 2>(v0, v1, a, batch, od, md, nslots, scale, out_dev, partials, pcap, s);
-    return rtile_launch<float, 4, 2, 512, 1>(v0, v1, a, batch, od, md, nslots, scale, out_dev, partials, pcap, s);
-  }
-  set_error("unknown dtype %d", dtype);
-  return 2;
 }
 
 }  // namespace b200q

@@ -78,10 +78,12 @@ struct RtArgs {
   int n, T, L, nops, nmat, nslots;
   int write0;                    // write vector 0 back (adjoint passes over several bras)
   int last_round;                // index of the last RT_ROUND record
-  int prefetch;                  // L2 prefetch of the CTA's next tile: bytes per prefetch
-                                 // instruction (0 = off)
+  int nrounds;                   // number of RT_ROUND records
+  int prefetch;                  // 1: the CTA's next tile is brought into the (idle) transpose
+                                 // buffer with bulk async copies while the last round computes
+  int nruns;                     // runs of consecutive non-tile bits (tile number -> base)
   int8_t hi_bits[16];            // global positions of tile positions L..T-1 (ascending)
-  int8_t out_bits[B200Q_MAX_BITS];   // ascending global positions of the n-T non-tile bits
+  int8_t run_s[16], run_len[16], run_g[16];   // tile-number bits [s, s+len) -> global bits [g, g+len)
   unsigned long long ntiles;     // 2^(n-T)
   unsigned long long base_hi;    // OR-ed into the tile base for "external" predicates
                                  // (the rank's global-qubit bits when the state is sharded)
@@ -101,10 +103,45 @@ __device__ __forceinline__ unsigned long long rt_gscatter(unsigned j, const RtAr
   return off;
 }
 
-// PFREG: software pipelining through registers — the loads of the CTA's NEXT tile are issued
-// (into a second register set) before the gates of the current tile run, so HBM latency hides
-// behind the FP64 work of the same CTA (one CTA per SM, up to 255 registers per thread).
-template <typename T_, int RB, int NV, int THREADS, bool PFREG = false>
+// ---- bulk async copy (TMA engine, 1-D) + mbarrier helpers --------------------------------
+__device__ __forceinline__ unsigned rt_smem_u32(const void* p) {
+  return (unsigned)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void rt_mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(rt_smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void rt_mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(rt_smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void rt_mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "RT_WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra RT_DONE_%=;\n"
+      "bra RT_WAIT_%=;\n"
+      "RT_DONE_%=:\n"
+      "}\n" ::"r"(rt_smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void rt_bulk_g2s(void* dst_smem, const void* src_gmem, unsigned bytes,
+                                            unsigned long long* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          rt_smem_u32(dst_smem)),
+      "l"(src_gmem), "r"(bytes), "r"(rt_smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void rt_fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+template <typename T_, int RB, int NV, int THREADS>
 struct RtKernel {
   static constexpr int NA = 1 << RB;
   static constexpr int TB = (THREADS == 128) ? 7 : (THREADS == 256) ? 8 : (THREADS == 512) ? 9 : 10;
@@ -260,32 +297,140 @@ struct RtKernel {
     if constexpr (RB > 4) { if (mask & 16u) flip_ket<4>(A); }
   }
 
+  // ---- single-qubit dense blocks with the matrix PINNED in registers -------------------------
+  // The interpreter's first version re-read the 2x2 matrix from shared memory for every
+  // amplitude pair (4 LDS.128 per 16 FP64 instructions; ncu: LDS 12 % of issued instructions,
+  // short-scoreboard the second stall reason).  Here the matrix is read once per record (or
+  // once per control half) into 8 registers and the 2^(RB-1) pairs run back to back as
+  // independent FMA chains.
+  //   d1_uniform: the same matrix for every pair of this thread (no control on a register bit);
+  //   d1_regctl : one control on register bit CB — pairs with that bit clear use m_b0, pairs
+  //               with it set use m_b1 (nullptr: leave those pairs untouched).
+
+  // Scheduling fences: the amplitudes are "touched" by an empty volatile asm, so the front end
+  // cannot hoist or common work across this point.  Without them the 2^(RB-1) independent
+  // pairs of a record are software-pipelined so deep that the kernel wants 194 registers and,
+  // at the 128-register cap of 2 CTAs/SM, spills amplitudes and re-shuffles the whole register
+  // file at every control-flow merge of the interpreter (checked with -Xptxas -v / nvdisasm).
+  static __device__ __forceinline__ void sfence(C& a, C& b, C& c, C& d) {
+    if constexpr (sizeof(T_) == 8)
+      asm volatile("" : "+d"(a.x), "+d"(a.y), "+d"(b.x), "+d"(b.y), "+d"(c.x), "+d"(c.y), "+d"(d.x), "+d"(d.y));
+    else
+      asm volatile("" : "+f"(a.x), "+f"(a.y), "+f"(b.x), "+f"(b.y), "+f"(c.x), "+f"(c.y), "+f"(d.x), "+f"(d.y));
+  }
+  static __device__ __forceinline__ void sfence_all(C (&A)[NV][NA]) {
+#pragma unroll
+    for (int v = 0; v < NV; ++v)
+#pragma unroll
+      for (int k = 0; k < NA; k += 4) sfence(A[v][k], A[v][k + 1], A[v][k + 2], A[v][k + 3]);
+  }
+
+  template <int Q>
+  static __device__ __forceinline__ void d1_uniform(C (&A)[NV][NA], const C* __restrict__ m) {
+    const C M[4] = {m[0], m[1], m[2], m[3]};
+    int cnt = 0;
+#pragma unroll
+    for (int k = 0; k < NA; ++k) {
+      if ((k >> Q) & 1) continue;
+      const int ix[2] = {k, k | (1 << Q)};
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        if ((cnt++ % 2) == 0) sfence_all(A);
+        matvec_inplace<2>(A[v], ix, M);
+      }
+    }
+  }
+
+  template <int Q, int CB, int BV>
+  static __device__ __forceinline__ void d1_half(C (&A)[NV][NA], const C* __restrict__ m) {
+    const C M[4] = {m[0], m[1], m[2], m[3]};
+    int cnt = 0;
+#pragma unroll
+    for (int k = 0; k < NA; ++k) {
+      if (((k >> Q) & 1) || (((k >> CB) & 1) != BV)) continue;
+      const int ix[2] = {k, k | (1 << Q)};
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        if ((cnt++ % 2) == 0) sfence_all(A);
+        matvec_inplace<2>(A[v], ix, M);
+      }
+    }
+  }
+
+  template <int Q, int CB>
+  static __device__ __forceinline__ void d1_regctl(C (&A)[NV][NA], const C* __restrict__ m_b0,
+                                                   const C* __restrict__ m_b1) {
+    if constexpr (Q != CB && Q < RB && CB < RB) {
+      if (m_b0) d1_half<Q, CB, 0>(A, m_b0);
+      if (m_b1) d1_half<Q, CB, 1>(A, m_b1);
+    }
+  }
+
+  // tile number -> global offset of the tile (scatter over the non-tile bits, run by run)
+  static __device__ __forceinline__ unsigned long long tile_base(const RtArgs& a,
+                                                                 const unsigned long long t) {
+    unsigned long long base = 0;
+    for (int r = 0; r < a.nruns; ++r)
+      base |= ((t >> a.run_s[r]) & ((1ull << a.run_len[r]) - 1ull)) << a.run_g[r];
+    return base;
+  }
+
+  // bring tile `t` of every vector into the (currently idle) transpose buffer: one bulk async
+  // copy per contiguous run of 2^L amplitudes, completion counted on `bar`
+  static __device__ __forceinline__ void issue_tile_copies(const RtArgs& a, C* vec0, C* vec1,
+                                                           C* tile, const unsigned long long t,
+                                                           unsigned long long* bar) {
+    const unsigned tsize = 1u << a.T;
+    const unsigned run = 1u << a.L;
+    const unsigned long long base = tile_base(a, t);
+    for (unsigned j = threadIdx.x; j < (tsize >> a.L) * NV; j += THREADS) {
+      const unsigned v = j >> (a.T - a.L), r = j & ((tsize >> a.L) - 1u);
+      rt_bulk_g2s(tile + (size_t)v * tsize + ((size_t)r << a.L),
+                  (v ? vec1 : vec0) + base + rt_gscatter(r << a.L, a), run * (unsigned)sizeof(C),
+                  bar);
+    }
+  }
+
   static __device__ __forceinline__ void run(const RtArgs& __restrict__ a, C* __restrict__ v0,
                                              C* __restrict__ v1, const RtOp* __restrict__ ops_g,
                                              const double2* __restrict__ mats_g,
                                              const long long mat_bstride,
                                              double* __restrict__ partials) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     const unsigned tsize = 1u << a.T;
     C* tile = reinterpret_cast<C*>(smem_raw);                                  // NV * 2^T
     C* mats = tile + (size_t)NV * tsize;                                        // nmat (padded even)
     RtOp* ops = reinterpret_cast<RtOp*>(mats + ((a.nmat + 1) & ~1));            // nops
     unsigned long long* koff = reinterpret_cast<unsigned long long*>(ops + a.nops);  // 2 * NA
     unsigned long long* toff = koff + 2 * NA;                                   // 2 * THREADS
-    double* accs = reinterpret_cast<double*>(toff + 2 * THREADS);               // nslots * NW
+    unsigned long long* bar = toff + 2 * THREADS;                               // 2 (one used)
+    double* accs = reinterpret_cast<double*>(bar + 2);                          // nslots * NW
+    unsigned short* tsl = reinterpret_cast<unsigned short*>(accs + a.nslots * NW);   // nrounds * THREADS
+    unsigned short* rsl = tsl + (size_t)a.nrounds * THREADS;                    // nrounds * 8
+    unsigned short* ldsl = rsl + (size_t)a.nrounds * 8;                         // THREADS + NA: round-0
+                                                                                // layout, unswizzled
     const unsigned tid = threadIdx.x;
 
     const double2* mg = mats_g + (long long)blockIdx.y * mat_bstride;
     for (int i = tid; i < a.nmat; i += THREADS) mats[i] = make_cx<T_>((T_)mg[i].x, (T_)mg[i].y);
     for (int i = tid; i < a.nops; i += THREADS) ops[i] = ops_g[i];
     for (int i = tid; i < a.nslots * NW; i += THREADS) accs[i] = 0.0;
+    if (tid == 0) rt_mbar_init(bar, 1);
+    __syncthreads();
+    if (tid == 0) {                    // number the rounds: q0 of a ROUND record = its index
+      int r = 0;
+      for (int i = 0; i < a.nops; ++i)
+        if ((ops[i].kind & 0xff) == RT_ROUND) ops[i].q0 = r++;
+    }
     __syncthreads();
 
-    C* vec[2] = {v0 + ((unsigned long long)blockIdx.y << a.n),
-                 NV > 1 ? v1 + ((unsigned long long)blockIdx.y << a.n) : nullptr};
+    C* const vec[2] = {v0 + ((unsigned long long)blockIdx.y << a.n),
+                       NV > 1 ? v1 + ((unsigned long long)blockIdx.y << a.n) : nullptr};
 
-    // global offsets of the first (load) and last (store) round layouts are tile independent:
-    // the per-thread parts live in shared memory (toff), the per-register-index parts too (koff)
+    // Per-CTA tables.  Global offsets of the first (load) and last (store) round layouts are
+    // tile independent: per-thread parts in toff, per-register-index parts in koff.  The
+    // swizzled shared-memory slot of every (round, thread) and (round, register bit) is
+    // computed once here instead of once per tile and round.
     {
       const RtOp& f = ops[0];
       const RtOp& l = ops[a.last_round];
@@ -296,63 +441,62 @@ struct RtKernel {
       }
       toff[tid] = rt_gscatter(tj, a);
       toff[THREADS + tid] = rt_gscatter(tl, a);
+      ldsl[tid] = (unsigned short)tj;
       if (tid < 2 * NA) {
         const RtOp& r = tid < NA ? f : l;
         const unsigned k = tid & (NA - 1);
         unsigned j = 0;
         for (int b = 0; b < RB; ++b) j |= ((k >> b) & 1u) << r.u.r.rbits[b];
         koff[tid] = rt_gscatter(j, a);
+        if (tid < NA) ldsl[THREADS + tid] = (unsigned short)j;
+      }
+      for (int i = 0; i < a.nops; ++i) {
+        const RtOp& r = ops[i];
+        if ((r.kind & 0xff) != RT_ROUND) continue;
+        unsigned t2 = 0;
+        for (int b = 0; b < TB; ++b) t2 |= ((tid >> b) & 1u) << r.u.r.tbits[b];
+        tsl[r.q0 * THREADS + tid] = (unsigned short)(t2 ^ rt_sw<SWW>(t2));
+        if (tid < RB) {
+          const unsigned rj = 1u << r.u.r.rbits[tid];
+          rsl[r.q0 * 8 + tid] = (unsigned short)(rj ^ rt_sw<SWW>(rj));
+        }
       }
     }
     __syncthreads();
-    // L2 prefetch granule (amplitudes), never longer than the contiguous run
-    const unsigned line_amps = (a.prefetch > 0 ? (unsigned)a.prefetch : 128u) / sizeof(C);
-    const unsigned pf_unit = (1u << a.L) < line_amps ? (1u << a.L) : line_amps;
+
+    const bool pf = a.prefetch != 0;
+    if (pf) {                          // prologue: the CTA's first tile
+      rt_fence_proxy_async();
+      if (tid == 0) rt_mbar_expect_tx(bar, (unsigned)(NV * tsize * sizeof(C)));
+      __syncthreads();
+      issue_tile_copies(a, vec[0], vec[1], tile, blockIdx.x, bar);
+    }
+    unsigned phase = 0;
 
     C A[NV][NA];
-    C B[PFREG ? NV : 1][PFREG ? NA : 1];
-    if (PFREG && blockIdx.x < (unsigned)a.ntiles) {
-      unsigned long long b0 = 0;
-      for (int b = 0; b < a.n - a.T; ++b)
-        b0 |= (unsigned long long)((blockIdx.x >> b) & 1u) << a.out_bits[b];
-#pragma unroll
-      for (int v = 0; v < NV; ++v) {
-        const C* src = vec[v] + b0 + toff[tid];
-#pragma unroll
-        for (int k = 0; k < NA; ++k) A[v][k] = src[koff[k]];
-      }
-    }
 
-    for (unsigned t = blockIdx.x; t < (unsigned)a.ntiles; t += gridDim.x) {
-      unsigned long long base = 0;
-      for (int b = 0; b < a.n - a.T; ++b) base |= (unsigned long long)((t >> b) & 1u) << a.out_bits[b];
-
-      // ---- optional: prefetch the CTA's next tile into L2 --------------------------------
-      if (a.prefetch && t + gridDim.x < (unsigned)a.ntiles) {
-        const unsigned tn = t + gridDim.x;
-        unsigned long long bn = 0;
-        for (int b = 0; b < a.n - a.T; ++b) bn |= (unsigned long long)((tn >> b) & 1u) << a.out_bits[b];
-        for (unsigned u = tid * pf_unit; u < tsize; u += THREADS * pf_unit) {
-          const unsigned long long g = bn | rt_gscatter(u, a);
-#pragma unroll
-          for (int v = 0; v < NV; ++v) asm volatile("prefetch.global.L2 [%0];" ::"l"(vec[v] + g));
-        }
-      }
+    for (unsigned long long t = blockIdx.x; t < a.ntiles; t += gridDim.x) {
+      const unsigned long long base = tile_base(a, t);
+      const unsigned long long baseE = base | a.base_hi;
+      const bool more = t + gridDim.x < a.ntiles;
+      bool issued = false;             // next tile's copies already in flight
 
       // ---- load (round 0 layout) ------------------------------------------------------------
-      if (PFREG) {
-        // issue the NEXT tile's loads now; they complete while this tile's gates run
-        if (t + gridDim.x < (unsigned)a.ntiles) {
-          const unsigned tn = t + gridDim.x;
-          unsigned long long bn = 0;
-          for (int b = 0; b < a.n - a.T; ++b)
-            bn |= (unsigned long long)((tn >> b) & 1u) << a.out_bits[b];
+      if (pf) {
+        rt_mbar_wait(bar, phase);
+        phase ^= 1u;
+        const unsigned tj = ldsl[tid];
 #pragma unroll
-          for (int v = 0; v < (PFREG ? NV : 1); ++v) {
-            const C* src = vec[v] + bn + toff[tid];
+        for (int v = 0; v < NV; ++v)
 #pragma unroll
-            for (int k = 0; k < (PFREG ? NA : 1); ++k) B[v][k] = src[koff[k]];
-          }
+          for (int k = 0; k < NA; ++k) A[v][k] = tile[v * tsize + (tj | ldsl[THREADS + k])];
+        if (a.last_round == 0 && more) {
+          // single-round segment: the buffer is idle for the whole compute phase
+          rt_fence_proxy_async();
+          if (tid == 0) rt_mbar_expect_tx(bar, (unsigned)(NV * tsize * sizeof(C)));
+          __syncthreads();
+          issue_tile_copies(a, vec[0], vec[1], tile, t + gridDim.x, bar);
+          issued = true;
         }
       } else {
 #pragma unroll
@@ -362,7 +506,7 @@ struct RtKernel {
           for (int k = 0; k < NA; ++k) A[v][k] = src[koff[k]];
         }
       }
-      int cur = 0;                     // index of the current round's record
+      int cur = 0;                     // round index (not record index) of the current layout
 
       for (int o = 1; o < a.nops; ++o) {
         const RtOp& op = ops[o];
@@ -370,13 +514,41 @@ struct RtKernel {
         if (kind <= RT_CX) {
           // ---- gates on register bits, with controls anywhere --------------------------------
           const RtGate& g = op.u.g;
-          const bool tsel = ((tid & g.ctrl_t) == g.cval_t) &&
-                            (((base | a.base_hi) & g.ctrl_e) == g.cval_e);
+          const bool tsel = ((tid & g.ctrl_t) == g.cval_t) && ((baseE & g.ctrl_e) == g.cval_e);
           const unsigned cr = g.ctrl_r, cv = g.cval_r;
           const bool has0 = (op.kind >> 8) & 1;
           const C* m = mats + op.mat_off;
           if (kind == RT_DENSE1) {
-            if (has0) {
+            if (cr == 0) {
+              const C* mm = tsel ? m : (has0 ? m + 4 : nullptr);
+              if (mm) {
+                switch (op.q0) {
+                  case 0: d1_uniform<0>(A, mm); break;
+                  case 1: if constexpr (RB > 1) d1_uniform<1>(A, mm); break;
+                  case 2: if constexpr (RB > 2) d1_uniform<2>(A, mm); break;
+                  case 3: if constexpr (RB > 3) d1_uniform<3>(A, mm); break;
+                  case 4: if constexpr (RB > 4) d1_uniform<4>(A, mm); break;
+                  default: break;
+                }
+              }
+            } else if ((cr & (cr - 1u)) == 0) {
+              // one control on a register bit: the matrix depends on that bit of k only
+              const int cb = __ffs((int)cr) - 1;
+              const C* ms = tsel ? m : (has0 ? m + 4 : nullptr);    // pairs whose control holds
+              const C* mo = has0 ? m + 4 : nullptr;                 // pairs whose control fails
+              const C* mb1 = cv ? ms : mo;
+              const C* mb0 = cv ? mo : ms;
+              switch (op.q0 * 8 + cb) {
+#define RT_D1C(Q, CB) case Q * 8 + CB: d1_regctl<Q, CB>(A, mb0, mb1); break;
+                RT_D1C(0, 1) RT_D1C(0, 2) RT_D1C(0, 3) RT_D1C(0, 4)
+                RT_D1C(1, 0) RT_D1C(1, 2) RT_D1C(1, 3) RT_D1C(1, 4)
+                RT_D1C(2, 0) RT_D1C(2, 1) RT_D1C(2, 3) RT_D1C(2, 4)
+                RT_D1C(3, 0) RT_D1C(3, 1) RT_D1C(3, 2) RT_D1C(3, 4)
+                RT_D1C(4, 0) RT_D1C(4, 1) RT_D1C(4, 2) RT_D1C(4, 3)
+#undef RT_D1C
+                default: break;
+              }
+            } else if (has0) {
               switch (op.q0) {
                 case 0: dense1<0, true>(A, m, tsel, cr, cv); break;
                 case 1: if constexpr (RB > 1) dense1<1, true>(A, m, tsel, cr, cv); break;
@@ -426,45 +598,37 @@ struct RtKernel {
           continue;
         }
         if (kind == RT_ROUND) {
-          // transpose through shared memory: store in the old layout, load in the new one.
-          // Both layouts are recomputed here from their records (nothing layout-related is
-          // kept in registers between rounds).
-          unsigned tslot, rsl[RB];
-          {
-            const RtOp& old = ops[cur];
-            unsigned tj = 0;
-            for (int b = 0; b < TB; ++b) tj |= ((tid >> b) & 1u) << old.u.r.tbits[b];
-            tslot = tj ^ rt_sw<SWW>(tj);
+          // transpose through shared memory: store in the old layout, load in the new one
+          // (slots come from the per-CTA tables)
+          const int nr = op.q0;
+          unsigned tslot = tsl[cur * THREADS + tid], rs[RB];
 #pragma unroll
-            for (int b = 0; b < RB; ++b) {
-              const unsigned rj = 1u << old.u.r.rbits[b];
-              rsl[b] = rj ^ rt_sw<SWW>(rj);
-            }
-          }
+          for (int b = 0; b < RB; ++b) rs[b] = rsl[cur * 8 + b];
           __syncthreads();
 #pragma unroll
           for (int v = 0; v < NV; ++v)
 #pragma unroll
-            for (int k = 0; k < NA; ++k) tile[v * tsize + (tslot ^ sel_xor(rsl, k))] = A[v][k];
-          {
-            unsigned tj = 0;
-            for (int b = 0; b < TB; ++b) tj |= ((tid >> b) & 1u) << op.u.r.tbits[b];
-            tslot = tj ^ rt_sw<SWW>(tj);
+            for (int k = 0; k < NA; ++k) tile[v * tsize + (tslot ^ sel_xor(rs, k))] = A[v][k];
+          tslot = tsl[nr * THREADS + tid];
 #pragma unroll
-            for (int b = 0; b < RB; ++b) {
-              const unsigned rj = 1u << op.u.r.rbits[b];
-              rsl[b] = rj ^ rt_sw<SWW>(rj);
-            }
-          }
+          for (int b = 0; b < RB; ++b) rs[b] = rsl[nr * 8 + b];
           __syncthreads();
 #pragma unroll
           for (int v = 0; v < NV; ++v)
 #pragma unroll
-            for (int k = 0; k < NA; ++k) A[v][k] = tile[v * tsize + (tslot ^ sel_xor(rsl, k))];
-          cur = o;
+            for (int k = 0; k < NA; ++k) A[v][k] = tile[v * tsize + (tslot ^ sel_xor(rs, k))];
+          cur = nr;
+          if (pf && o == a.last_round && more) {
+            // the buffer is idle from here to the next tile's first transposition: fetch the
+            // next tile into it while this tile's last round computes and stores
+            rt_fence_proxy_async();
+            if (tid == 0) rt_mbar_expect_tx(bar, (unsigned)(NV * tsize * sizeof(C)));
+            __syncthreads();
+            issue_tile_copies(a, vec[0], vec[1], tile, t + gridDim.x, bar);
+            issued = true;
+          }
           continue;
         }
-        const unsigned long long baseE = base | a.base_hi;
         if (kind == RT_PARITY) {
           const RtGate& g = op.u.g;
           if (((tid & g.ctrl_t) != g.cval_t) || ((baseE & g.ctrl_e) != g.cval_e)) continue;
@@ -538,12 +702,7 @@ struct RtKernel {
 #pragma unroll
         for (int k = 0; k < NA; ++k) dst[koff[NA + k]] = A[v][k];
       }
-      if (PFREG) {
-#pragma unroll
-        for (int v = 0; v < (PFREG ? NV : 1); ++v)
-#pragma unroll
-          for (int k = 0; k < (PFREG ? NA : 1); ++k) A[v][k] = B[v][k];
-      }
+      (void)issued;
     }
 
     if (a.nslots > 0) {
@@ -557,12 +716,12 @@ struct RtKernel {
   }
 };
 
-template <typename T_, int RB, int NV, int THREADS, int MINB, bool PFREG = false>
+template <typename T_, int RB, int NV, int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB)
 k_rtile(const __grid_constant__ RtArgs a, cx<T_>* __restrict__ v0, cx<T_>* __restrict__ v1,
         const RtOp* __restrict__ ops_g, const double2* __restrict__ mats_g,
         const long long mat_bstride, double* __restrict__ partials) {
-  RtKernel<T_, RB, NV, THREADS, PFREG>::run(a, v0, v1, ops_g, mats_g, mat_bstride, partials);
+  RtKernel<T_, RB, NV, THREADS>::run(a, v0, v1, ops_g, mats_g, mat_bstride, partials);
 }
 
 }  // namespace b200q
