@@ -12,9 +12,9 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(CSRC, "libb200q.so")
-SOURCES = ["api.cu", "rtile.cu"]          # compiled in parallel, one object each
+SOURCES = ["api.cu", "rtile.cu", "rtile_d.cu", "rtile_f.cu"]          # compiled in parallel, one object each
 HEADERS = ["common.cuh", "gates.cuh", "measure.cuh", "sample.cuh", "adjoint.cuh", "tile.cuh",
-           "rtile.cuh", "rtile_host.h", os.path.join("..", "..", "include", "b200q.h")]
+           "rtile.cuh", "rtile_host.h", "rtile_launch.cuh", os.path.join("..", "..", "include", "b200q.h")]
 OBJDIR = os.path.join(CSRC, "build")
 
 NVCC_FLAGS = [

@@ -26,6 +26,7 @@ import numpy as np
 
 DENSE1, DENSE2, CX, PARITY, DIAG, SWAP = 0, 1, 2, 3, 4, 5
 GENERIC = -1
+GEN = 7          # adjoint generator term (RT_GEN record); defined here for merge_blocks
 
 
 class TileOp(C.Structure):
@@ -58,6 +59,11 @@ class Prim:
     ny: int = 0                                      # GEN: number of Y factors
     coef: float = 0.0                                # GEN: real coefficient of the Pauli term
     zbits: list = field(default_factory=list)        # GEN: bits carrying Z or Y
+    seq: int = 0                                     # merge_blocks: stream position of the first
+                                                     # constituent of an accumulated block
+    pure_cx: bool = False                            # merge_blocks: block is exactly one CX so far
+    deferred: list = field(default_factory=list)     # merge_blocks: (GEN, 2x2 Pauli) evaluated
+                                                     # right after this block
 
     @property
     def bits(self):
@@ -188,6 +194,72 @@ def _embed(m1, pos):
     return np.kron(m1, np.eye(2)) if pos == 0 else np.kron(np.eye(2), m1)
 
 
+_PAULI_2x2 = {
+    "X": np.array([[0, 1], [1, 0]], dtype=complex),
+    "Y": np.array([[0, -1j], [1j, 0]], dtype=complex),
+    "Z": np.array([[1, 0], [0, -1]], dtype=complex),
+}
+
+
+def _commute(a, b) -> bool:
+    return bool(np.allclose(a @ b, b @ a, rtol=0, atol=1e-14))
+
+
+def _gen_single_bit(g: Prim):
+    """(bit, letter) when the generator term is a Pauli on exactly one bit, else None."""
+    bits = g.bits
+    if len(bits) != 1:
+        return None
+    (b,) = bits
+    x, z = b in g.targets, b in g.zbits
+    return b, ("Y" if x and z else "X" if x else "Z")
+
+
+def _place_generator(g: Prim, pending: dict, out: list) -> bool:
+    """Try to place a one-bit generator term without breaking up the pending block on its bit.
+
+    ``<bra|G|ket>`` is unchanged when the same unitary acts on bra and ket and G is conjugated
+    along, so the term may be evaluated (a) *before* a pending pure CNOT on its bit, conjugated
+    through it (Z_t -> Z_c Z_t, Y_t -> Z_c Y_t, X_t -> X_t), or (b) *after* the pending block,
+    as long as every gate merged into the block from now on commutes with it (RY with Y, any
+    diagonal with Z ...).  With both moves the reverse sweep of [RY, RZ, CNOT] on a wire stays
+    ONE controlled-select record with its two generator terms on either side, instead of three
+    records separated by inner products.  Returns False when neither move is valid."""
+    one = _gen_single_bit(g)
+    if one is None:
+        return False
+    b, letter = one
+    q = pending.get(b)
+    readers = [t for t in pending if b in pending[t].ctrl]     # pending blocks controlled by b
+    if q is None:
+        if readers and letter != "Z":
+            return False
+        out.append(g)                 # Z on a control commutes with the controlled blocks
+        return True
+    if q.pure_cx and not q.deferred:
+        (c, v), = q.ctrl.items()
+        hoisted = Prim(GEN, targets=list(g.targets), zbits=list(g.zbits), ny=g.ny, coef=g.coef,
+                       ngates=0, param=g.param, slot=g.slot)
+        if letter in "ZY":
+            hoisted.zbits = hoisted.zbits + [c]
+            if not v:
+                hoisted.coef = -hoisted.coef          # control on |0>: X_c CX X_c
+        # the hoisted term is emitted ahead of every pending block; blocks that started before
+        # the CNOT in the stream are overtaken and must commute with it
+        for t, q2 in pending.items():
+            if q2 is q or q2.seq > q.seq:
+                continue
+            for bit in hoisted.bits & q2.bits:
+                if bit in q2.targets or bit in hoisted.targets:
+                    return False                      # only Z on a control of q2 commutes
+        out.append(hoisted)
+        return True
+    if readers:
+        return False                                  # cannot happen (see merge_blocks), be safe
+    q.deferred.append((g, _PAULI_2x2[letter]))
+    return True
+
+
 def merge_blocks(prims: list[Prim], level: int = 1) -> list[Prim]:
     """level 0: nothing; 1: products of single-qubit runs, with singly-controlled X gates on
     the same target folded in as *controlled-select* blocks (``mat`` where the control holds,
@@ -199,52 +271,74 @@ def merge_blocks(prims: list[Prim], level: int = 1) -> list[Prim]:
     out: list[Prim] = []
     pending: dict[int, Prim] = {}            # target bit -> accumulated block (not yet emitted)
 
+    def emit(t):
+        q = pending.pop(t)
+        out.append(q)
+        out.extend(g for g, _ in q.deferred)
+        q.deferred = []
+
     def flush(bits):
         """Emit every pending block that shares a bit (target or control) with ``bits``."""
         bits = set(bits)
         for b in sorted(pending):
             if pending[b].bits & bits:
-                out.append(pending.pop(b))
+                emit(b)
 
     def flush_controlled_by(b):
         for t in sorted(pending):
             if b in pending[t].ctrl:
-                out.append(pending.pop(t))
+                emit(t)
 
-    for p in prims:
-        one = _as_1q_matrix(p) if p.kind not in (GENERIC, GEN) else None
+    for seq, p in enumerate(prims):
+        if p.kind == GEN:
+            # Generator terms (adjoint reverse sweep) are inner products, not gates: they only
+            # have to be evaluated at a point of the stream where the value is the same.
+            if not p.bits:
+                out.append(p)                     # identity term: Im<bra|ket> is invariant
+                continue
+            if _place_generator(p, pending, out):
+                continue
+            flush(p.bits)
+            out.append(p)
+            continue
+        one = _as_1q_matrix(p) if p.kind != GENERIC else None
         if one is not None:
             b, m = one
+            m = np.asarray(m, dtype=complex)
             flush_controlled_by(b)               # blocks that read b as a control come first
+            if b in pending and any(not _commute(P, m) for _, P in pending[b].deferred):
+                emit(b)                          # a deferred generator must stay before m
             if b in pending:
                 q = pending[b]
-                q.mat = np.asarray(m) @ q.mat
+                q.mat = m @ q.mat
                 if q.mat0 is not None:
-                    q.mat0 = np.asarray(m) @ q.mat0
+                    q.mat0 = m @ q.mat0
                 q.ngates += p.ngates
+                q.pure_cx = False
             else:
-                pending[b] = Prim(DENSE1, targets=[b], mat=np.asarray(m, dtype=complex),
-                                  ngates=p.ngates)
+                pending[b] = Prim(DENSE1, targets=[b], mat=m.copy(), ngates=p.ngates, seq=seq)
             continue
         if p.kind == CX and len(p.ctrl) == 1:
             t = p.targets[0]
             (c, v), = p.ctrl.items()
             flush_controlled_by(t)               # they read t before it is flipped
             if c in pending:
-                out.append(pending.pop(c))       # the control's own block acts first
+                emit(c)                          # the control's own block acts first
             q = pending.get(t)
-            if q is not None and q.ctrl and q.ctrl != {c: v}:
-                out.append(pending.pop(t))
+            if q is not None and ((q.ctrl and q.ctrl != {c: v}) or q.deferred):
+                emit(t)
                 q = None
             if q is None:
                 pending[t] = Prim(DENSE1, targets=[t], ctrl={c: v}, mat=_X.copy(),
-                                  mat0=np.eye(2, dtype=complex), ngates=p.ngates)
+                                  mat0=np.eye(2, dtype=complex), ngates=p.ngates, seq=seq,
+                                  pure_cx=True)
             else:
                 if not q.ctrl:
                     q.ctrl = {c: v}
                     q.mat0 = q.mat
                 q.mat = _X @ q.mat
                 q.ngates += p.ngates
+                q.pure_cx = False
             continue
         if level >= 2 and p.kind == DENSE2 and not p.ctrl:
             # absorb pending (uncontrolled) single-qubit blocks that precede this gate
@@ -252,7 +346,7 @@ def merge_blocks(prims: list[Prim], level: int = 1) -> list[Prim]:
                 flush_controlled_by(b)
             m = p.mat
             for pos, b in enumerate(p.targets):
-                if b in pending and not pending[b].ctrl:
+                if b in pending and not pending[b].ctrl and not pending[b].deferred:
                     q = pending.pop(b)
                     m = m @ _embed(q.mat, pos)
                     p.ngates += q.ngates
@@ -555,7 +649,10 @@ def schedule_rounds(prims, tile_bits, RB: int, sww: int = 3):
     first = True
     while remaining or first:
         if first:
-            R, run, keep = greedy(io_allowed, remaining)
+            # The first round is read out of the landing buffer the bulk copies filled (natural,
+            # unswizzled order), not from global memory: any position >= sww may be a register
+            # bit; positions 0..sww-1 stay on the lowest lane bits (conflict-free reads).
+            R, run, keep = greedy(set(range(min(sww, T - RB), T)), remaining)
             io = True
         else:
             # prefer a round that is IO-compatible when it finishes the segment

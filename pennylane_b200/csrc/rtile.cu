@@ -10,63 +10,32 @@
 
 namespace b200q {
 
-// out[row] = scale * sum over CTAs, fixed order (same contract as k_final_reduce, measure.cuh)
-static __global__ void __launch_bounds__(256)
-k_rt_final_reduce(const double* __restrict__ partials, double* __restrict__ out, const int ncta,
-                  const double scale) {
-  __shared__ double sh[32];
-  double acc = 0.0;
-  for (int i = threadIdx.x; i < ncta; i += blockDim.x) acc += partials[(size_t)blockIdx.x * ncta + i];
-  acc = block_sum(acc, sh);
-  if (threadIdx.x == 0) out[blockIdx.x] = acc * scale;
-}
-
-// geometry of the register-tiled kernel: (dtype, nvec) -> (T, RB, THREADS)
-void rtile_geom(int dtype, int nvec, int& T, int& RB, int& threads) {
-  if (nvec <= 1) {
-    threads = 256; RB = dtype == B200Q_C128 ? 4 : 5;
-  } else { threads = 512; RB = dtype == B200Q_C128 ? 3 : 4; }
-  T = (threads == 256 ? 8 : 9) + RB;
-}
+int rtile_run_c128(bool ws, void* v0, void* v1, const RtArgs& a, int64_t batch, const RtOp* od,
+                   const double2* md, int nslots, double scale, double* out_dev, double* partials,
+                   size_t pcap, cudaStream_t s);
+int rtile_run_c64(bool ws, void* v0, void* v1, const RtArgs& a, int64_t batch, const RtOp* od,
+                  const double2* md, int nslots, double scale, double* out_dev, double* partials,
+                  size_t pcap, cudaStream_t s);
 
 static int env_int(const char* name, int dflt) {
   const char* e = getenv(name);
   return e ? atoi(e) : dflt;
 }
 
-template <typename T, int RB, int NV, int THREADS, int MINB>
-static int rtile_launch(void* v0, void* v1, const RtArgs& a, int64_t batch, const RtOp* ops_dev,
-                        const double2* mats_dev, int nslots, double scale, double* out_dev,
-                        double* partials, size_t partial_cap, cudaStream_t s) {
-  const size_t smem = ((size_t)NV * sizeof(cx<T>) << a.T) + sizeof(cx<T>) * ((a.nmat + 1) & ~1) +
-                      (size_t)a.nops * sizeof(RtOp) +
-                      (size_t)((2 << RB) + 2 * THREADS + 2) * sizeof(unsigned long long) +
-                      (size_t)nslots * (THREADS / 32) * sizeof(double) +
-                      ((size_t)a.nrounds * (THREADS + 8) + THREADS + (1 << RB)) * sizeof(unsigned short);
-  B200Q_REQUIRE(smem <= 227 * 1024, "rtile: %zu bytes of shared memory needed (%d ops, %d slots)",
-                smem, a.nops, nslots);
-  static bool attr_set = false;
-  if (!attr_set) {
-    B200Q_CHECK(cudaFuncSetAttribute(k_rtile<T, RB, NV, THREADS, MINB>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
-  }
-  uint64_t per_sm = std::max<uint64_t>(1, std::min<uint64_t>(MINB, (227 * 1024) / smem));
-  static const int ctas_knob = env_int("B200Q_RT_CTAS", 0);                    // tuning knob
-  if (ctas_knob > 0) per_sm = ctas_knob;
-  const uint64_t cap = (uint64_t)sm_count() * per_sm;
-  dim3 grid((unsigned)std::min<uint64_t>(a.ntiles, cap), (unsigned)batch);
-  if (nslots > 0)
-    B200Q_REQUIRE((size_t)batch * nslots * grid.x <= partial_cap, "rtile: workspace too small for %d slots",
-                  nslots);
-  k_rtile<T, RB, NV, THREADS, MINB><<<grid, THREADS, smem, s>>>(
-      a, (cx<T>*)v0, (cx<T>*)v1, ops_dev, mats_dev, 0, partials);
-  B200Q_LAUNCH_CHECK();
-  if (nslots > 0) {
-    k_rt_final_reduce<<<(unsigned)(batch * nslots), 256, 0, s>>>(partials, out_dev, (int)grid.x, scale);
-    B200Q_LAUNCH_CHECK();
-  }
-  return 0;
+// tuning knob, read once.  Forward kernel: 0 = warp-specialised (128 consumer threads + one
+// producer warp, 3 CTAs/SM, landing buffer filled by bulk async copies), 1 = 256 threads x
+// 2 CTAs/SM with the next tile fetched into the idle transpose buffer.
+static int rtile_variant() {
+  static const int v = env_int("B200Q_RT_VARIANT", 0);
+  return v;
+}
+
+// geometry of the register-tiled kernel: (dtype, nvec) -> (T, RB, THREADS = consumer threads)
+void rtile_geom(int dtype, int nvec, int& T, int& RB, int& threads) {
+  if (nvec <= 1) {
+    threads = rtile_variant() == 0 ? 128 : 256; RB = dtype == B200Q_C128 ? 4 : 5;
+  } else { threads = 512; RB = dtype == B200Q_C128 ? 3 : 4; }
+  T = (threads == 128 ? 7 : threads == 256 ? 8 : 9) + RB;
 }
 
 int rtile_dispatch(void* v0, void* v1, int n, int dtype, int64_t batch, const int* tile_bits,
@@ -120,7 +89,7 @@ int rtile_dispatch(void* v0, void* v1, int n, int dtype, int64_t batch, const in
   // bulk-copy prefetch of the next tile (default on); needs >= 16-byte contiguous runs
   static const int pf_knob = env_int("B200Q_RT_PREFETCH", 1);                  // tuning knob
   const size_t elem = dtype == B200Q_C128 ? 16 : 8;
-  a.prefetch = (pf_knob && ((elem << L) >= 16) && (((uintptr_t)v0 | (uintptr_t)v1) % 16 == 0)) ? 1 : 0;
+  a.prefetch = ((pf_knob || (rtile_variant() == 0 && !v1)) && ((elem << L) >= 16) && (((uintptr_t)v0 | (uintptr_t)v1) % 16 == 0)) ? 1 : 0;
   const size_t ops_bytes = (size_t)nops * sizeof(RtOp);
   const size_t mat_bytes = (size_t)nmat * sizeof(double2);
   B200Q_REQUIRE(work && ops_bytes + mat_bytes + 512 <= kTermRegion && work_bytes >= kWorkBytes,
@@ -133,14 +102,13 @@ int rtile_dispatch(void* v0, void* v1, int n, int dtype, int64_t batch, const in
   const size_t pcap = (work_bytes - kTermRegion) / sizeof(double);
   const RtOp* od = (const RtOp*)w;
   const double2* md = (const double2*)(w + moff);
-  if (dtype == B200Q_C128) {
-    if (!v1) return rtile_launch<double, 4, 1, 256, 2>(v0, v1, a, batch, od, md, nslots, scale, out_dev, partials, pcap, s);
-    return rtile_launch<double, 3, 2, 512, 1>(v0, v1, a, batch, od, md, nslots, scale, out_dev, partials, pcap, s);
-  }
-  if (dtype == B200Q_C64) {
-    if (!v1) return rtile_launch<float, 5, 1, 256, 2>(v0, v1, a, batch, od, md, nslots, scale, out_dev, partials, pcap, s);
-    return rtile_launch<float, 4, 2, 512, 1>(v0, v1, a, batch, od, md, nslots, scale, out_dev, partials, pcap, s);
-  }
+  const bool ws = rtile_variant() == 0;
+  if (ws && !v1)
+    B200Q_REQUIRE(a.prefetch, "rtile: the warp-specialised kernel needs 16-byte aligned runs (L=%d)", L);
+  if (dtype == B200Q_C128)
+    return rtile_run_c128(ws, v0, v1, a, batch, od, md, nslots, scale, out_dev, partials, pcap, s);
+  if (dtype == B200Q_C64)
+    return rtile_run_c64(ws, v0, v1, a, batch, od, md, nslots, scale, out_dev, partials, pcap, s);
   set_error("unknown dtype %d", dtype);
   return 2;
 }

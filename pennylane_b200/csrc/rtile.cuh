@@ -141,8 +141,14 @@ __device__ __forceinline__ void rt_fence_proxy_async() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
-template <typename T_, int RB, int NV, int THREADS>
+// WS (warp-specialised): the CTA has THREADS consumer threads plus ONE producer warp.  The
+// producer streams the CTA's next tile into a separate landing buffer with bulk async copies
+// (full/empty mbarrier pair) while the consumers work on the current one in registers and in the
+// transpose buffer, so the HBM read of tile i+1 overlaps ALL of tile i's compute.  Small tiles
+// (128 consumer threads) keep 3 such CTAs resident per SM.
+template <typename T_, int RB, int NV, int THREADS, bool WS = false>
 struct RtKernel {
+  static constexpr int NTH = THREADS + (WS ? 32 : 0);      // threads per CTA
   static constexpr int NA = 1 << RB;
   static constexpr int TB = (THREADS == 128) ? 7 : (THREADS == 256) ? 8 : (THREADS == 512) ? 9 : 10;
   static constexpr int SWW = (sizeof(T_) == 8) ? 3 : 4;    // swizzle width: 16-byte / 8-byte elements
@@ -377,13 +383,20 @@ struct RtKernel {
 
   // bring tile `t` of every vector into the (currently idle) transpose buffer: one bulk async
   // copy per contiguous run of 2^L amplitudes, completion counted on `bar`
+  static __device__ __forceinline__ void csync() {         // barrier over the consumer threads
+    if constexpr (WS) asm volatile("bar.sync 1, %0;" ::"n"(THREADS) : "memory");
+    else __syncthreads();
+  }
+
   static __device__ __forceinline__ void issue_tile_copies(const RtArgs& a, C* vec0, C* vec1,
                                                            C* tile, const unsigned long long t,
-                                                           unsigned long long* bar) {
+                                                           unsigned long long* bar,
+                                                           const unsigned first = threadIdx.x,
+                                                           const unsigned stride = THREADS) {
     const unsigned tsize = 1u << a.T;
     const unsigned run = 1u << a.L;
     const unsigned long long base = tile_base(a, t);
-    for (unsigned j = threadIdx.x; j < (tsize >> a.L) * NV; j += THREADS) {
+    for (unsigned j = first; j < (tsize >> a.L) * NV; j += stride) {
       const unsigned v = j >> (a.T - a.L), r = j & ((tsize >> a.L) - 1u);
       rt_bulk_g2s(tile + (size_t)v * tsize + ((size_t)r << a.L),
                   (v ? vec1 : vec0) + base + rt_gscatter(r << a.L, a), run * (unsigned)sizeof(C),
@@ -399,11 +412,12 @@ struct RtKernel {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const unsigned tsize = 1u << a.T;
     C* tile = reinterpret_cast<C*>(smem_raw);                                  // NV * 2^T
-    C* mats = tile + (size_t)NV * tsize;                                        // nmat (padded even)
+    C* land = WS ? tile + (size_t)NV * tsize : tile;                            // WS: NV * 2^T more
+    C* mats = land + (size_t)NV * tsize;                                        // nmat (padded even)
     RtOp* ops = reinterpret_cast<RtOp*>(mats + ((a.nmat + 1) & ~1));            // nops
     unsigned long long* koff = reinterpret_cast<unsigned long long*>(ops + a.nops);  // 2 * NA
     unsigned long long* toff = koff + 2 * NA;                                   // 2 * THREADS
-    unsigned long long* bar = toff + 2 * THREADS;                               // 2 (one used)
+    unsigned long long* bar = toff + 2 * THREADS;                               // full, empty
     double* accs = reinterpret_cast<double*>(bar + 2);                          // nslots * NW
     unsigned short* tsl = reinterpret_cast<unsigned short*>(accs + a.nslots * NW);   // nrounds * THREADS
     unsigned short* rsl = tsl + (size_t)a.nrounds * THREADS;                    // nrounds * 8
@@ -412,10 +426,13 @@ struct RtKernel {
     const unsigned tid = threadIdx.x;
 
     const double2* mg = mats_g + (long long)blockIdx.y * mat_bstride;
-    for (int i = tid; i < a.nmat; i += THREADS) mats[i] = make_cx<T_>((T_)mg[i].x, (T_)mg[i].y);
-    for (int i = tid; i < a.nops; i += THREADS) ops[i] = ops_g[i];
-    for (int i = tid; i < a.nslots * NW; i += THREADS) accs[i] = 0.0;
-    if (tid == 0) rt_mbar_init(bar, 1);
+    for (int i = tid; i < a.nmat; i += NTH) mats[i] = make_cx<T_>((T_)mg[i].x, (T_)mg[i].y);
+    for (int i = tid; i < a.nops; i += NTH) ops[i] = ops_g[i];
+    for (int i = tid; i < a.nslots * NW; i += NTH) accs[i] = 0.0;
+    if (tid == 0) {
+      rt_mbar_init(bar, 1);
+      rt_mbar_init(bar + 1, NW);        // empty: one arrival per consumer warp
+    }
     __syncthreads();
     if (tid == 0) {                    // number the rounds: q0 of a ROUND record = its index
       int r = 0;
@@ -431,7 +448,7 @@ struct RtKernel {
     // tile independent: per-thread parts in toff, per-register-index parts in koff.  The
     // swizzled shared-memory slot of every (round, thread) and (round, register bit) is
     // computed once here instead of once per tile and round.
-    {
+    if (tid < THREADS) {
       const RtOp& f = ops[0];
       const RtOp& l = ops[a.last_round];
       unsigned tj = 0, tl = 0;
@@ -464,7 +481,21 @@ struct RtKernel {
     }
     __syncthreads();
 
-    const bool pf = a.prefetch != 0;
+    if constexpr (WS) {
+      if (tid >= THREADS) {
+        // ---- producer warp ------------------------------------------------------------------
+        const unsigned lane = tid & 31u;
+        unsigned i = 0;
+        for (unsigned long long t = blockIdx.x; t < a.ntiles; t += gridDim.x, ++i) {
+          if (i > 0) rt_mbar_wait(bar + 1, (i - 1u) & 1u);      // consumers drained tile i-1
+          if (lane == 0) rt_mbar_expect_tx(bar, (unsigned)(NV * tsize * sizeof(C)));
+          __syncwarp();
+          issue_tile_copies(a, vec[0], vec[1], land, t, bar, lane, 32u);
+        }
+        return;
+      }
+    }
+    const bool pf = !WS && a.prefetch != 0;
     if (pf) {                          // prologue: the CTA's first tile
       rt_fence_proxy_async();
       if (tid == 0) rt_mbar_expect_tx(bar, (unsigned)(NV * tsize * sizeof(C)));
@@ -482,7 +513,18 @@ struct RtKernel {
       bool issued = false;             // next tile's copies already in flight
 
       // ---- load (round 0 layout) ------------------------------------------------------------
-      if (pf) {
+      if constexpr (WS) {
+        rt_mbar_wait(bar, phase);
+        phase ^= 1u;
+        const unsigned tj = ldsl[tid];
+#pragma unroll
+        for (int v = 0; v < NV; ++v)
+#pragma unroll
+          for (int k = 0; k < NA; ++k) A[v][k] = land[v * tsize + (tj | ldsl[THREADS + k])];
+        __syncwarp();
+        if ((tid & 31u) == 0)          // this warp has drained the landing buffer
+          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(rt_smem_u32(bar + 1)) : "memory");
+      } else if (pf) {
         rt_mbar_wait(bar, phase);
         phase ^= 1u;
         const unsigned tj = ldsl[tid];
@@ -604,7 +646,7 @@ struct RtKernel {
           unsigned tslot = tsl[cur * THREADS + tid], rs[RB];
 #pragma unroll
           for (int b = 0; b < RB; ++b) rs[b] = rsl[cur * 8 + b];
-          __syncthreads();
+          csync();
 #pragma unroll
           for (int v = 0; v < NV; ++v)
 #pragma unroll
@@ -612,7 +654,7 @@ struct RtKernel {
           tslot = tsl[nr * THREADS + tid];
 #pragma unroll
           for (int b = 0; b < RB; ++b) rs[b] = rsl[nr * 8 + b];
-          __syncthreads();
+          csync();
 #pragma unroll
           for (int v = 0; v < NV; ++v)
 #pragma unroll
@@ -706,7 +748,7 @@ struct RtKernel {
     }
 
     if (a.nslots > 0) {
-      __syncthreads();
+      csync();
       for (int s = tid; s < a.nslots; s += THREADS) {
         double acc = 0.0;
         for (int w = 0; w < NW; ++w) acc += accs[s * NW + w];
@@ -716,12 +758,12 @@ struct RtKernel {
   }
 };
 
-template <typename T_, int RB, int NV, int THREADS, int MINB>
-__global__ void __launch_bounds__(THREADS, MINB)
+template <typename T_, int RB, int NV, int THREADS, int MINB, bool WS = false>
+__global__ void __launch_bounds__(THREADS + (WS ? 32 : 0), MINB)
 k_rtile(const __grid_constant__ RtArgs a, cx<T_>* __restrict__ v0, cx<T_>* __restrict__ v1,
         const RtOp* __restrict__ ops_g, const double2* __restrict__ mats_g,
         const long long mat_bstride, double* __restrict__ partials) {
-  RtKernel<T_, RB, NV, THREADS>::run(a, v0, v1, ops_g, mats_g, mat_bstride, partials);
+  RtKernel<T_, RB, NV, THREADS, WS>::run(a, v0, v1, ops_g, mats_g, mat_bstride, partials);
 }
 
 }  // namespace b200q

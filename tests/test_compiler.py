@@ -162,10 +162,13 @@ def test_round_schedule_reproduces_circuit(level, n, T, L, RB, sww):
                 psi = _apply_prim(p, psi, n)
             continue
         rounds = schedule_rounds(seg.prims, seg.tile_bits, RB, sww)
-        # IO rounds keep tile positions 0..lanes-1 on the lanes
-        for r in (rounds[0], rounds[-1]):
-            assert r.tpos[:lanes] == list(range(lanes))
-            assert all(p >= lanes for p in r.rpos)
+        # the last (store) round keeps tile positions 0..lanes-1 on the lanes; the first round is
+        # read from the landing buffer: only positions 0..sww-1 must stay on the lowest lane bits
+        assert rounds[-1].tpos[:lanes] == list(range(lanes))
+        assert all(p >= lanes for p in rounds[-1].rpos)
+        low = min(sww, T - RB)
+        assert rounds[0].tpos[:low] == list(range(low))
+        assert all(p >= low for p in rounds[0].rpos)
         for r in rounds:
             assert sorted(r.rpos + r.tpos) == list(range(T))
         arr, table, nrec = encode_rt_segment(seg, RB, sww, rounds=rounds)
