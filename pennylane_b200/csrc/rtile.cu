@@ -53,6 +53,7 @@ int rtile_dispatch(void* v0, void* v1, int n, int dtype, int64_t batch, const in
   a.n = n; a.T = Tn; a.L = L; a.nops = nops; a.nmat = nmat; a.nslots = nslots; a.write0 = write0;
   a.base_hi = base_hi;
   for (int i = 0; i < nops; ++i) {
+    if ((ops_host[i].kind & 0xff) == RT_DENSE1 && a.nd1 < 32) a.nd1++;
     if (ops_host[i].kind == RT_ROUND) {
       a.last_round = i;
       a.nrounds++;

@@ -82,6 +82,7 @@ struct RtArgs {
   int prefetch;                  // 1: the CTA's next tile is brought into the (idle) transpose
                                  // buffer with bulk async copies while the last round computes
   int nruns;                     // runs of consecutive non-tile bits (tile number -> base)
+  int nd1;                       // number of predecoded single-qubit block records (<= 32)
   int8_t hi_bits[16];            // global positions of tile positions L..T-1 (ascending)
   int8_t run_s[16], run_len[16], run_g[16];   // tile-number bits [s, s+len) -> global bits [g, g+len)
   unsigned long long ntiles;     // 2^(n-T)
@@ -331,9 +332,17 @@ struct RtKernel {
       for (int k = 0; k < NA; k += 4) sfence(A[v][k], A[v][k + 1], A[v][k + 2], A[v][k + 3]);
   }
 
+  // 16-byte (complex128) / 8-byte (complex64) shared-memory load by 32-bit address
+  static __device__ __forceinline__ C lds_c(const unsigned addr) {
+    C r;
+    if constexpr (sizeof(T_) == 8) asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "r"(addr));
+    else asm("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "r"(addr));
+    return r;
+  }
+
   template <int Q>
-  static __device__ __forceinline__ void d1_uniform(C (&A)[NV][NA], const C* __restrict__ m) {
-    const C M[4] = {m[0], m[1], m[2], m[3]};
+  static __device__ __forceinline__ void d1_uniform(C (&A)[NV][NA], const unsigned m) {
+    const C M[4] = {lds_c(m), lds_c(m + sizeof(C)), lds_c(m + 2 * sizeof(C)), lds_c(m + 3 * sizeof(C))};
     int cnt = 0;
 #pragma unroll
     for (int k = 0; k < NA; ++k) {
@@ -348,8 +357,8 @@ struct RtKernel {
   }
 
   template <int Q, int CB, int BV>
-  static __device__ __forceinline__ void d1_half(C (&A)[NV][NA], const C* __restrict__ m) {
-    const C M[4] = {m[0], m[1], m[2], m[3]};
+  static __device__ __forceinline__ void d1_half(C (&A)[NV][NA], const unsigned m) {
+    const C M[4] = {lds_c(m), lds_c(m + sizeof(C)), lds_c(m + 2 * sizeof(C)), lds_c(m + 3 * sizeof(C))};
     int cnt = 0;
 #pragma unroll
     for (int k = 0; k < NA; ++k) {
@@ -363,12 +372,18 @@ struct RtKernel {
     }
   }
 
+  // matrices are named by their index in units of two table entries (255 = leave untouched)
+  static constexpr unsigned D1_SKIP = 255u;
   template <int Q, int CB>
-  static __device__ __forceinline__ void d1_regctl(C (&A)[NV][NA], const C* __restrict__ m_b0,
-                                                   const C* __restrict__ m_b1) {
-    if constexpr (Q != CB && Q < RB && CB < RB) {
-      if (m_b0) d1_half<Q, CB, 0>(A, m_b0);
-      if (m_b1) d1_half<Q, CB, 1>(A, m_b1);
+  static __device__ __forceinline__ void d1_regctl(C (&A)[NV][NA], const unsigned mats_s,
+                                                   const unsigned b0, const unsigned b1) {
+    if constexpr (Q < RB && CB < RB) {
+      if constexpr (Q == CB) {
+        if (b0 != D1_SKIP) d1_uniform<Q>(A, mats_s + b0 * 2u * (unsigned)sizeof(C));
+      } else {
+        if (b0 != D1_SKIP) d1_half<Q, CB, 0>(A, mats_s + b0 * 2u * (unsigned)sizeof(C));
+        if (b1 != D1_SKIP) d1_half<Q, CB, 1>(A, mats_s + b1 * 2u * (unsigned)sizeof(C));
+      }
     }
   }
 
@@ -423,6 +438,10 @@ struct RtKernel {
     unsigned short* rsl = tsl + (size_t)a.nrounds * THREADS;                    // nrounds * 8
     unsigned short* ldsl = rsl + (size_t)a.nrounds * 8;                         // THREADS + NA: round-0
                                                                                 // layout, unswizzled
+    unsigned* rd = reinterpret_cast<unsigned*>(ldsl + THREADS + NA);            // nops + 1 descriptors
+    unsigned* kst32 = rd + a.nops + 1;                                          // NA: store offsets
+    unsigned short* ent = reinterpret_cast<unsigned short*>(kst32 + NA);        // nd1 * THREADS
+    unsigned char* d1rec = reinterpret_cast<unsigned char*>(ent + (size_t)a.nd1 * THREADS);   // 32
     const unsigned tid = threadIdx.x;
 
     const double2* mg = mats_g + (long long)blockIdx.y * mat_bstride;
@@ -434,12 +453,38 @@ struct RtKernel {
       rt_mbar_init(bar + 1, NW);        // empty: one arrival per consumer warp
     }
     __syncthreads();
-    if (tid == 0) {                    // number the rounds: q0 of a ROUND record = its index
-      int r = 0;
-      for (int i = 0; i < a.nops; ++i)
-        if ((ops[i].kind & 0xff) == RT_ROUND) ops[i].q0 = r++;
+    // Record descriptors (one uniform 32-bit load per record in the tile loop):
+    //   byte 0: 0xF0 | kind for records decoded from their 64-byte form, or, for single-qubit
+    //           blocks with at most one control on a register bit, the handler Q * 8 + CB
+    //           (CB = Q: no register control);  byte 1: predecode slot;  bytes 2-3: the
+    //           (b0, b1) matrix pair used when the record's controls OUTSIDE the tile fail.
+    // The (b0, b1) pair of every (slot, thread) for the case that they hold is tabulated once
+    // per CTA in `ent`: in the tile loop such a record costs one table load and a jump instead
+    // of ~60 instructions of mask tests and pointer selects.
+    if (tid == 0) {
+      int r = 0, s1 = 0;
+      for (int i = 0; i < a.nops; ++i) {
+        const int k = ops[i].kind & 0xff;
+        unsigned d = 0xF0u | (unsigned)k;
+        if (k == RT_ROUND) ops[i].q0 = r++;
+        else if (k == RT_DENSE1) {
+          const unsigned cr = ops[i].u.g.ctrl_r;
+          const bool has0 = (ops[i].kind >> 8) & 1;
+          const unsigned idx0 = (unsigned)(ops[i].mat_off >> 1) + 2u;
+          if ((cr & (cr - 1u)) == 0 && s1 < a.nd1 && s1 < 32 && !(ops[i].mat_off & 1) && idx0 < D1_SKIP) {
+            const unsigned cb = cr ? (unsigned)(__ffs((int)cr) - 1) : (unsigned)ops[i].q0;
+            const unsigned e0 = has0 ? idx0 : D1_SKIP;
+            d = ((unsigned)ops[i].q0 * 8u + cb) | ((unsigned)s1 << 8) | (e0 << 16) | (e0 << 24);
+            d1rec[s1++] = (unsigned char)i;
+          }
+        }
+        rd[i] = d;
+      }
+      rd[a.nops] = 0xFFu | ((unsigned)s1 << 8);
     }
     __syncthreads();
+    const unsigned nd1u = rd[a.nops] >> 8;           // predecoded records
+    const unsigned mats_s = rt_smem_u32(mats);
 
     C* const vec[2] = {v0 + ((unsigned long long)blockIdx.y << a.n),
                        NV > 1 ? v1 + ((unsigned long long)blockIdx.y << a.n) : nullptr};
@@ -466,6 +511,18 @@ struct RtKernel {
         for (int b = 0; b < RB; ++b) j |= ((k >> b) & 1u) << r.u.r.rbits[b];
         koff[tid] = rt_gscatter(j, a);
         if (tid < NA) ldsl[THREADS + tid] = (unsigned short)j;
+        else kst32[k] = (unsigned)koff[tid];          // store offsets, 32-bit (used when n <= 32)
+      }
+      for (unsigned s1 = 0; s1 < nd1u; ++s1) {
+        const RtOp& r = ops[d1rec[s1]];
+        const RtGate& g = r.u.g;
+        const bool has0 = (r.kind >> 8) & 1;
+        const unsigned idx1 = (unsigned)(r.mat_off >> 1), idx0 = idx1 + 2u;
+        const unsigned mo = has0 ? idx0 : D1_SKIP;                          // control fails
+        const unsigned ms = ((tid & g.ctrl_t) == g.cval_t) ? idx1 : mo;     // control holds
+        unsigned b0 = ms, b1 = ms;
+        if (g.ctrl_r) { b1 = g.cval_r ? ms : mo; b0 = g.cval_r ? mo : ms; }
+        ent[s1 * THREADS + tid] = (unsigned short)(b0 | (b1 << 8));
       }
       for (int i = 0; i < a.nops; ++i) {
         const RtOp& r = ops[i];
@@ -550,7 +607,39 @@ struct RtKernel {
       }
       int cur = 0;                     // round index (not record index) of the current layout
 
+      // controls outside the tile of the predecoded records: one ballot per tile
+      unsigned emask;
+      {
+        const unsigned lane = tid & 31u;
+        bool p = false;
+        if (lane < nd1u) {
+          const RtGate& g = ops[d1rec[lane]].u.g;
+          p = (baseE & g.ctrl_e) == g.cval_e;
+        }
+        emask = __ballot_sync(0xffffffffu, p);
+      }
+
+      unsigned rdn = rd[1];
       for (int o = 1; o < a.nops; ++o) {
+        const unsigned rdc = rdn;
+        rdn = rd[o + 1];               // next descriptor: in flight while this record computes
+        if ((rdc & 0xffu) < 0x40u) {
+          // ---- predecoded single-qubit block ---------------------------------------------------
+          const unsigned slot = (rdc >> 8) & 0xffu;
+          const unsigned e = ((emask >> slot) & 1u) ? (unsigned)ent[slot * THREADS + tid] : (rdc >> 16);
+          const unsigned b0 = e & 0xffu, b1 = (e >> 8) & 0xffu;
+          switch (rdc & 0xffu) {
+#define RT_D1C(Q, CB) case Q * 8 + CB: d1_regctl<Q, CB>(A, mats_s, b0, b1); break;
+            RT_D1C(0, 0) RT_D1C(0, 1) RT_D1C(0, 2) RT_D1C(0, 3) RT_D1C(0, 4)
+            RT_D1C(1, 0) RT_D1C(1, 1) RT_D1C(1, 2) RT_D1C(1, 3) RT_D1C(1, 4)
+            RT_D1C(2, 0) RT_D1C(2, 1) RT_D1C(2, 2) RT_D1C(2, 3) RT_D1C(2, 4)
+            RT_D1C(3, 0) RT_D1C(3, 1) RT_D1C(3, 2) RT_D1C(3, 3) RT_D1C(3, 4)
+            RT_D1C(4, 0) RT_D1C(4, 1) RT_D1C(4, 2) RT_D1C(4, 3) RT_D1C(4, 4)
+#undef RT_D1C
+            default: break;
+          }
+          continue;
+        }
         const RtOp& op = ops[o];
         const int kind = op.kind & 0xff;
         if (kind <= RT_CX) {
@@ -561,36 +650,7 @@ struct RtKernel {
           const bool has0 = (op.kind >> 8) & 1;
           const C* m = mats + op.mat_off;
           if (kind == RT_DENSE1) {
-            if (cr == 0) {
-              const C* mm = tsel ? m : (has0 ? m + 4 : nullptr);
-              if (mm) {
-                switch (op.q0) {
-                  case 0: d1_uniform<0>(A, mm); break;
-                  case 1: if constexpr (RB > 1) d1_uniform<1>(A, mm); break;
-                  case 2: if constexpr (RB > 2) d1_uniform<2>(A, mm); break;
-                  case 3: if constexpr (RB > 3) d1_uniform<3>(A, mm); break;
-                  case 4: if constexpr (RB > 4) d1_uniform<4>(A, mm); break;
-                  default: break;
-                }
-              }
-            } else if ((cr & (cr - 1u)) == 0) {
-              // one control on a register bit: the matrix depends on that bit of k only
-              const int cb = __ffs((int)cr) - 1;
-              const C* ms = tsel ? m : (has0 ? m + 4 : nullptr);    // pairs whose control holds
-              const C* mo = has0 ? m + 4 : nullptr;                 // pairs whose control fails
-              const C* mb1 = cv ? ms : mo;
-              const C* mb0 = cv ? mo : ms;
-              switch (op.q0 * 8 + cb) {
-#define RT_D1C(Q, CB) case Q * 8 + CB: d1_regctl<Q, CB>(A, mb0, mb1); break;
-                RT_D1C(0, 1) RT_D1C(0, 2) RT_D1C(0, 3) RT_D1C(0, 4)
-                RT_D1C(1, 0) RT_D1C(1, 2) RT_D1C(1, 3) RT_D1C(1, 4)
-                RT_D1C(2, 0) RT_D1C(2, 1) RT_D1C(2, 3) RT_D1C(2, 4)
-                RT_D1C(3, 0) RT_D1C(3, 1) RT_D1C(3, 2) RT_D1C(3, 4)
-                RT_D1C(4, 0) RT_D1C(4, 1) RT_D1C(4, 2) RT_D1C(4, 3)
-#undef RT_D1C
-                default: break;
-              }
-            } else if (has0) {
+            if (has0) {
               switch (op.q0) {
                 case 0: dense1<0, true>(A, m, tsel, cr, cv); break;
                 case 1: if constexpr (RB > 1) dense1<1, true>(A, m, tsel, cr, cv); break;
@@ -741,8 +801,13 @@ struct RtKernel {
       for (int v = 0; v < NV; ++v) {
         if (v == 0 && !a.write0) continue;
         C* dst = vec[v] + base + toff[THREADS + tid];
+        if (a.n <= 32) {
 #pragma unroll
-        for (int k = 0; k < NA; ++k) dst[koff[NA + k]] = A[v][k];
+          for (int k = 0; k < NA; ++k) dst[kst32[k]] = A[v][k];
+        } else {
+#pragma unroll
+          for (int k = 0; k < NA; ++k) dst[koff[NA + k]] = A[v][k];
+        }
       }
       (void)issued;
     }

@@ -30,7 +30,9 @@ static int rtile_launch(void* v0, void* v1, const RtArgs& a, int64_t batch, cons
                       (size_t)a.nops * sizeof(RtOp) +
                       (size_t)((2 << RB) + 2 * THREADS + 2) * sizeof(unsigned long long) +
                       (size_t)nslots * (THREADS / 32) * sizeof(double) +
-                      ((size_t)a.nrounds * (THREADS + 8) + THREADS + (1 << RB)) * sizeof(unsigned short);
+                      ((size_t)a.nrounds * (THREADS + 8) + THREADS + (1 << RB)) * sizeof(unsigned short) +
+                      ((size_t)a.nops + 1 + (1 << RB)) * sizeof(unsigned) +
+                      (size_t)a.nd1 * THREADS * sizeof(unsigned short) + 32;
   B200Q_REQUIRE(smem <= 227 * 1024, "rtile: %zu bytes of shared memory needed (%d ops, %d slots)",
                 smem, a.nops, nslots);
   static bool attr_set = false;
