@@ -26,7 +26,7 @@ static int env_int(const char* name, int dflt) {
 // producer warp, 3 CTAs/SM, landing buffer filled by bulk async copies), 1 = 256 threads x
 // 2 CTAs/SM with the next tile fetched into the idle transpose buffer.
 static int rtile_variant() {
-  static const int v = env_int("B200Q_RT_VARIANT", 0);
+  static const int v = env_int("B200Q_RT_VARIANT", 1);
   return v;
 }
 

@@ -241,17 +241,38 @@ struct RtKernel {
     }
   }
 
+  // Conditional in-place exchange of two reals: (a, b) <- m ? (b, a) : (a, b), m = 0 or ~0, as
+  // three XOR/AND operations per 32-bit word.  Branch-free and born in place: a register swap
+  // written as moves under a (divergent or uniform) branch made ptxas re-shuffle the whole
+  // amplitude file at the interpreter's control-flow merges (ncu on the adjoint kernel: 52 % of
+  // all issued instructions were MOVs).
+  static __device__ __forceinline__ void cswap(T_& a, T_& b, const unsigned m) {
+    if constexpr (sizeof(T_) == 8) {
+      unsigned al = (unsigned)__double2loint(a), ah = (unsigned)__double2hiint(a);
+      unsigned bl = (unsigned)__double2loint(b), bh = (unsigned)__double2hiint(b);
+      const unsigned tl = (al ^ bl) & m, th = (ah ^ bh) & m;
+      al ^= tl; bl ^= tl; ah ^= th; bh ^= th;
+      a = __hiloint2double((int)ah, (int)al);
+      b = __hiloint2double((int)bh, (int)bl);
+    } else {
+      unsigned ua = __float_as_uint(a), ub = __float_as_uint(b);
+      const unsigned t = (ua ^ ub) & m;
+      a = __uint_as_float(ua ^ t);
+      b = __uint_as_float(ub ^ t);
+    }
+  }
+
   template <int Q>
-  static __device__ __forceinline__ void cx_gate(C (&A)[NV][NA], unsigned cr, unsigned cv) {
+  static __device__ __forceinline__ void cx_gate(C (&A)[NV][NA], const bool tsel, unsigned cr,
+                                                 unsigned cv) {
 #pragma unroll
     for (int k = 0; k < NA; ++k) {
       if ((k >> Q) & 1) continue;
-      if ((k & cr) != cv) continue;
+      const unsigned m = (tsel && ((k & cr) == cv)) ? 0xffffffffu : 0u;
 #pragma unroll
       for (int v = 0; v < NV; ++v) {
-        const C x0 = A[v][k];
-        A[v][k] = A[v][k | (1 << Q)];
-        A[v][k | (1 << Q)] = x0;
+        cswap(A[v][k].x, A[v][k | (1 << Q)].x, m);
+        cswap(A[v][k].y, A[v][k | (1 << Q)].y, m);
       }
     }
   }
@@ -263,45 +284,42 @@ struct RtKernel {
     a.y = fma(p.x, a.y, ty);
   }
 
-  // sum_k sign_k * {Re, Im}(conj(bra_k) * ket_{k ^ PM}),  sign_k = (-1)^(popc((k ^ xr) & zr) + tpar).
-  // Only PM = 0 is instantiated: the X part of a generator term is applied to the ket in
-  // registers first (flip_ket_mask, pure register moves) and undone afterwards.  A switch over
-  // compile-time partner masks looked cheaper on paper but made ptxas spill ~4-12 KB per thread
-  // at the 128-register cap of the 512-thread adjoint kernel (checked with -Xptxas -v).
+  // sum_k sign_k * {Re, Im}(conj(bra_k) * ket_{k ^ PM}),  sign_k = (-1)^(popc((k ^ PM) & zr) + tpar).
+  // PM (the X part of the generator term on register bits) is a compile-time constant: the
+  // partner amplitude is named directly, nothing moves.  The sign is applied by flipping the
+  // sign bit of the product.
   template <int PM>
-  static __device__ __forceinline__ double gen_term(const C (&A)[NV][NA], const unsigned xr,
-                                                    const unsigned zr, const unsigned tpar,
-                                                    const bool odd) {
+  static __device__ __forceinline__ double gen_term(const C (&A)[NV][NA], const unsigned zr,
+                                                    const unsigned tpar, const bool odd) {
+    unsigned zb[RB];
+#pragma unroll
+    for (int b = 0; b < RB; ++b) zb[b] = (zr >> b) & 1u;
     double acc = 0.0;
 #pragma unroll
     for (int k = 0; k < NA; ++k) {
       const C b = A[NV - 1][k], x = A[0][k ^ PM];
-      const unsigned par = (__popc(((unsigned)k ^ xr) & zr) & 1u) ^ tpar;
+      const unsigned par = sel_xor(zb, k ^ PM) ^ tpar;
       double val;
-      if (odd) val = (double)b.x * (double)x.x + (double)b.y * (double)x.y;   // Re
-      else val = (double)b.x * (double)x.y - (double)b.y * (double)x.x;       // Im
-      acc += par ? -val : val;
+      if (odd) val = fma((double)b.y, (double)x.y, (double)b.x * (double)x.x);    // Re
+      else val = fma(-(double)b.y, (double)x.x, (double)b.x * (double)x.y);       // Im
+      val = __hiloint2double(__double2hiint(val) ^ (int)(par << 31), __double2loint(val));
+      acc += val;
     }
     return acc;
   }
 
-  template <int Q> static __device__ __forceinline__ void flip_ket(C (&A)[NV][NA]) {
-#pragma unroll
-    for (int k = 0; k < NA; ++k) {
-      if ((k >> Q) & 1) continue;
-      const C x0 = A[0][k];
-      A[0][k] = A[0][k | (1 << Q)];
-      A[0][k | (1 << Q)] = x0;
+  static __device__ __forceinline__ double gen_dispatch(const C (&A)[NV][NA], const unsigned xr,
+                                                        const unsigned zr, const unsigned tpar,
+                                                        const bool odd) {
+    switch (xr) {
+#define RT_GEN_CASE(PM) case PM: if constexpr (PM < NA) return gen_term<PM>(A, zr, tpar, odd); break;
+      RT_GEN_CASE(0) RT_GEN_CASE(1) RT_GEN_CASE(2) RT_GEN_CASE(3) RT_GEN_CASE(4) RT_GEN_CASE(5)
+      RT_GEN_CASE(6) RT_GEN_CASE(7) RT_GEN_CASE(8) RT_GEN_CASE(9) RT_GEN_CASE(10) RT_GEN_CASE(11)
+      RT_GEN_CASE(12) RT_GEN_CASE(13) RT_GEN_CASE(14) RT_GEN_CASE(15)
+#undef RT_GEN_CASE
+      default: break;
     }
-  }
-
-  // flip the ket on every register bit of `mask` (a permutation; applying it twice undoes it)
-  static __device__ __forceinline__ void flip_ket_mask(C (&A)[NV][NA], const unsigned mask) {
-    if (mask & 1u) flip_ket<0>(A);
-    if constexpr (RB > 1) { if (mask & 2u) flip_ket<1>(A); }
-    if constexpr (RB > 2) { if (mask & 4u) flip_ket<2>(A); }
-    if constexpr (RB > 3) { if (mask & 8u) flip_ket<3>(A); }
-    if constexpr (RB > 4) { if (mask & 16u) flip_ket<4>(A); }
+    return 0.0;
   }
 
   // ---- single-qubit dense blocks with the matrix PINNED in registers -------------------------
@@ -670,15 +688,13 @@ struct RtKernel {
               }
             }
           } else if (kind == RT_CX) {
-            if (tsel) {
-              switch (op.q0) {
-                case 0: cx_gate<0>(A, cr, cv); break;
-                case 1: if constexpr (RB > 1) cx_gate<1>(A, cr, cv); break;
-                case 2: if constexpr (RB > 2) cx_gate<2>(A, cr, cv); break;
-                case 3: if constexpr (RB > 3) cx_gate<3>(A, cr, cv); break;
-                case 4: if constexpr (RB > 4) cx_gate<4>(A, cr, cv); break;
-                default: break;
-              }
+            switch (op.q0) {
+              case 0: cx_gate<0>(A, tsel, cr, cv); break;
+              case 1: if constexpr (RB > 1) cx_gate<1>(A, tsel, cr, cv); break;
+              case 2: if constexpr (RB > 2) cx_gate<2>(A, tsel, cr, cv); break;
+              case 3: if constexpr (RB > 3) cx_gate<3>(A, tsel, cr, cv); break;
+              case 4: if constexpr (RB > 4) cx_gate<4>(A, tsel, cr, cv); break;
+              default: break;
             }
           } else {   // RT_DENSE2
             switch (op.q0 * 8 + op.q1) {
@@ -785,9 +801,7 @@ struct RtKernel {
             const bool odd = ny & 1;
             const unsigned zr = op.u.p.zr;
             const unsigned xr = op.u.p.xr;
-            if (xr) flip_ket_mask(A, xr);
-            double s = gen_term<0>(A, xr, zr, tpar, odd);
-            if (xr) flip_ket_mask(A, xr);
+            double s = gen_dispatch(A, xr, zr, tpar, odd);
             s *= op.u.p.coef;
             s = warp_sum(s);
             if ((tid & 31u) == 0) accs[op.q0 * NW + (tid >> 5)] += s;
