@@ -12,7 +12,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(CSRC, "libb200q.so")
-SOURCES = ["api.cu", "rtile.cu", "rtile_d.cu", "rtile_f.cu"]          # compiled in parallel, one object each
+SOURCES = ["api.cu", "rtile.cu"] + [f"rtile_k_{p}_{k}.cu" for p in "df"
+                                    for k in ("fwd", "ws", "adj", "adj2")]          # compiled in parallel, one object each
 HEADERS = ["common.cuh", "gates.cuh", "measure.cuh", "sample.cuh", "adjoint.cuh", "tile.cuh",
            "rtile.cuh", "rtile_host.h", "rtile_launch.cuh", os.path.join("..", "..", "include", "b200q.h")]
 OBJDIR = os.path.join(CSRC, "build")
@@ -66,7 +67,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             raise RuntimeError(f"nvcc failed:\n{' '.join(cmd)}\n{res.stdout}\n{res.stderr}")
         return obj, res.stderr
 
-    with ThreadPoolExecutor(max_workers=len(SOURCES)) as pool:
+    with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 4)) as pool:
         results = list(pool.map(compile_one, SOURCES))
     if verbose:
         for _, log in results:

@@ -5,17 +5,14 @@
 #include <algorithm>
 
 #include "common.cuh"
-#include "rtile.cuh"
-#include "rtile_host.h"
+#include "rtile_launch.cuh"
 
 namespace b200q {
 
-int rtile_run_c128(bool ws, void* v0, void* v1, const RtArgs& a, int64_t batch, const RtOp* od,
-                   const double2* md, int nslots, double scale, double* out_dev, double* partials,
-                   size_t pcap, cudaStream_t s);
-int rtile_run_c64(bool ws, void* v0, void* v1, const RtArgs& a, int64_t batch, const RtOp* od,
-                  const double2* md, int nslots, double scale, double* out_dev, double* partials,
-                  size_t pcap, cudaStream_t s);
+#define RT_EXTERN(T, RB, NV, TH, MINB, WS) \
+  extern template int rtile_launch<T, RB, NV, TH, MINB, WS>(RT_LAUNCH_ARGS);
+RT_FOR_EACH_VARIANT(RT_EXTERN)
+#undef RT_EXTERN
 
 static int env_int(const char* name, int dflt) {
   const char* e = getenv(name);
@@ -30,11 +27,17 @@ static int rtile_variant() {
   return v;
 }
 
+// adjoint kernel (two vectors): 0 = 512 threads x 1 CTA/SM, 1 = 256 threads x 2 CTAs/SM
+static int rtile_adj_variant() {
+  static const int v = env_int("B200Q_RT_ADJ_VARIANT", 0);
+  return v;
+}
+
 // geometry of the register-tiled kernel: (dtype, nvec) -> (T, RB, THREADS = consumer threads)
 void rtile_geom(int dtype, int nvec, int& T, int& RB, int& threads) {
   if (nvec <= 1) {
     threads = rtile_variant() == 0 ? 128 : 256; RB = dtype == B200Q_C128 ? 4 : 5;
-  } else { threads = 512; RB = dtype == B200Q_C128 ? 3 : 4; }
+  } else { threads = rtile_adj_variant() == 0 ? 512 : 256; RB = dtype == B200Q_C128 ? 3 : 4; }
   T = (threads == 128 ? 7 : threads == 256 ? 8 : 9) + RB;
 }
 
@@ -106,10 +109,22 @@ int rtile_dispatch(void* v0, void* v1, int n, int dtype, int64_t batch, const in
   const bool ws = rtile_variant() == 0;
   if (ws && !v1)
     B200Q_REQUIRE(a.prefetch, "rtile: the warp-specialised kernel needs 16-byte aligned runs (L=%d)", L);
-  if (dtype == B200Q_C128)
-    return rtile_run_c128(ws, v0, v1, a, batch, od, md, nslots, scale, out_dev, partials, pcap, s);
-  if (dtype == B200Q_C64)
-    return rtile_run_c64(ws, v0, v1, a, batch, od, md, nslots, scale, out_dev, partials, pcap, s);
+#define RT_GO(T, RB, NV, TH, MINB, WS) \
+  return rtile_launch<T, RB, NV, TH, MINB, WS>(v0, v1, a, batch, od, md, nslots, scale, out_dev, partials, pcap, s)
+  const bool adj2 = rtile_adj_variant() != 0;
+  if (dtype == B200Q_C128) {
+    if (!v1 && ws) RT_GO(double, 4, 1, 128, 3, true);
+    if (!v1) RT_GO(double, 4, 1, 256, 2, false);
+    if (adj2) RT_GO(double, 3, 2, 256, 2, false);
+    RT_GO(double, 3, 2, 512, 1, false);
+  }
+  if (dtype == B200Q_C64) {
+    if (!v1 && ws) RT_GO(float, 5, 1, 128, 3, true);
+    if (!v1) RT_GO(float, 5, 1, 256, 2, false);
+    if (adj2) RT_GO(float, 4, 2, 256, 2, false);
+    RT_GO(float, 4, 2, 512, 1, false);
+  }
+#undef RT_GO
   set_error("unknown dtype %d", dtype);
   return 2;
 }

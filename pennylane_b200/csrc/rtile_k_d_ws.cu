@@ -1,0 +1,6 @@
+// b200q — one explicit instantiation of the register-tiled kernel (see rtile_launch.cuh).
+#include "rtile_launch.cuh"
+
+namespace b200q {
+template int rtile_launch<double, 4, 1, 128, 3, true>(RT_LAUNCH_ARGS);
+}  // namespace b200q

@@ -1,5 +1,6 @@
-// b200q — launch templates of the register-tiled kernel, instantiated once per precision in
-// rtile_d.cu / rtile_f.cu (separate translation units: they compile in parallel).
+// b200q — launch template of the register-tiled kernel.  Every kernel variant is explicitly
+// instantiated in its own translation unit (rtile_k_*.cu, one line each) so that the large
+// interpreter kernels compile in parallel; rtile.cu sees them as extern templates.
 #pragma once
 #include <stdlib.h>
 
@@ -22,8 +23,8 @@ k_rt_final_reduce(const double* __restrict__ partials, double* __restrict__ out,
   if (threadIdx.x == 0) out[blockIdx.x] = acc * scale;
 }
 
-template <typename T, int RB, int NV, int THREADS, int MINB, bool WS = false>
-static int rtile_launch(void* v0, void* v1, const RtArgs& a, int64_t batch, const RtOp* ops_dev,
+template <typename T, int RB, int NV, int THREADS, int MINB, bool WS>
+int rtile_launch(void* v0, void* v1, const RtArgs& a, int64_t batch, const RtOp* ops_dev,
                         const double2* mats_dev, int nslots, double scale, double* out_dev,
                         double* partials, size_t partial_cap, cudaStream_t s) {
   const size_t smem = ((size_t)NV * sizeof(cx<T>) << a.T) * (WS ? 2 : 1) + sizeof(cx<T>) * ((a.nmat + 1) & ~1) +
@@ -59,18 +60,16 @@ static int rtile_launch(void* v0, void* v1, const RtArgs& a, int64_t batch, cons
   return 0;
 }
 
-// one precision: the three kernel variants (warp-specialised forward, 256-thread forward, adjoint)
-template <typename T>
-static int rtile_run(bool ws, void* v0, void* v1, const RtArgs& a, int64_t batch, const RtOp* od,
-                     const double2* md, int nslots, double scale, double* out_dev, double* partials,
-                     size_t pcap, cudaStream_t s) {
-  constexpr int RBF = sizeof(T) == 8 ? 4 : 5;      // register bits, forward
-  constexpr int RBA = sizeof(T) == 8 ? 3 : 4;      // register bits, adjoint (two vectors)
-  if (!v1 && ws)
-    return rtile_launch<T, RBF, 1, 128, 3, true>(v0, v1, a, batch, od, md, nslots, scale, out_dev, partials, pcap, s);
-  if (!v1)
-    return rtile_launch<T, RBF, 1, 256, 2>(v0, v1, a, batch, od, md, nslots, scale, out_dev, partials, pcap, s);
-  return rtile_launch<T, RBA, 2, 512, 1>(v0, v1, a, batch, od, md, nslots, scale, out_dev, partials, pcap, s);
-}
+#define RT_LAUNCH_ARGS                                                                          \
+  void *v0, void *v1, const RtArgs &a, int64_t batch, const RtOp *ops_dev,                      \
+      const double2 *mats_dev, int nslots, double scale, double *out_dev, double *partials,     \
+      size_t partial_cap, cudaStream_t s
+
+// the variants that exist (kept in sync with rtile_k_*.cu and rtile_run in rtile.cu)
+#define RT_FOR_EACH_VARIANT(X)                                                                  \
+  X(double, 4, 1, 256, 2, false) X(double, 4, 1, 128, 3, true) X(double, 3, 2, 512, 1, false)   \
+  X(double, 3, 2, 256, 2, false)                                                                \
+  X(float, 5, 1, 256, 2, false) X(float, 5, 1, 128, 3, true) X(float, 4, 2, 512, 1, false)      \
+  X(float, 4, 2, 256, 2, false)
 
 }  // namespace b200q

@@ -28,7 +28,15 @@ def get_final_state(circuit, dtype=np.complex128, device=None, buffer=None, fusi
     ops_ = list(circuit.operations)
     n = circuit.num_wires
     prep = ops_[0] if ops_ and _is_prep(ops_[0]) else None
-    sv = StateVector(n, dtype=dtype, device=device, buffer=buffer)
+    # A broadcast tape gets its (B, 2^n) state up front: growing the state at the first batched
+    # gate (simulate.py:235) would hold the old and the new buffer at once — at 32 qubits,
+    # B = 2, complex128 that is 64 + 128 GiB on a 180 GB device.  Gates before the first
+    # batched one then act on B identical copies, which costs time but not memory.
+    B = getattr(circuit, "batch_size", None)
+    if buffer is None and B is not None and B > 1 and prep is None:
+        sv = StateVector(n, dtype=dtype, device=device, batch=int(B))
+    else:
+        sv = StateVector(n, dtype=dtype, device=device, buffer=buffer)
     if buffer is not None:
         sv.reset()
     if prep is not None:

@@ -1,9 +1,11 @@
 #!/bin/bash
-# bench sweep over kernel variant / run length (forward only)
+# bench sweep: each argument is a string of environment assignments (plus optional bench args after --)
 mkdir -p gpurun_out
-show() { python -c "import sys,json; d=json.loads(open('$1').read().strip().split('\n')[-1]); print('$2', round(d['value']), round(d['roofline']['frac'],3), d['state_sweeps_per_step'], d.get('adjoint',{}).get('seconds_per_step'))"; }
-for cfg in ${CFGS:-"1 4" "1 5" "0 5" "0 4"}; do
-  set -- $cfg
-  B200Q_RT_VARIANT=$1 B200Q_TILE_L=$2 timeout 600 python bench.py --no-cpu-baseline --no-adjoint > gpurun_out/sweep_v$1_L$2.json 2> gpurun_out/sweep_v$1_L$2.err; echo "rc=$?"
-  show gpurun_out/sweep_v$1_L$2.json "v$1 L$2"
+i=0
+for cfg in "$@"; do
+  i=$((i+1))
+  envs="${cfg%%--*}"; args=""
+  if [[ "$cfg" == *--* ]]; then args="--${cfg#*--}"; fi
+  env $envs timeout 900 python bench.py --no-cpu-baseline $args > gpurun_out/sweep_$i.json 2> gpurun_out/sweep_$i.err; echo "[$cfg] rc=$?"
+  python -c "import sys,json; d=json.loads(open('gpurun_out/sweep_$i.json').read().strip().split('\n')[-1]); print('   ', round(d['value']), round(d['roofline']['frac'],3), d['state_sweeps_per_step'], 'e2e', round(d['e2e']['value']), 'adjoint', (d.get('adjoint') or {}).get('seconds_per_step'))" || tail -3 gpurun_out/sweep_$i.err
 done
