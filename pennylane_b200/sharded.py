@@ -386,6 +386,32 @@ class CudaEngine:
     def probs_device(self, local_wires):
         return self.sv.probs_device(local_wires)
 
+    def probs_inplace_device(self, chunk_bits: int = 26):
+        """|psi|^2 over all local wires written over the state itself (the state is consumed):
+        at 33 local qubits the complex128 shard is 128 GiB and a separate 64 GiB probability
+        vector does not fit next to it.  Chunk c of 2^chunk_bits amplitudes is reduced into a
+        staging buffer by the ordinary probs kernel and then copied to doubles [c*K, (c+1)*K)
+        of the state buffer — bytes whose amplitudes were consumed by this or an earlier chunk
+        (8(c+1)K <= 16cK for c >= 1; chunk 0 is already in the staging buffer)."""
+        import torch
+        from ._lib import check, int_array
+
+        sv = self.sv
+        if sv.batch != 1:
+            raise NotImplementedError("in-place probabilities of a broadcast state")
+        kb = min(int(chunk_bits), sv.n)
+        K = 1 << kb
+        stage = torch.empty(K, dtype=torch.float64, device=sv.device)
+        front = sv.data.view(torch.float64).reshape(-1)[: 1 << sv.n]
+        elem = 16 if sv.dtype_code else 8
+        bits = int_array(list(range(kb - 1, -1, -1)))
+        w, wb = sv.workspace()
+        for c in range(1 << (sv.n - kb)):
+            check(sv.lib.b200q_probs(C.c_void_p(sv.data.data_ptr() + c * K * elem), kb, sv.dtype_code, 1,
+                                     bits, kb, C.c_void_p(stage.data_ptr()), w, wb, sv.stream))
+            front[c * K:(c + 1) * K].copy_(stage)
+        return front
+
     # -- sampler building blocks (all on 2**m float64 device vectors) ---------------------------
     def _scalar(self, value):
         import torch
@@ -809,9 +835,11 @@ class ShardedStateVector:
         return r if self.batch > 1 else float(r[0])
 
     # -- sampling ------------------------------------------------------------------------------
-    def sample(self, shots, rng, wires=None, exact=True):
+    def sample(self, shots, rng, wires=None, exact=True, consume=None):
         """(shots, m) int64 samples, bit-identical on every rank and to sampling.py:500-531 under
-        the same Generator state (every rank must hold an identically seeded ``rng``)."""
+        the same Generator state (every rank must hold an identically seeded ``rng``).
+        ``consume``: build the probabilities over the state itself (the state is destroyed);
+        default: only when a separate probability vector would not fit in free device memory."""
         import torch
 
         if self.batch != 1:
@@ -822,7 +850,13 @@ class ShardedStateVector:
             return self.engine.sample_replicated(p, shots, rng, exact)
         self.restore_identity_map()
         eng, dist, nl = self.engine, self.dist, self.nl
-        p = eng.probs_device(list(range(nl)))[0]
+        if consume is None and hasattr(eng, "probs_inplace_device") and torch.cuda.is_available():
+            free, _ = torch.cuda.mem_get_info()
+            consume = free < (8 << nl) + (2 << 30)
+        if consume and hasattr(eng, "probs_inplace_device"):
+            p = eng.probs_inplace_device()
+        else:
+            p = eng.probs_device(list(range(nl)))[0]
         u = rng.random(shots)
         nan = np.array([1.0 if eng.has_nan(p, nl) else 0.0])
         if self._ordered_sum(nan)[0] > 0:

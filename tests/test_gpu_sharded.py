@@ -71,6 +71,14 @@ def _check_all(dist, n, seed, fusion, world_note=""):
         got = simulate_sharded(tape, dist, rng=np.random.default_rng(seed), fusion=fusion)
         refs = o_sim.simulate(tape, rng=np.random.default_rng(seed))
         out[f"samples_{kind}"] = 0.0 if np.array_equal(got, refs) else 1.0
+        # the state-consuming sampler (probabilities built over the state buffer in chunks)
+        sv2 = ShardedStateVector(n, dist, dtype=np.complex128, fusion=fusion)
+        sv2.apply_operations(ops_)
+        eng = sv2.engine
+        orig = eng.probs_inplace_device
+        eng.probs_inplace_device = lambda: orig(chunk_bits=max(3, sv2.nl - 3))   # several chunks
+        got2 = sv2.sample(2000, np.random.default_rng(seed), None, True, consume=True)
+        out[f"samples_consume_{kind}"] = 0.0 if np.array_equal(got2, refs) else 1.0
     return out
 
 
