@@ -206,6 +206,17 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def ncu_traffic(family, n):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the
+    committed `ncu --set full` capture of that kernel at this size (profiles/ncu_traffic.json,
+    written from the .ncu-rep by tools/ncu_summary.py); None when no capture matches."""
+    try:
+        table = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        return float(table[family][str(n)]["dram_bytes_per_launch"])
+    except Exception:
+        return None
+
+
 def workload_config(args, n):
     return {"workload": f"hea{n}_c128: {n}-qubit hardware-efficient ansatz, {args.layers} layers x "
                         f"(RY,RZ per wire + CNOT ring) = {2 * n * args.layers} params / "
@@ -335,14 +346,14 @@ def run_ours(args):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
-    kernel_of = {"tile_segment": "k_tile<double,256> (fused segment: 2*S per launch)",
+    kernel_of = {"tile_segment": "k_rtile<double,4,1,256,2> (fused segment: 2*S per launch)",
                  "RY": "k_dense<double,1,byval>", "RZ": "k_parity_phase<double>",
                  "CNOT": "k_dense<double,1,byval> (1 control)"}
     all_gate_bytes = sum(v["bytes"] for k, v in fam_stats.items() if k != "expval")
     all_gate_secs = sum(v["seconds"] for k, v in fam_stats.items() if k != "expval")
     roofline = {"bound": "hbm", "kernel": kernel_of.get(dom, dom),
                 "achieved": fam_stats[dom]["gbps"], "peak": peak, "unit": "GB/s",
-                "frac": fam_stats[dom]["gbps"] / peak, "traffic": None, "peak_source": peak_src,
+                "frac": fam_stats[dom]["gbps"] / peak, "traffic": ncu_traffic(dom, n), "peak_source": peak_src,
                 "share_of_step": fam_stats[dom]["seconds"] / (total_ms * 1e-3),
                 "per_family": {k: {"launches": v["launches"], "gbps": v["gbps"],
                                    "frac": (v["gbps"] or 0) / peak,
@@ -386,14 +397,37 @@ def run_ours(args):
     if not args.no_adjoint:
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        res, jac = dev.execute_and_compute_derivatives(tape)
+        res, jac = dev.execute_and_compute_derivatives(tape)      # first call: allocates ket + bra
         torch.cuda.synchronize()
-        adj_s = time.perf_counter() - t0
+        adj_first = time.perf_counter() - t0
+        reps = 1 if args.quick else 2
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            res, jac = dev.execute_and_compute_derivatives(tape)
+        torch.cuda.synchronize()
+        adj_s = (time.perf_counter() - t0) / reps
         S = 16.0 * (1 << n)
+        # what the reference's algorithm moves (one sweep per gate) ...
         adj_bytes = ngates * 2 * S + sum(2 * credited_bytes(o, n) for o in ops_)  # fwd + (ket+bra)
-        adjoint = {"seconds_per_step": adj_s, "params": len(jac), "n_obs": 1,
-                   "algorithmic_gbps": adj_bytes / adj_s / 1e9,
-                   "frac_of_hbm_peak": adj_bytes / adj_s / 1e9 / peak,
+        # ... and what the fused reverse sweep moves: 2*S per forward segment, 4*S (ket + bra,
+        # read + write) per reverse segment, 3*S to form the bra from the ket
+        rev_segments = None
+        fused_bytes = None
+        if args.fusion == "on":
+            from pennylane_b200.adjoint import _fused_reverse_program
+            from pennylane_b200.compiler import merge_blocks, pack_segments
+            T2, RB2, _ = sv.rt_geometry(2)
+            _, L2 = sv.default_tile(2)
+            prog = _fused_reverse_program(tape, n, RB2, args.fusion_level)
+            if prog is not None:
+                rev_segments = len(pack_segments(merge_blocks(prog[0], args.fusion_level), n, T=T2, L=L2,
+                                                 max_ops=64))
+                fused_bytes = (len(fused_segments) * 2 + rev_segments * 4 + 3) * S
+        adjoint = {"seconds_per_step": adj_s, "first_call_seconds": adj_first, "params": len(jac), "n_obs": 1,
+                   "reverse_segments": rev_segments,
+                   "fused_gbps": fused_bytes / adj_s / 1e9 if fused_bytes else None,
+                   "frac_of_hbm_peak": fused_bytes / adj_s / 1e9 / peak if fused_bytes else None,
+                   "per_gate_algorithmic_gbps": adj_bytes / adj_s / 1e9,
                    "grad_norm": float(np.linalg.norm(np.array(jac, dtype=float)))}
     clk = clocks.stop()
 
