@@ -361,6 +361,30 @@ def run_ours(args):
                                for k, v in fam_stats.items()},
                 "all_gates_gbps": all_gate_bytes / all_gate_secs / 1e9}
 
+    # The per-gate kernels (the reference's "one sweep per gate", simulate.py:214-235) beside the
+    # fused one: a few unfused launches of each gate family on wires spread over the register,
+    # timed outside the step (they are the path's fusion=0 parity mode and the sharded fallback).
+    if fused_segments is not None and not args.quick:
+        per_gate = {}
+        wires = sorted({0, n // 3, n // 2, (2 * n) // 3, n - 1})
+        probes = {"RY": [q.RY(0.3 + w, wires=w) for w in wires],
+                  "RZ": [q.RZ(0.7 + w, wires=w) for w in wires],
+                  "CNOT": [q.CNOT(wires=[w, (w + 1) % n]) for w in wires]}
+        for name, plist in probes.items():
+            for op in plist:
+                sv.apply_operation(op)
+            torch.cuda.synchronize()
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for op in plist:
+                sv.apply_operation(op)
+            e1.record()
+            torch.cuda.synchronize()
+            byt = sum(credited_bytes(op, n) for op in plist)
+            gb = byt / (e0.elapsed_time(e1) * 1e-3) / 1e9
+            per_gate[name] = {"kernel": kernel_of[name], "launches": len(plist), "gbps": gb, "frac": gb / peak}
+        roofline["per_gate_kernels"] = per_gate
+
     # e2e: public API, host parameters in / host scalar out, wall clock
     dev = qb.B200Qubit(wires=n, seed=0, fusion=args.fusion_level if args.fusion == "on" else 0)
     par = np.random.default_rng(3).uniform(0, 2 * np.pi, (args.layers, n, 2))

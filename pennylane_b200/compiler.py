@@ -532,7 +532,12 @@ def encode_segment(seg: Segment):
 # ---------------------------------------------------------------------------------------------
 RT_ROUND, RT_GEN = 6, 7
 GEN = 7            # Prim kind: generator Pauli term of a trainable gate (adjoint sweeps)
-_IO_LANES = 5      # tile positions 0..4 stay on the lanes in the first / last round
+import os as _os
+
+# tile positions 0.._IO_LANES-1 stay on the lanes in the last (store) round: every warp store
+# instruction then covers whole 2^_IO_LANES-amplitude runs (3 = single 128-byte lines of
+# complex128 measured the same gates/s as 5 on B200; 5 keeps 512-byte runs)
+_IO_LANES = int(_os.environ.get("B200Q_IO_LANES", 5))
 
 
 class _RtGate(C.Structure):

@@ -31,8 +31,16 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 k_probs_full(const cx<T>* __restrict__ state, double* __restrict__ out, const uint64_t total) {
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride)
-    out[i] = abs2_exact(state[i]);
+  constexpr int U = 4;               // independent loads in flight per thread
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + (U - 1) * stride < total; i += U * stride) {
+    cx<T> a[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) a[u] = state[i + u * stride];
+#pragma unroll
+    for (int u = 0; u < U; ++u) out[i + u * stride] = abs2_exact(a[u]);
+  }
+  for (; i < total; i += stride) out[i] = abs2_exact(state[i]);
 }
 
 // ---- marginal probabilities ---------------------------------------------------------------
@@ -150,7 +158,28 @@ k_expval_diag(const cx<T>* __restrict__ state, const int n, const PauliTerm* __r
   const uint64_t N = 1ull << n;
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   double acc = 0.0;
-  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride) {
+  // U independent 16-byte loads in flight per thread: one load per iteration left the kernel at
+  // 0.55 of the HBM peak (2.4 MB outstanding over the whole GPU against ~13 MB of bandwidth x
+  // latency).  The summation order stays a fixed function of (grid, n): deterministic.
+  constexpr int U = 8;
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + (U - 1) * stride < N; i += U * stride) {
+    cx<T> a[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) a[u] = st[i + u * stride];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const uint64_t idx = i + u * stride;
+      const double p = (double)a[u].x * (double)a[u].x + (double)a[u].y * (double)a[u].y;
+      double w = 0.0;
+      for (int t = 0; t < nterms; ++t) {
+        const double c = tt[t].coeff;
+        w += (__popcll(idx & tt[t].zmask) & 1) ? -c : c;
+      }
+      acc = fma(p, w, acc);
+    }
+  }
+  for (; i < N; i += stride) {
     const cx<T> a = st[i];
     const double p = (double)a.x * (double)a.x + (double)a.y * (double)a.y;
     double w = 0.0;
@@ -185,7 +214,38 @@ k_expval_offdiag(const cx<T>* __restrict__ state, const int n, const uint64_t xm
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   const int8_t piv = (int8_t)pivot;
   double acc = 0.0;
-  for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < half; g += stride) {
+  constexpr int U = 4;               // U pairs = 2U independent loads in flight per thread
+  uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; g + (U - 1) * stride < half; g += U * stride) {
+    cx<T> av[U], bv[U];
+    uint64_t iv[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      iv[u] = insert_zero_bits(g + u * stride, &piv, 1);
+      av[u] = st[iv[u]];
+      bv[u] = st[iv[u] ^ xmask];
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const uint64_t i = iv[u];
+      const cx<T> a = av[u], b = bv[u];
+      const double zr = (double)b.x * (double)a.x + (double)b.y * (double)a.y;
+      const double zi = (double)b.x * (double)a.y - (double)b.y * (double)a.x;
+      double w_re = 0.0, w_im = 0.0;
+      for (int t = 0; t < nterms; ++t) {
+        double c = tt[t].coeff;
+        if (__popcll(i & tt[t].zmask) & 1) c = -c;
+        switch (tt[t].ny & 3) {
+          case 0: w_re += c; break;
+          case 1: w_im += c; break;
+          case 2: w_re -= c; break;
+          default: w_im -= c; break;
+        }
+      }
+      acc += 2.0 * (w_re * zr - w_im * zi);
+    }
+  }
+  for (; g < half; g += stride) {
     const uint64_t i = insert_zero_bits(g, &piv, 1);
     const uint64_t j = i ^ xmask;
     const cx<T> a = st[i], b = st[j];

@@ -152,7 +152,8 @@ def test_round_schedule_reproduces_circuit(level, n, T, L, RB, sww):
         ref = apply_operation(op, ref)
     segs = compile_ops(ops_, n, level=level, T=T, L=L)
     psi = state.reshape(-1).copy()
-    lanes = min(5, T - RB)
+    from pennylane_b200.compiler import _IO_LANES
+    lanes = min(_IO_LANES, T - RB)
     for seg in segs:
         if seg.tile_bits is None:
             p = seg.prims[0]
