@@ -178,6 +178,14 @@ int b200q_apply_rtile(void* vec0, void* vec1, int n, int dtype, int64_t batch, c
                       int T, int L, const void* ops_host, int nops, const void* mats_host, int nmat,
                       int nslots, int write0, uint64_t base_hi, double scale, double* out_dev,
                       void* work, size_t work_bytes, void* stream);
+/* Same, for a broadcast state (simulate.py:235, apply_operation.py:186-197): mats_host holds
+ * `batch` consecutive tables of nmat entries, batch element b reads table b (gates whose
+ * parameters carry a leading batch axis; tables of unbatched records are simply repeated). */
+int b200q_apply_rtile_bcast(void* vec0, void* vec1, int n, int dtype, int64_t batch,
+                            const int* tile_bits, int T, int L, const void* ops_host, int nops,
+                            const void* mats_host, int nmat, int nslots, int write0,
+                            uint64_t base_hi, double scale, double* out_dev, void* work,
+                            size_t work_bytes, void* stream);
 
 /* One reverse-sweep step of adjoint differentiation on vecs = [1 + n_bras][2^n] (row 0 = ket):
  *   z_b = <bra_b| G |ket>,  ket <- A ket,  bra_b <- A bra_b      (A = U^dagger, k <= 3)

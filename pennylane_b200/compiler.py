@@ -78,14 +78,25 @@ def _is_diag(m):
     return not np.any(m[~np.eye(m.shape[0], dtype=bool)])
 
 
-def lower(op, bit_of) -> list[Prim]:
-    """Operator -> primitives (apply_operation.py:258-351 dispatch, re-done for the tile kernel)."""
+def lower(op, bit_of, batched_ok: bool = False) -> list[Prim]:
+    """Operator -> primitives (apply_operation.py:258-351 dispatch, re-done for the tile kernel).
+
+    ``batched_ok``: single-qubit gates with broadcast parameters (``op.batch_size``,
+    apply_operation.py:186-197) become dense blocks whose matrix carries a leading batch axis —
+    the register kernel reads one matrix table per batch element; without it they stay generic
+    per-gate launches."""
     name = op.name
     wires = list(op.wires)
     bits = [bit_of(w) for w in wires]
     if name in ("Identity", "Barrier", "Snapshot", "WireCut"):
         return []
-    if getattr(op, "batch_size", None) is not None or hasattr(op, "state_vector"):
+    if hasattr(op, "state_vector"):
+        return [Prim(GENERIC, targets=bits, op=op)]
+    if getattr(op, "batch_size", None) is not None:
+        if batched_ok and len(bits) == 1 and getattr(op, "has_matrix", True):
+            m = np.asarray(op.matrix(), dtype=complex)
+            if m.ndim == 3 and m.shape[1:] == (2, 2):
+                return [Prim(DENSE1, targets=bits, mat=m)]
         return [Prim(GENERIC, targets=bits, op=op)]
     data = op.data
     if name == "GlobalPhase":
@@ -346,7 +357,8 @@ def merge_blocks(prims: list[Prim], level: int = 1) -> list[Prim]:
                 flush_controlled_by(b)
             m = p.mat
             for pos, b in enumerate(p.targets):
-                if b in pending and not pending[b].ctrl and not pending[b].deferred:
+                if b in pending and not pending[b].ctrl and not pending[b].deferred \
+                        and np.ndim(pending[b].mat) == 2:
                     q = pending.pop(b)
                     m = m @ _embed(q.mat, pos)
                     p.ngates += q.ngates
@@ -368,7 +380,9 @@ def merge_blocks(prims: list[Prim], level: int = 1) -> list[Prim]:
     # normalise accumulated blocks (a product may have become diagonal / X / identity)
     norm = []
     for p in out:
-        if p.kind == DENSE1 and not p.ctrl:
+        if p.kind == DENSE1 and np.ndim(p.mat) == 3:
+            norm.append(p)                       # broadcast block: one matrix per batch element
+        elif p.kind == DENSE1 and not p.ctrl:
             q = _dense(p.targets, {}, p.mat)
             q.ngates = p.ngates
             if q.kind == DIAG and np.allclose(q.mat, 1.0):
@@ -455,13 +469,14 @@ def pack_segments(prims: list[Prim], n: int, T: int = 12, L: int = 5, max_ops: i
     return segments
 
 
-def compile_ops(ops_, n: int, bit_of=None, level: int = 1, T: int = 12, L: int = 5):
+def compile_ops(ops_, n: int, bit_of=None, level: int = 1, T: int = 12, L: int = 5,
+                batched_ok: bool = False):
     """Operators -> list of :class:`Segment`."""
     if bit_of is None:
         bit_of = lambda w: n - 1 - int(w)          # noqa: E731
     prims: list[Prim] = []
     for op in ops_:
-        prims.extend(lower(op, bit_of))
+        prims.extend(lower(op, bit_of, batched_ok))
     prims = merge_blocks(prims, level)
     return pack_segments(prims, n, T=T, L=L)
 
@@ -694,7 +709,16 @@ def encode_rt_segment(seg: Segment, RB: int, sww: int = 3, rounds=None):
         rounds = schedule_rounds(seg.prims, tile_bits, RB, sww)
     nrec = sum(1 + len(r.prims) for r in rounds)
     ops_arr = (RtOp * nrec)()
-    mats: list[complex] = []
+    cols: list[np.ndarray] = []      # (k,) or (B, k) pieces of the matrix table, in order
+    nmat = 0
+
+    def push(arr, batched=False):
+        nonlocal nmat
+        arr = np.asarray(arr, dtype=complex)
+        arr = arr.reshape(arr.shape[0], -1) if batched else arr.reshape(-1)
+        cols.append(arr)
+        nmat += arr.shape[-1]
+
     i = 0
     for rnd in rounds:
         o = ops_arr[i]; i += 1
@@ -722,7 +746,7 @@ def encode_rt_segment(seg: Segment, RB: int, sww: int = 3, rounds=None):
 
         for p in rnd.prims:
             o = ops_arr[i]; i += 1
-            o.mat_off = len(mats)
+            o.mat_off = nmat
             if p.kind == GEN:
                 o.kind = RT_GEN
                 o.q0 = int(p.slot)
@@ -743,32 +767,40 @@ def encode_rt_segment(seg: Segment, RB: int, sww: int = 3, rounds=None):
                         o.u.d.src[j] = rbit[pp] if pp in rbit else 32 + tbit[pp]
                     else:
                         o.u.d.src[j] = 64 + b
-                mats.extend(np.asarray(p.mat, dtype=complex).reshape(-1))
+                push(p.mat)
             else:
                 o.kind = p.kind
                 g = o.u.g
                 g.ctrl_r, g.cval_r, g.ctrl_t, g.cval_t, g.ctrl_e, g.cval_e = split_mask(p.ctrl)
                 if p.kind == DENSE1:
                     o.q0 = rbit[pos[p.targets[0]]]
-                    mats.extend(np.asarray(p.mat, dtype=complex).reshape(-1))
+                    push(p.mat, np.ndim(p.mat) == 3)
                     if p.mat0 is not None:
                         o.kind = DENSE1 | 0x100
-                        mats.extend(np.asarray(p.mat0, dtype=complex).reshape(-1))
+                        push(p.mat0, np.ndim(p.mat0) == 3)
                 elif p.kind == DENSE2:
                     q0, q1 = rbit[pos[p.targets[0]]], rbit[pos[p.targets[1]]]
                     m = np.asarray(p.mat, dtype=complex)
                     if q0 < q1:
                         q0, q1, m = q1, q0, _swap_2q(m)
                     o.q0, o.q1 = q0, q1
-                    mats.extend(m.reshape(-1))
+                    push(m)
                 elif p.kind == CX:
                     o.q0 = rbit[pos[p.targets[0]]]
                 elif p.kind == PARITY:
                     g.par_r, _, g.par_t, _, g.par_e, _ = split_mask({b: 1 for b in p.other})
-                    mats.extend(np.asarray(p.mat, dtype=complex).reshape(-1)[:2])
+                    push(np.asarray(p.mat, dtype=complex).reshape(-1)[:2])
                 else:  # pragma: no cover
                     raise ValueError(f"primitive kind {p.kind} has no register-kernel record")
-            if len(mats) % 2:
-                mats.append(0j)
-    table = np.ascontiguousarray(np.array(mats if mats else [0j, 0j], dtype=np.complex128))
+            if nmat % 2:
+                push([0j])
+    if not cols:
+        push([0j, 0j])
+    B = max((c.shape[0] for c in cols if c.ndim == 2), default=0)
+    if B:        # broadcast parameters: one table row per batch element
+        table = np.concatenate([c if c.ndim == 2 else np.broadcast_to(c, (B, c.shape[0])) for c in cols],
+                               axis=1)
+    else:
+        table = np.concatenate(cols)
+    table = np.ascontiguousarray(table, dtype=np.complex128)
     return ops_arr, table, nrec

@@ -794,6 +794,16 @@ int b200q_apply_rtile(void* vec0, void* vec1, int n, int dtype, int64_t batch, c
                         work, work_bytes, (cudaStream_t)stream);
 }
 
+int b200q_apply_rtile_bcast(void* vec0, void* vec1, int n, int dtype, int64_t batch,
+                            const int* tile_bits, int T, int L, const void* ops_host, int nops,
+                            const void* mats_host, int nmat, int nslots, int write0,
+                            uint64_t base_hi, double scale, double* out_dev, void* work,
+                            size_t work_bytes, void* stream) {
+  return rtile_dispatch(vec0, vec1, n, dtype, batch, tile_bits, T, L, (const RtOp*)ops_host, nops,
+                        (const double2*)mats_host, nmat, nslots, write0, base_hi, scale, out_dev,
+                        work, work_bytes, (cudaStream_t)stream, 1);
+}
+
 int b200q_adjoint_step(void* vecs, int n, int dtype, int n_bras, const int* tgt_bits, int k,
                        const int* ctrl_bits, const int* ctrl_vals, int nc, const void* adj_host,
                        const void* gen_host, double* out_dev, void* work, size_t work_bytes,

@@ -44,7 +44,7 @@ void rtile_geom(int dtype, int nvec, int& T, int& RB, int& threads) {
 int rtile_dispatch(void* v0, void* v1, int n, int dtype, int64_t batch, const int* tile_bits,
                    int Tn, int L, const RtOp* ops_host, int nops, const double2* mats_host,
                    int nmat, int nslots, int write0, uint64_t base_hi, double scale,
-                   double* out_dev, void* work, size_t work_bytes, cudaStream_t s) {
+                   double* out_dev, void* work, size_t work_bytes, cudaStream_t s, int mat_batched) {
   int gT, gRB, gTh;
   rtile_geom(dtype, v1 ? 2 : 1, gT, gRB, gTh);
   B200Q_REQUIRE(Tn == gT && Tn <= n && L >= 0 && L <= Tn, "rtile: T=%d (need %d) L=%d n=%d", Tn, gT, L, n);
@@ -95,7 +95,8 @@ int rtile_dispatch(void* v0, void* v1, int n, int dtype, int64_t batch, const in
   const size_t elem = dtype == B200Q_C128 ? 16 : 8;
   a.prefetch = ((pf_knob || (rtile_variant() == 0 && !v1)) && ((elem << L) >= 16) && (((uintptr_t)v0 | (uintptr_t)v1) % 16 == 0)) ? 1 : 0;
   const size_t ops_bytes = (size_t)nops * sizeof(RtOp);
-  const size_t mat_bytes = (size_t)nmat * sizeof(double2);
+  const size_t mat_bytes = (size_t)nmat * sizeof(double2) * (mat_batched ? (size_t)batch : 1);
+  const long long mat_bstride = mat_batched ? nmat : 0;
   B200Q_REQUIRE(work && ops_bytes + mat_bytes + 512 <= kTermRegion && work_bytes >= kWorkBytes,
                 "rtile: segment tables too large for the workspace");
   char* w = (char*)work;
@@ -110,7 +111,7 @@ int rtile_dispatch(void* v0, void* v1, int n, int dtype, int64_t batch, const in
   if (ws && !v1)
     B200Q_REQUIRE(a.prefetch, "rtile: the warp-specialised kernel needs 16-byte aligned runs (L=%d)", L);
 #define RT_GO(T, RB, NV, TH, MINB, WS) \
-  return rtile_launch<T, RB, NV, TH, MINB, WS>(v0, v1, a, batch, od, md, nslots, scale, out_dev, partials, pcap, s)
+  return rtile_launch<T, RB, NV, TH, MINB, WS>(v0, v1, a, batch, od, md, mat_bstride, nslots, scale, out_dev, partials, pcap, s)
   const bool adj2 = rtile_adj_variant() != 0;
   if (dtype == B200Q_C128) {
     if (!v1 && ws) RT_GO(double, 4, 1, 128, 3, true);

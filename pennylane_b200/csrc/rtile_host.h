@@ -18,6 +18,7 @@ void rtile_geom(int dtype, int nvec, int& T, int& RB, int& threads);
 int rtile_dispatch(void* v0, void* v1, int n, int dtype, int64_t batch, const int* tile_bits,
                    int Tn, int L, const RtOp* ops_host, int nops, const double2* mats_host,
                    int nmat, int nslots, int write0, uint64_t base_hi, double scale,
-                   double* out_dev, void* work, size_t work_bytes, cudaStream_t s);
+                   double* out_dev, void* work, size_t work_bytes, cudaStream_t s,
+                   int mat_batched = 0);
 
 }  // namespace b200q

@@ -346,7 +346,9 @@ class StateVector:
         from .compiler import compile_ops
 
         dT, dL = self.default_tile()
-        segs = compile_ops(ops_, self.n, bit_of=bit_of, level=level, T=T or dT, L=L if L is not None else dL)
+        rtT, _, _ = self.rt_geometry(1)
+        segs = compile_ops(ops_, self.n, bit_of=bit_of, level=level, T=T or dT, L=L if L is not None else dL,
+                           batched_ok=(T or dT) == rtT and self.n >= rtT)
         for seg in segs:
             self.run_segment(seg)
         return len(segs)
@@ -371,10 +373,19 @@ class StateVector:
                 enc = encode_rt_segment(seg, rtRB, 3 if self.dtype_code else 4)
                 seg._rt_enc = enc
             ops_arr, table, nrec = enc
-            check(self.lib.b200q_apply_rtile(
+            if table.ndim == 2:                    # broadcast parameters: one table per batch element
+                if table.shape[0] != self.batch:
+                    if self.batch != 1:
+                        raise ValueError(f"broadcast gates of batch {table.shape[0]} on a state of "
+                                         f"batch {self.batch}")
+                    self._resize_batch(table.shape[0])
+                fn = self.lib.b200q_apply_rtile_bcast
+            else:
+                fn = self.lib.b200q_apply_rtile
+            check(fn(
                 self.ptr, None, self.n, self.dtype_code, self.batch, int_array(seg.tile_bits),
                 rtT, _low_run(seg.tile_bits), C.cast(ops_arr, C.c_void_p), nrec,
-                table.ctypes.data_as(C.c_void_p), int(table.size), 0, 1, int(base_hi), 1.0, None,
+                table.ctypes.data_as(C.c_void_p), int(table.shape[-1]), 0, 1, int(base_hi), 1.0, None,
                 w, wb, self.stream))
             return
         ops_arr, table = encode_segment(seg)

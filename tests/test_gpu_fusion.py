@@ -146,6 +146,43 @@ def test_rtile_batched_states_share_the_program():
     assert np.max(np.abs(sv.to_numpy() - ref)) < 1e-12
 
 
+@pytest.mark.parametrize("dtype", [np.complex128, np.complex64])
+def test_rtile_broadcast_parameters_are_fused(dtype):
+    """Gates with a leading batch axis on their parameters (apply_operation.py:186-197) go through
+    the register-tiled kernel as dense blocks with one matrix table per batch element
+    (b200q_apply_rtile_bcast), merged with their unbatched neighbours and folded CNOTs."""
+    import pennylane_b200 as qb
+    from pennylane_b200 import ops as q
+    from pennylane_b200.compiler import GENERIC, compile_ops
+    from oracle import simulate as o_sim
+
+    n, B = 14, 3
+    rng = np.random.default_rng(44)
+    ops_ = []
+    for layer in range(3):
+        for i in range(n):
+            ops_ += [q.RY(rng.uniform(0, 6, B), wires=i), q.RZ(rng.uniform(0, 6, B), wires=i)]
+            if i % 3 == 0:
+                ops_.append(q.Hadamard(wires=i))
+            if i % 4 == 1:
+                ops_.append(q.Rot(rng.uniform(0, 6, B), 0.3, rng.uniform(0, 6, B), wires=i))
+        ops_ += [q.CNOT(wires=[i, (i + 1 + layer) % n]) for i in range(n)]
+        ops_ += [q.RX(rng.uniform(0, 6, B), wires=i) for i in range(0, n, 2)]
+        ops_.append(q.IsingZZ(0.4, wires=[1, 5]))
+    T = qb.StateVector(n, dtype=dtype).rt_geometry(1)[0]
+    segs = compile_ops(ops_, n, level=1, T=T, L=5, batched_ok=True)
+    assert all(p.kind != GENERIC for s in segs for p in s.prims) and len(segs) < 20
+    heis = q.LinearCombination(
+        [1.0] * (3 * (n - 1)),
+        [P(wires=i) @ P(wires=i + 1) for i in range(n - 1) for P in (q.PauliX, q.PauliY, q.PauliZ)])
+    tape = qb.QuantumScript(ops_, [qb.expval(heis), qb.probs(wires=[0, 7, 13])])
+    e, p = qb.B200Qubit(c_dtype=dtype, fusion=1).execute(tape)
+    re, rp = o_sim.simulate(tape)
+    tol = TOL[np.dtype(dtype)]
+    assert e.shape == (B,) and p.shape == (B, 8)
+    assert np.max(np.abs(e - re)) < tol * 30 and np.max(np.abs(p - rp)) < tol * 3
+
+
 def test_rtile_hea_matches_unfused_at_20_qubits():
     import bench
     from pennylane_b200 import StateVector
