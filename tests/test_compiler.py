@@ -240,3 +240,49 @@ def test_fused_reverse_sweep_program(level, n, T, L, RB):
             jac[param] += -sums[slot]
     assert sorted(filled) == list(range(len(trainable)))
     assert np.max(np.abs(jac - ref)) < 1e-12
+
+
+def test_reverse_sweep_keeps_one_dense_record_per_wire_and_layer():
+    """Generator terms are hoisted through a pending CNOT (Z_t -> Z_c Z_t) or deferred behind the
+    block they commute with (compiler._place_generator): the reverse sweep of [RY, RZ] + CNOT ring
+    has ONE dense record per (wire, layer), not one per rotation — and still the oracle's
+    Jacobian through the record emulator."""
+    import pennylane_b200 as qb
+    from oracle import adjoint_jacobian as o_adj
+    from oracle import simulate as o_sim
+    from oracle.apply_operation import apply_operation as o_apply
+    from pennylane_b200.adjoint import _fused_reverse_program
+    from pennylane_b200.compiler import GEN, encode_rt_segment, merge_blocks, pack_segments
+    from rt_emulator import run_records
+
+    n, layers, T, L, RB = 10, 3, 9, 5, 3
+    rng = np.random.default_rng(9)
+    ops_ = []
+    for _ in range(layers):
+        for w in range(n):
+            ops_ += [q.RY(rng.uniform(0, 6), wires=w), q.RZ(rng.uniform(0, 6), wires=w)]
+        ops_ += [q.CNOT(wires=[w, (w + 1) % n]) for w in range(n)]
+    obs = q.PauliZ(wires=0) @ q.PauliY(wires=3)
+    tape = qb.QuantumScript(ops_, [qb.expval(obs)])
+    prims, filled, trainable = _fused_reverse_program(tape, n, RB, 1)
+    merged = merge_blocks(prims, 1)
+    assert sum(p.kind == DENSE1 for p in merged) == n * layers
+    assert sum(p.kind == GEN for p in merged) == 2 * n * layers
+    # hoisted Z terms picked up the CNOT's control: two Z factors, no X part
+    assert any(p.kind == GEN and len(p.zbits) == 2 and not p.targets for p in merged)
+    state, _ = o_sim.get_final_state(tape)
+    ref = np.array(o_adj.adjoint_jacobian(tape, state), dtype=float)
+    ket = state.reshape(-1).copy()
+    bra = 2.0 * o_apply(obs, state).reshape(-1)
+    jac = np.zeros(len(trainable))
+    for seg in pack_segments(merged, n, T=T, L=L, max_ops=64):
+        local = {}
+        for p in seg.prims:
+            if p.kind == GEN:
+                p.slot = local.setdefault(p.param, len(local))
+        arr, table, nrec = encode_rt_segment(seg, RB)
+        ket, bra, sums = run_records(ket, n, seg.tile_bits, arr, table, RB, bra=bra, nslots=len(local))
+        for param, slot in local.items():
+            jac[param] += -sums[slot]
+    assert sorted(filled) == list(range(len(trainable)))
+    assert np.max(np.abs(jac - ref)) < 1e-12
