@@ -39,6 +39,8 @@ product constructs ``CudaEngine`` only and never falls back.
 """
 from __future__ import annotations
 
+import os
+
 import ctypes as C
 from dataclasses import dataclass, field
 
@@ -276,7 +278,7 @@ def plan_remap(phys, nl, want_local, nxt):
     return swaps, ExchangeStep(rank_bits, k), phys
 
 
-def plan(ops_, n, g, phys=None, bit_of=None):
+def plan(ops_, n, g, phys=None, bit_of=None, defer=None):
     """Cut an operator list into run steps separated by exchanges.  Returns (steps, final phys).
 
     List scheduling over the circuit's dependency order: a run step takes every operator that
@@ -288,6 +290,9 @@ def plan(ops_, n, g, phys=None, bit_of=None):
     if bit_of is None:
         bit_of = lambda w: n - 1 - int(w)            # noqa: E731
     phys = list(range(n)) if phys is None else list(phys)
+    if defer is None:
+        defer = os.environ.get("B200Q_SHARD_DEFER", "1") != "0"
+    deferred_once: set = set()
     steps = []
     remaining = list(ops_)
     while remaining:
@@ -310,10 +315,47 @@ def plan(ops_, n, g, phys=None, bit_of=None):
             raise RuntimeError("sharded planner made no progress")
         nxt = _next_use(keep, 0, n, bit_of)
         swaps, ex, new_phys = plan_remap(phys, nl, first_must, nxt)
+        if defer:
+            leaving = {b for b in range(n) if new_phys[b] >= nl and phys[b] < nl}
+            run, keep = _defer_trailing_1q(run, keep, remaining, leaving, bit_of, deferred_once)
         steps.append(RunStep(run, list(phys), swaps))
         steps.append(ex)
         phys, remaining = new_phys, keep
     return steps, phys
+
+
+def _defer_trailing_1q(run, keep, remaining, leaving, bit_of, deferred_once):
+    """Move the trailing single-qubit gates of a run step into the next one when the first gate
+    waiting on their wire is a CNOT targeting it.
+
+    A greedy run step of a layered ansatz is [rest of the CNOT ring of layer l][rotations of layer
+    l+1]: the rotations are runnable, the CNOTs after them are not.  In that order the fusion
+    pass cannot fold a CNOT into the rotation block on its target (the next CNOT of the ring
+    reads that wire as its control in between), and every CNOT stays a record of its own.  Run
+    one step later, the rotations precede their CNOT and the pair is ONE controlled-select record
+    (compiler.merge_blocks).  Wires about to become rank bits are left alone (their gates would
+    be blocked in the next step), and a gate is deferred at most once (termination)."""
+    first_keep = {}
+    for op in keep:
+        for w in op.wires:
+            first_keep.setdefault(bit_of(w), op)
+    moved, closed = set(), set()
+    for op in reversed(run):
+        bits = {bit_of(w) for w in op.wires}
+        if len(bits) == 1:
+            (b,) = bits
+            nxt_op = first_keep.get(b)
+            if (b not in closed and b not in leaving and id(op) not in deferred_once
+                    and nxt_op is not None and nxt_op.name == "CNOT"
+                    and bit_of(nxt_op.wires[1]) == b):
+                moved.add(id(op))
+                continue
+        closed |= bits
+    if not moved:
+        return run, keep
+    deferred_once |= moved
+    kept = {id(op) for op in keep} | moved
+    return [op for op in run if id(op) not in moved], [op for op in remaining if id(op) in kept]
 
 
 # ---------------------------------------------------------------------------------------------
