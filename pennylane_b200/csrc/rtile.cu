@@ -14,6 +14,65 @@ namespace b200q {
 RT_FOR_EACH_VARIANT(RT_EXTERN)
 #undef RT_EXTERN
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
+typedef CUresult (*TmaEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                CUtensorMapFloatOOBfill);
+static TmaEncodeFn tma_encode_fn() {
+  static TmaEncodeFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return (TmaEncodeFn)p;
+  }();
+  return fn;
+}
+
+// The tile of a segment as ONE box of a tensor map over the state: dim 0 = the contiguous run of
+// 2^L amplitudes (as 8-byte elements), then one dim per group of consecutive tile bits (box =
+// whole dim) or non-tile bits (box = 1, coordinate = those bits of the tile base).  Fills
+// a.tma_rank / tma_lo / tma_len and both maps; leaves tma_rank = 0 when the shape does not fit
+// (more than 5 dims, a tile group wider than 8 bits, runs shorter than 16 bytes).
+static void build_tile_maps(RtArgs& a, int n, int dtype, uint64_t inmask, int L, void* v0, void* v1,
+                            CUtensorMap& tm0, CUtensorMap& tm1) {
+  a.tma_rank = 0;
+  TmaEncodeFn enc = tma_encode_fn();
+  if (!enc) return;
+  const uint64_t ampB = dtype == B200Q_C128 ? 16 : 8;
+  cuuint64_t dims[5], strides[4];
+  cuuint32_t box[5], estr[5] = {1, 1, 1, 1, 1};
+  dims[0] = (ampB / 8) << L;
+  box[0] = (cuuint32_t)dims[0];
+  if (dims[0] > 256 || dims[0] * 8 < 16) return;
+  int rank = 1;
+  int8_t lo[5] = {0, 0, 0, 0, 0}, len[5] = {0, 0, 0, 0, 0};
+  for (int b = L; b < n;) {
+    const bool tile = (inmask >> b) & 1;
+    int e = b;
+    while (e < n && (((inmask >> e) & 1) != 0) == tile) ++e;
+    if (rank >= 5 || (tile && e - b > 8) || e - b > 31) return;
+    dims[rank] = 1ull << (e - b);
+    strides[rank - 1] = (1ull << b) * ampB;
+    box[rank] = tile ? (cuuint32_t)dims[rank] : 1u;
+    lo[rank] = (int8_t)b;
+    len[rank] = tile ? 0 : (int8_t)(e - b);
+    ++rank;
+    b = e;
+  }
+  if (rank < 2) return;
+  for (int v = 0; v < (v1 ? 2 : 1); ++v) {
+    CUresult rc = enc(v ? &tm1 : &tm0, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, (cuuint32_t)rank, v ? v1 : v0, dims,
+                      strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS) return;
+  }
+  a.tma_rank = rank;
+  for (int r = 0; r < 5; ++r) { a.tma_lo[r] = lo[r]; a.tma_len[r] = len[r]; }
+}
+
 static int env_int(const char* name, int dflt) {
   const char* e = getenv(name);
   return e ? atoi(e) : dflt;
@@ -94,6 +153,14 @@ int rtile_dispatch(void* v0, void* v1, int n, int dtype, int64_t batch, const in
   static const int pf_knob = env_int("B200Q_RT_PREFETCH", 1);                  // tuning knob
   const size_t elem = dtype == B200Q_C128 ? 16 : 8;
   a.prefetch = ((pf_knob || (rtile_variant() == 0 && !v1)) && ((elem << L) >= 16) && (((uintptr_t)v0 | (uintptr_t)v1) % 16 == 0)) ? 1 : 0;
+  // one TMA instruction per tile when the tile is a box of a <= 5-dim view of the state
+  // (B200Q_RT_TMA=0: always one bulk copy per run); broadcast states keep the per-run copies
+  CUtensorMap tm0, tm1;
+  memset(&tm0, 0, sizeof(tm0));
+  memset(&tm1, 0, sizeof(tm1));
+  static const int tma_knob = env_int("B200Q_RT_TMA", 1);                      // tuning knob
+  if (tma_knob && a.prefetch && batch == 1 && !(rtile_variant() == 0 && !v1))
+    build_tile_maps(a, n, dtype, inmask, L, v0, v1, tm0, tm1);
   const size_t ops_bytes = (size_t)nops * sizeof(RtOp);
   const size_t mat_bytes = (size_t)nmat * sizeof(double2) * (mat_batched ? (size_t)batch : 1);
   const long long mat_bstride = mat_batched ? nmat : 0;
@@ -111,7 +178,7 @@ int rtile_dispatch(void* v0, void* v1, int n, int dtype, int64_t batch, const in
   if (ws && !v1)
     B200Q_REQUIRE(a.prefetch, "rtile: the warp-specialised kernel needs 16-byte aligned runs (L=%d)", L);
 #define RT_GO(T, RB, NV, TH, MINB, WS) \
-  return rtile_launch<T, RB, NV, TH, MINB, WS>(v0, v1, a, batch, od, md, mat_bstride, nslots, scale, out_dev, partials, pcap, s)
+  return rtile_launch<T, RB, NV, TH, MINB, WS>(v0, v1, a, batch, od, md, mat_bstride, nslots, scale, out_dev, partials, pcap, s, tm0, tm1)
   const bool adj2 = rtile_adj_variant() != 0;
   if (dtype == B200Q_C128) {
     if (!v1 && ws) RT_GO(double, 4, 1, 128, 3, true);

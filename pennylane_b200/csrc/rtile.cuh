@@ -25,6 +25,8 @@
 // Reference analogue: none (default.qubit sweeps the state once per gate,
 // simulate.py:214-235).  Algorithmic bytes per launch: 2*S*NV.
 #pragma once
+#include <cuda.h>          // CUtensorMap (the descriptor is encoded on the host, rtile.cu)
+
 #include "common.cuh"
 
 namespace b200q {
@@ -83,6 +85,12 @@ struct RtArgs {
                                  // buffer with bulk async copies while the last round computes
   int nruns;                     // runs of consecutive non-tile bits (tile number -> base)
   int nd1;                       // number of predecoded single-qubit block records (<= 32)
+  int tma_rank;                  // > 0: the tile is ONE box of a rank-`tma_rank` tensor map over the
+                                 // state (dim 0 = the contiguous run, then one dim per group of
+                                 // consecutive tile / non-tile bits): one TMA instruction per tile
+                                 // instead of one bulk copy per run
+  int8_t tma_lo[5], tma_len[5];  // dims 1..rank-1: non-tile group -> coordinate = bits
+                                 // [lo, lo+len) of the tile base; tile group -> len = 0
   int8_t hi_bits[16];            // global positions of tile positions L..T-1 (ascending)
   int8_t run_s[16], run_len[16], run_g[16];   // tile-number bits [s, s+len) -> global bits [g, g+len)
   unsigned long long ntiles;     // 2^(n-T)
@@ -137,6 +145,30 @@ __device__ __forceinline__ void rt_bulk_g2s(void* dst_smem, const void* src_gmem
           rt_smem_u32(dst_smem)),
       "l"(src_gmem), "r"(bytes), "r"(rt_smem_u32(bar))
       : "memory");
+}
+// one box of the tensor map `tm` -> shared memory, completion counted on `bar`
+__device__ __forceinline__ void rt_tma_load(void* dst_smem, const CUtensorMap* tm, const int rank,
+                                            const int (&c)[5], unsigned long long* bar) {
+  const unsigned d = rt_smem_u32(dst_smem), b = rt_smem_u32(bar);
+  const unsigned long long t = reinterpret_cast<unsigned long long>(tm);
+  switch (rank) {
+    case 2:
+      asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                   ::"r"(d), "l"(t), "r"(c[0]), "r"(c[1]), "r"(b) : "memory");
+      break;
+    case 3:
+      asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                   ::"r"(d), "l"(t), "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(b) : "memory");
+      break;
+    case 4:
+      asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+                   ::"r"(d), "l"(t), "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3]), "r"(b) : "memory");
+      break;
+    default:
+      asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+                   ::"r"(d), "l"(t), "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3]), "r"(c[4]), "r"(b) : "memory");
+      break;
+  }
 }
 __device__ __forceinline__ void rt_fence_proxy_async() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -437,11 +469,39 @@ struct RtKernel {
     }
   }
 
+  // Fetch tile `t` of every vector into `tile` (non-WS kernels): every thread calls this once it
+  // no longer needs the buffer.  With a tensor map it is one TMA instruction per vector, issued
+  // by thread 0; otherwise one bulk copy per contiguous run, spread over the threads.
+  static __device__ __forceinline__ void fetch_tile(const RtArgs& a, C* vec0, C* vec1, C* tile,
+                                                    const unsigned long long t,
+                                                    unsigned long long* bar, const CUtensorMap* tm0,
+                                                    const CUtensorMap* tm1) {
+    const unsigned bytes = (unsigned)(NV * sizeof(C)) << a.T;
+    rt_fence_proxy_async();
+    if (a.tma_rank > 0) {
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        const unsigned long long base = tile_base(a, t);
+        int c[5] = {0, 0, 0, 0, 0};
+        for (int r = 1; r < a.tma_rank; ++r)
+          if (a.tma_len[r]) c[r] = (int)((base >> a.tma_lo[r]) & ((1ull << a.tma_len[r]) - 1ull));
+        rt_mbar_expect_tx(bar, bytes);
+        rt_tma_load(tile, tm0, a.tma_rank, c, bar);
+        if (NV > 1) rt_tma_load(tile + ((size_t)1 << a.T), tm1, a.tma_rank, c, bar);
+      }
+    } else {
+      if (threadIdx.x == 0) rt_mbar_expect_tx(bar, bytes);
+      __syncthreads();
+      issue_tile_copies(a, vec0, vec1, tile, t, bar);
+    }
+  }
+
   static __device__ __forceinline__ void run(const RtArgs& __restrict__ a, C* __restrict__ v0,
                                              C* __restrict__ v1, const RtOp* __restrict__ ops_g,
                                              const double2* __restrict__ mats_g,
                                              const long long mat_bstride,
-                                             double* __restrict__ partials) {
+                                             double* __restrict__ partials,
+                                             const CUtensorMap* tm0, const CUtensorMap* tm1) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const unsigned tsize = 1u << a.T;
     C* tile = reinterpret_cast<C*>(smem_raw);                                  // NV * 2^T
@@ -571,12 +631,7 @@ struct RtKernel {
       }
     }
     const bool pf = !WS && a.prefetch != 0;
-    if (pf) {                          // prologue: the CTA's first tile
-      rt_fence_proxy_async();
-      if (tid == 0) rt_mbar_expect_tx(bar, (unsigned)(NV * tsize * sizeof(C)));
-      __syncthreads();
-      issue_tile_copies(a, vec[0], vec[1], tile, blockIdx.x, bar);
-    }
+    if (pf) fetch_tile(a, vec[0], vec[1], tile, blockIdx.x, bar, tm0, tm1);   // the CTA's first tile
     unsigned phase = 0;
 
     C A[NV][NA];
@@ -609,10 +664,7 @@ struct RtKernel {
           for (int k = 0; k < NA; ++k) A[v][k] = tile[v * tsize + (tj | ldsl[THREADS + k])];
         if (a.last_round == 0 && more) {
           // single-round segment: the buffer is idle for the whole compute phase
-          rt_fence_proxy_async();
-          if (tid == 0) rt_mbar_expect_tx(bar, (unsigned)(NV * tsize * sizeof(C)));
-          __syncthreads();
-          issue_tile_copies(a, vec[0], vec[1], tile, t + gridDim.x, bar);
+          fetch_tile(a, vec[0], vec[1], tile, t + gridDim.x, bar, tm0, tm1);
           issued = true;
         }
       } else {
@@ -739,10 +791,7 @@ struct RtKernel {
           if (pf && o == a.last_round && more) {
             // the buffer is idle from here to the next tile's first transposition: fetch the
             // next tile into it while this tile's last round computes and stores
-            rt_fence_proxy_async();
-            if (tid == 0) rt_mbar_expect_tx(bar, (unsigned)(NV * tsize * sizeof(C)));
-            __syncthreads();
-            issue_tile_copies(a, vec[0], vec[1], tile, t + gridDim.x, bar);
+            fetch_tile(a, vec[0], vec[1], tile, t + gridDim.x, bar, tm0, tm1);
             issued = true;
           }
           continue;
@@ -841,8 +890,9 @@ template <typename T_, int RB, int NV, int THREADS, int MINB, bool WS = false>
 __global__ void __launch_bounds__(THREADS + (WS ? 32 : 0), MINB)
 k_rtile(const __grid_constant__ RtArgs a, cx<T_>* __restrict__ v0, cx<T_>* __restrict__ v1,
         const RtOp* __restrict__ ops_g, const double2* __restrict__ mats_g,
-        const long long mat_bstride, double* __restrict__ partials) {
-  RtKernel<T_, RB, NV, THREADS, WS>::run(a, v0, v1, ops_g, mats_g, mat_bstride, partials);
+        const long long mat_bstride, double* __restrict__ partials,
+        const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1) {
+  RtKernel<T_, RB, NV, THREADS, WS>::run(a, v0, v1, ops_g, mats_g, mat_bstride, partials, &tm0, &tm1);
 }
 
 }  // namespace b200q
