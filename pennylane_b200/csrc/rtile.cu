@@ -159,7 +159,7 @@ int rtile_dispatch(void* v0, void* v1, int n, int dtype, int64_t batch, const in
   memset(&tm0, 0, sizeof(tm0));
   memset(&tm1, 0, sizeof(tm1));
   static const int tma_knob = env_int("B200Q_RT_TMA", 1);                      // tuning knob
-  if (tma_knob && a.prefetch && batch == 1 && !(rtile_variant() == 0 && !v1))
+  if (tma_knob && a.prefetch && batch == 1 && !v1 && rtile_variant() != 0)
     build_tile_maps(a, n, dtype, inmask, L, v0, v1, tm0, tm1);
   const size_t ops_bytes = (size_t)nops * sizeof(RtOp);
   const size_t mat_bytes = (size_t)nmat * sizeof(double2) * (mat_batched ? (size_t)batch : 1);
@@ -170,6 +170,11 @@ int rtile_dispatch(void* v0, void* v1, int n, int dtype, int64_t batch, const in
   B200Q_CHECK(cudaMemcpyAsync(w, ops_host, ops_bytes, cudaMemcpyHostToDevice, s));
   const size_t moff = (ops_bytes + 255) & ~(size_t)255;
   if (nmat) B200Q_CHECK(cudaMemcpyAsync(w + moff, mats_host, mat_bytes, cudaMemcpyHostToDevice, s));
+  if (a.tma_rank > 0) {
+    static_assert(kRtTensorMapOffset + 2 * sizeof(CUtensorMap) <= kTermRegion, "tensor maps outside the table region");
+    CUtensorMap both[2] = {tm0, tm1};
+    B200Q_CHECK(cudaMemcpyAsync(w + kRtTensorMapOffset, both, sizeof(both), cudaMemcpyHostToDevice, s));
+  }
   double* partials = (double*)(w + kTermRegion);
   const size_t pcap = (work_bytes - kTermRegion) / sizeof(double);
   const RtOp* od = (const RtOp*)w;
@@ -178,7 +183,7 @@ int rtile_dispatch(void* v0, void* v1, int n, int dtype, int64_t batch, const in
   if (ws && !v1)
     B200Q_REQUIRE(a.prefetch, "rtile: the warp-specialised kernel needs 16-byte aligned runs (L=%d)", L);
 #define RT_GO(T, RB, NV, TH, MINB, WS) \
-  return rtile_launch<T, RB, NV, TH, MINB, WS>(v0, v1, a, batch, od, md, mat_bstride, nslots, scale, out_dev, partials, pcap, s, tm0, tm1)
+  return rtile_launch<T, RB, NV, TH, MINB, WS>(v0, v1, a, batch, od, md, mat_bstride, nslots, scale, out_dev, partials, pcap, s)
   const bool adj2 = rtile_adj_variant() != 0;
   if (dtype == B200Q_C128) {
     if (!v1 && ws) RT_GO(double, 4, 1, 128, 3, true);

@@ -76,6 +76,10 @@ struct __align__(16) RtOp {
 };
 static_assert(sizeof(RtOp) == 64, "RtOp must be 64 bytes (mirrored by ctypes in compiler.py)");
 
+// byte offset of the two CUtensorMap descriptors from the start of the uploaded record table
+// (the last 512 bytes of the 4 MiB table region of the workspace, see rtile_host.h)
+static constexpr size_t kRtTensorMapOffset = (4ull << 20) - 512;
+
 struct RtArgs {
   int n, T, L, nops, nmat, nslots;
   int write0;                    // write vector 0 back (adjoint passes over several bras)
@@ -478,7 +482,9 @@ struct RtKernel {
                                                     const CUtensorMap* tm1) {
     const unsigned bytes = (unsigned)(NV * sizeof(C)) << a.T;
     rt_fence_proxy_async();
-    if (a.tma_rank > 0) {
+    // (forward kernels only: in the two-vector adjoint kernel the extra path cost registers —
+    // 416 -> 532 bytes of spills, 1.71 -> 1.82 s per Jacobian — for no measurable gain)
+    if (NV == 1 && a.tma_rank > 0) {
       __syncthreads();
       if (threadIdx.x == 0) {
         const unsigned long long base = tile_base(a, t);
@@ -487,7 +493,6 @@ struct RtKernel {
           if (a.tma_len[r]) c[r] = (int)((base >> a.tma_lo[r]) & ((1ull << a.tma_len[r]) - 1ull));
         rt_mbar_expect_tx(bar, bytes);
         rt_tma_load(tile, tm0, a.tma_rank, c, bar);
-        if (NV > 1) rt_tma_load(tile + ((size_t)1 << a.T), tm1, a.tma_rank, c, bar);
       }
     } else {
       if (threadIdx.x == 0) rt_mbar_expect_tx(bar, bytes);
@@ -500,8 +505,11 @@ struct RtKernel {
                                              C* __restrict__ v1, const RtOp* __restrict__ ops_g,
                                              const double2* __restrict__ mats_g,
                                              const long long mat_bstride,
-                                             double* __restrict__ partials,
-                                             const CUtensorMap* tm0, const CUtensorMap* tm1) {
+                                             double* __restrict__ partials) {
+    // the two tensor maps (vector 0, vector 1) sit at a fixed offset behind the uploaded records
+    const CUtensorMap* tm0 = reinterpret_cast<const CUtensorMap*>(
+        reinterpret_cast<const char*>(ops_g) + kRtTensorMapOffset);
+    const CUtensorMap* tm1 = nullptr;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const unsigned tsize = 1u << a.T;
     C* tile = reinterpret_cast<C*>(smem_raw);                                  // NV * 2^T
@@ -890,9 +898,8 @@ template <typename T_, int RB, int NV, int THREADS, int MINB, bool WS = false>
 __global__ void __launch_bounds__(THREADS + (WS ? 32 : 0), MINB)
 k_rtile(const __grid_constant__ RtArgs a, cx<T_>* __restrict__ v0, cx<T_>* __restrict__ v1,
         const RtOp* __restrict__ ops_g, const double2* __restrict__ mats_g,
-        const long long mat_bstride, double* __restrict__ partials,
-        const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1) {
-  RtKernel<T_, RB, NV, THREADS, WS>::run(a, v0, v1, ops_g, mats_g, mat_bstride, partials, &tm0, &tm1);
+        const long long mat_bstride, double* __restrict__ partials) {
+  RtKernel<T_, RB, NV, THREADS, WS>::run(a, v0, v1, ops_g, mats_g, mat_bstride, partials);
 }
 
 }  // namespace b200q

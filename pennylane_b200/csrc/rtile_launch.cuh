@@ -26,8 +26,7 @@ k_rt_final_reduce(const double* __restrict__ partials, double* __restrict__ out,
 template <typename T, int RB, int NV, int THREADS, int MINB, bool WS>
 int rtile_launch(void* v0, void* v1, const RtArgs& a, int64_t batch, const RtOp* ops_dev,
                         const double2* mats_dev, long long mat_bstride, int nslots, double scale, double* out_dev,
-                        double* partials, size_t partial_cap, cudaStream_t s, const CUtensorMap& tm0,
-                        const CUtensorMap& tm1) {
+                        double* partials, size_t partial_cap, cudaStream_t s) {
   const size_t smem = ((size_t)NV * sizeof(cx<T>) << a.T) * (WS ? 2 : 1) + sizeof(cx<T>) * ((a.nmat + 1) & ~1) +
                       (size_t)a.nops * sizeof(RtOp) +
                       (size_t)((2 << RB) + 2 * THREADS + 2) * sizeof(unsigned long long) +
@@ -52,7 +51,7 @@ int rtile_launch(void* v0, void* v1, const RtArgs& a, int64_t batch, const RtOp*
     B200Q_REQUIRE((size_t)batch * nslots * grid.x <= partial_cap, "rtile: workspace too small for %d slots",
                   nslots);
   k_rtile<T, RB, NV, THREADS, MINB, WS><<<grid, THREADS + (WS ? 32 : 0), smem, s>>>(
-      a, (cx<T>*)v0, (cx<T>*)v1, ops_dev, mats_dev, mat_bstride, partials, tm0, tm1);
+      a, (cx<T>*)v0, (cx<T>*)v1, ops_dev, mats_dev, mat_bstride, partials);
   B200Q_LAUNCH_CHECK();
   if (nslots > 0) {
     k_rt_final_reduce<<<(unsigned)(batch * nslots), 256, 0, s>>>(partials, out_dev, (int)grid.x, scale);
@@ -65,7 +64,7 @@ int rtile_launch(void* v0, void* v1, const RtArgs& a, int64_t batch, const RtOp*
   void *v0, void *v1, const RtArgs &a, int64_t batch, const RtOp *ops_dev,                      \
       const double2 *mats_dev, long long mat_bstride, int nslots, double scale,                \
       double *out_dev, double *partials,                                                        \
-      size_t partial_cap, cudaStream_t s, const CUtensorMap &tm0, const CUtensorMap &tm1
+      size_t partial_cap, cudaStream_t s
 
 // the variants that exist (kept in sync with rtile_k_*.cu and rtile_run in rtile.cu)
 #define RT_FOR_EACH_VARIANT(X)                                                                  \
