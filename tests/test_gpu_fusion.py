@@ -195,3 +195,16 @@ def test_rtile_hea_matches_unfused_at_20_qubits():
     for op in ops_:
         b.apply_operation(op)
     assert np.max(np.abs(a.to_numpy() - b.to_numpy())) < 1e-13
+
+
+def test_differential_fuzz_of_the_fused_paths():
+    """tools/fuzz_gpu.py: random circuits (all primitive kinds, broadcast rotations, random L /
+    fusion level / precision) and random trainable circuits' Jacobians against the oracle."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, os.path.join(root, "tools", "fuzz_gpu.py"), "16"],
+                         capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
