@@ -33,6 +33,8 @@ extern "C" {
 #define B200Q_DTYPE_C128 1
 #define B200Q_CDF_EXACT 0 /* numpy-ordered float64 additions: bit-exact shots      */
 #define B200Q_CDF_FAST 1  /* blocked parallel scan: fastest, ~1e-16 CDF differences */
+#define B200Q_CDF_EXACT_SERIAL 2 /* the same bits as EXACT from one dependent chain of additions
+                                    (the checker of the parallel exact scan)               */
 
 const char* b200q_last_error(void);
 int b200q_version(void);

@@ -486,6 +486,45 @@ using namespace b200q;
     return 2;                                                    \
   } while (0)
 
+namespace b200q {
+
+// In-place numpy-ordered cumsum (bit-exact), parallel: see sample.cuh "exact mode, parallel".
+// Small vectors keep the serial chain (it is a few microseconds there).
+static int cumsum_exact(double* p_dev, uint64_t count, const double* carry_in_dev, void* work,
+                        size_t work_bytes, cudaStream_t s) {
+  if (count < (uint64_t)4 * EXC_CHUNK) {
+    k_cumsum_serial<1024><<<1, 64, 0, s>>>(p_dev, p_dev, count, carry_in_dev);
+    B200Q_LAUNCH_CHECK();
+    return 0;
+  }
+  const uint64_t nchunks = (count + EXC_CHUNK - 1) / EXC_CHUNK;
+  const size_t need = (nchunks + 64) * 48;
+  B200Q_REQUIRE(work && work_bytes >= kWorkBytes && need <= work_bytes - kTermRegion,
+                "cumsum: workspace too small for 2^%d values (exact mode needs %zu bytes)",
+                (int)(63 - __builtin_clzll(count)), need + kTermRegion);
+  char* base = (char*)work + kTermRegion;
+  double* approx = (double*)base + 8;                                   // nchunks (+ padding)
+  unsigned long long* a0 = (unsigned long long*)(approx + nchunks + 8);
+  unsigned long long* a1 = a0 + nchunks;
+  double* start = (double*)(a1 + nchunks);
+  int* flags = (int*)(start + nchunks);
+  k_scan_block_totals<<<(unsigned)nchunks, 256, 0, s>>>(p_dev, approx, count);
+  B200Q_LAUNCH_CHECK();
+  k_scan_totals<<<1, 1024, 0, s>>>(approx, nchunks, carry_in_dev);
+  B200Q_LAUNCH_CHECK();
+  const unsigned grid = (unsigned)((nchunks + 3) / 4);
+  k_excum_summaries<<<grid, 128, 0, s>>>(p_dev, count, approx, nchunks, a0, a1, flags);
+  B200Q_LAUNCH_CHECK();
+  k_excum_ordered<<<1, 32, 0, s>>>(p_dev, p_dev, count, approx, nchunks, a0, a1, flags, start,
+                                   carry_in_dev);
+  B200Q_LAUNCH_CHECK();
+  k_excum_replay<<<grid, 128, 0, s>>>(p_dev, p_dev, count, nchunks, flags, start);
+  B200Q_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace b200q
+
 extern "C" {
 
 const char* b200q_last_error(void) { return g_err; }
@@ -654,6 +693,8 @@ int b200q_sample(double* probs_dev, int m, const double* uniforms_dev, int64_t s
   B200Q_LAUNCH_CHECK();
   // cdf = probs.cumsum()
   if (mode == B200Q_CDF_EXACT) {
+    if (int rc = cumsum_exact(probs_dev, count, nullptr, work, work_bytes, s)) return rc;
+  } else if (mode == B200Q_CDF_EXACT_SERIAL) {
     k_cumsum_serial<1024><<<1, 64, 0, s>>>(probs_dev, probs_dev, count);
     B200Q_LAUNCH_CHECK();
   } else if (mode == B200Q_CDF_FAST) {
@@ -720,7 +761,8 @@ int b200q_cumsum(double* p_dev, int m, int mode, const double* carry_in_dev, voi
   cudaStream_t s = (cudaStream_t)stream;
   B200Q_REQUIRE(m >= 0 && m <= 40 && p_dev, "cumsum: bad arguments");
   const uint64_t count = 1ull << m;
-  if (mode == B200Q_CDF_EXACT) {
+  if (mode == B200Q_CDF_EXACT) return cumsum_exact(p_dev, count, carry_in_dev, work, work_bytes, s);
+  if (mode == B200Q_CDF_EXACT_SERIAL) {
     k_cumsum_serial<1024><<<1, 64, 0, s>>>(p_dev, p_dev, count, carry_in_dev);
     B200Q_LAUNCH_CHECK();
     return 0;

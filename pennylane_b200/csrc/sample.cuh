@@ -147,6 +147,188 @@ k_cumsum_serial(const double* p, double* cdf, const uint64_t count,
   }
 }
 
+// ---- exact mode, parallel --------------------------------------------------------------------
+// numpy's cumsum is the dependent chain s_i = fl(s_{i-1} + p_i).  With non-negative terms the
+// chain can be cut into independent pieces WITHOUT changing a single bit: while the running sum
+// stays inside one binade [2^e, 2^(e+1)) it is an integer multiple M of u = ulp = 2^(e-52), and
+//     fl(M u + p) = (M + k) u,   k = p / u rounded to the nearest integer,
+// where k does not depend on M — except when p / u lies exactly half-way (ties go to the even
+// M + k), and a tie only needs the PARITY of M.  So a run of terms acts on the state as
+//     M -> M + (M even ? a0 : a1),
+// and such maps compose associatively: a chunk is summarised by the pair (a0, a1), chunks are
+// combined in order by one warp, and every chunk is then replayed from its exact start state.
+// A chunk is only summarised for ONE binade, predicted from an ordinary (approximate) parallel
+// prefix of the chunk totals; where the prediction is wrong or the sum crosses into the next
+// binade inside the chunk (a few dozen chunks out of half a million at 30 qubits) the ordered
+// pass falls back to the plain rounded additions for that chunk.  Zero, subnormal and huge
+// terms are covered by the same rules (unit exponent 1 for zero / subnormal sums; a term whose
+// own unit is larger than the sum's forces the fallback).  Checked bit for bit against the
+// serial kernel and numpy on adversarial inputs (tests/test_gpu_sampling.py).
+constexpr int EXC_LANE = 64;                    // consecutive terms per lane
+constexpr int EXC_CHUNK = 32 * EXC_LANE;        // terms per warp-chunk (= block of the fast scan)
+
+struct ExcSum { unsigned long long a0, a1; int bad; };
+
+// unit exponent (biased; 1 for zero / subnormal) and integer significand of a non-negative double
+__device__ __forceinline__ void exc_split(const double s, int& ue, unsigned long long& m) {
+  const unsigned long long b = (unsigned long long)__double_as_longlong(s);
+  const int eb = (int)((b >> 52) & 0x7ffull);
+  const unsigned long long man = b & ((1ull << 52) - 1ull);
+  ue = eb ? eb : 1;
+  m = eb ? (man | (1ull << 52)) : man;
+}
+__device__ __forceinline__ double exc_join(const int ue, const unsigned long long m) {
+  const unsigned long long b = m < (1ull << 52) ? m : (((unsigned long long)ue << 52) | (m - (1ull << 52)));
+  return __longlong_as_double((long long)b);
+}
+// p / u = k (+ 1/2 if tie); bad: the term's unit is larger than the sum's (certain binade change)
+__device__ __forceinline__ void exc_term(const double p, const int ue, unsigned long long& k, bool& tie,
+                                         bool& bad) {
+  int ep;
+  unsigned long long mp;
+  exc_split(p, ep, mp);
+  k = 0; tie = false; bad = false;
+  if (mp == 0) return;
+  const int d = ue - ep;
+  if (d < 0) { bad = true; return; }
+  if (d == 0) { k = mp; return; }
+  if (d >= 54) return;
+  const unsigned long long r = mp & ((1ull << d) - 1ull), half = 1ull << (d - 1);
+  k = (mp >> d) + (r > half ? 1ull : 0ull);
+  tie = r == half;
+}
+// f then g
+__device__ __forceinline__ ExcSum exc_compose(const ExcSum f, const ExcSum g) {
+  ExcSum r;
+  r.a0 = f.a0 + ((f.a0 & 1ull) ? g.a1 : g.a0);
+  r.a1 = f.a1 + ((f.a1 & 1ull) ? g.a0 : g.a1);       // start odd: parity after f = 1 ^ (a1 & 1)
+  r.bad = f.bad | g.bad;
+  return r;
+}
+// summary of the lane's EXC_LANE consecutive terms for unit exponent `ue`
+__device__ __forceinline__ ExcSum exc_lane_summary(const double* __restrict__ p, const uint64_t first,
+                                                   const uint64_t count, const int ue) {
+  ExcSum s; s.a0 = 0; s.a1 = 0; s.bad = 0;
+  for (int i = 0; i < EXC_LANE; ++i) {
+    const uint64_t g = first + i;
+    if (g >= count) break;
+    unsigned long long k; bool tie, bad;
+    exc_term(p[g], ue, k, tie, bad);
+    s.bad |= bad ? 1 : 0;
+    const unsigned long long t0 = s.a0 + k, t1 = s.a1 + k;
+    s.a0 = t0 + ((tie && (t0 & 1ull)) ? 1ull : 0ull);           // start even: parity of M + a0 + k
+    s.a1 = t1 + ((tie && !(t1 & 1ull)) ? 1ull : 0ull);          // start odd
+  }
+  return s;
+}
+__device__ __forceinline__ ExcSum exc_shfl_up(const ExcSum v, const int o) {
+  ExcSum r;
+  r.a0 = __shfl_up_sync(0xffffffffu, v.a0, o);
+  r.a1 = __shfl_up_sync(0xffffffffu, v.a1, o);
+  r.bad = __shfl_up_sync(0xffffffffu, v.bad, o);
+  return r;
+}
+
+// K1: one warp per chunk; approx[c] = approximate value of the running sum before chunk c
+__global__ void __launch_bounds__(128)
+k_excum_summaries(const double* __restrict__ p, const uint64_t count, const double* __restrict__ approx,
+                  const uint64_t nchunks, unsigned long long* __restrict__ a0,
+                  unsigned long long* __restrict__ a1, int* __restrict__ flags) {
+  const uint64_t c = (uint64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (c >= nchunks) return;
+  const int lane = threadIdx.x & 31;
+  int ue; unsigned long long m0;
+  exc_split(approx[c], ue, m0);
+  ExcSum s = exc_lane_summary(p, c * EXC_CHUNK + (uint64_t)lane * EXC_LANE, count, ue);
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const ExcSum e = exc_shfl_up(s, o);
+    if (lane >= o) s = exc_compose(e, s);
+  }
+  if (lane == 31) { a0[c] = s.a0; a1[c] = s.a1; flags[c] = s.bad; }
+}
+
+// K2: ONE warp walks the chunks in order with the exact state (replicated in every lane).
+// start[c] = exact running sum before chunk c; flags[c] |= 2 where the chunk was done here.
+__global__ void __launch_bounds__(32)
+k_excum_ordered(const double* p, double* cdf, const uint64_t count, const double* __restrict__ approx,
+                const uint64_t nchunks, const unsigned long long* __restrict__ a0,
+                const unsigned long long* __restrict__ a1, int* __restrict__ flags,
+                double* __restrict__ start, const double* __restrict__ carry_in) {
+  const int lane = threadIdx.x;
+  double s = carry_in ? *carry_in : 0.0;
+  bool first = carry_in == nullptr;              // numpy: out[0] = p[0] (no addition)
+  for (uint64_t base = 0; base < nchunks; base += 32) {
+    const uint64_t mine = base + lane;
+    unsigned long long la0 = 0, la1 = 0; int lbad = 1, lue = 0;
+    if (mine < nchunks) {
+      la0 = a0[mine]; la1 = a1[mine]; lbad = flags[mine];
+      unsigned long long mm; exc_split(approx[mine], lue, mm);
+    }
+    double my_start = 0.0; int my_flag = 0;
+    const int lim = (int)min((uint64_t)32, nchunks - base);
+    for (int j = 0; j < lim; ++j) {
+      const unsigned long long ca0 = __shfl_sync(0xffffffffu, la0, j), ca1 = __shfl_sync(0xffffffffu, la1, j);
+      const int cbad = __shfl_sync(0xffffffffu, lbad, j), cue = __shfl_sync(0xffffffffu, lue, j);
+      int ue; unsigned long long m;
+      exc_split(s, ue, m);
+      const unsigned long long add = (m & 1ull) ? ca1 : ca0;
+      const bool ok = !first && !cbad && cue == ue && add < (1ull << 53) && m + add < (1ull << 53);
+      if (lane == j) { my_start = s; my_flag = ok ? 0 : 2; }
+      if (ok) {
+        s = exc_join(ue, m + add);
+      } else {
+        // plain rounded additions for this chunk (lane 0 owns the chain; loads are independent)
+        const uint64_t b0 = (base + j) * EXC_CHUNK;
+        const uint64_t e0 = min(count, b0 + (uint64_t)EXC_CHUNK);
+        if (lane == 0) {
+          double run = s;
+          uint64_t i = b0;
+          if (first) { run = p[i]; cdf[i] = run; ++i; }
+#pragma unroll 4
+          for (; i < e0; ++i) { run = __dadd_rn(run, p[i]); cdf[i] = run; }
+          s = run;
+        }
+        s = __shfl_sync(0xffffffffu, s, 0);
+        first = false;
+      }
+    }
+    if (mine < nchunks) { start[mine] = my_start; flags[mine] |= my_flag; }
+  }
+}
+
+// K3: replay every chunk that was not done by the ordered pass from its exact start state
+__global__ void __launch_bounds__(128)
+k_excum_replay(const double* p, double* cdf, const uint64_t count, const uint64_t nchunks,
+               const int* __restrict__ flags, const double* __restrict__ start) {
+  const uint64_t c = (uint64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (c >= nchunks || (flags[c] & 2)) return;
+  const int lane = threadIdx.x & 31;
+  int ue; unsigned long long m;
+  exc_split(start[c], ue, m);
+  const uint64_t first = c * EXC_CHUNK + (uint64_t)lane * EXC_LANE;
+  const ExcSum mine = exc_lane_summary(p, first, count, ue);
+  ExcSum s = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const ExcSum e = exc_shfl_up(s, o);
+    if (lane >= o) s = exc_compose(e, s);
+  }
+  // exclusive prefix of the lanes before this one
+  ExcSum ex = exc_shfl_up(s, 1);
+  if (lane == 0) { ex.a0 = 0; ex.a1 = 0; }
+  m += (m & 1ull) ? ex.a1 : ex.a0;
+  for (int i = 0; i < EXC_LANE; ++i) {
+    const uint64_t g = first + i;
+    if (g >= count) break;
+    unsigned long long k; bool tie, bad;
+    exc_term(p[g], ue, k, tie, bad);
+    if (tie && ((m + k) & 1ull)) ++k;
+    m += k;
+    cdf[g] = exc_join(ue, m);
+  }
+}
+
 // ---- fast mode: blocked parallel inclusive scan (deterministic, not numpy-ordered) ------------
 // phase 1: per-block totals; phase 2: exclusive scan of the totals by a single CTA;
 // phase 3: per-block scan + offset.  2048 elements per block.

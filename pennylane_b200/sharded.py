@@ -491,7 +491,7 @@ class CudaEngine:
         returns the last entry."""
         from ._lib import check
 
-        need = ((1 << m) // 2048 + 128) * 8 + (4 << 20)
+        need = ((1 << m) // 2048 + 128) * 48 + (4 << 20)      # exact mode: 48 bytes per 2048-term chunk
         w, wb = self.sv.workspace(need)
         c = None if carry is None else self._scalar(carry)
         check(self.sv.lib.b200q_cumsum(C.c_void_p(p.data_ptr()), m, 0 if exact else 1,
