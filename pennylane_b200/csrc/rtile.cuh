@@ -12,10 +12,15 @@
 // thread bits or outside the tile — they are predicates, not data).  Between rounds the tile
 // is transposed through an XOR-swizzled shared-memory buffer (one conflict-free store + load
 // of the tile), so the shared-memory traffic per tile is 2 * (rounds-1) tile copies instead
-// of 2 per gate.  The first round loads straight from global memory and the last stores
-// straight back; the host makes those two rounds keep tile positions 0..4 on the lanes so
-// every warp access covers whole 128-byte lines.  The next tile of the CTA's grid-stride loop
-// is prefetched into L2 while the current one is being computed.
+// of 2 per gate.  The CTA's NEXT tile is brought into the transpose buffer by the TMA engine
+// (one tensor box, or one bulk copy per contiguous run; completion on an mbarrier) as soon as
+// the last transposition of the current tile has left the buffer idle, so the first round reads
+// shared memory; the last round stores straight back to global memory, and the host keeps tile
+// positions 0..4 on its lanes so every warp store covers whole 512-byte runs.  Single-qubit
+// block records are predecoded once per CTA (per-thread matrix choice tabulated, controls
+// outside the tile resolved by one ballot per tile) and run with their matrix pinned in
+// registers.  Template parameters: T_ (float / double), RB register bits, NV vectors (2 =
+// adjoint), THREADS, WS (warp-specialised variant with a producer warp and a landing buffer).
 //
 // Adjoint mode (NV = 2): vector 0 is the ket, vector 1 a bra; gates are applied to both, and
 // RT_GEN records accumulate coef * Im <bra| P |ket> for a Pauli term P of the generator of a
