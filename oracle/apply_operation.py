@@ -138,12 +138,29 @@ def _rotation_1q(op, state, is_state_batched, compute_coeffs):   # apply_operati
     return _apply_single_qubit_np(mat, state, axis)
 
 
+def _apply_grover_without_matrix(state, op_wires, is_state_batched):
+    """apply_operation.py:849-880: G = 2P - I with P the projector on the all-plus state of the
+    operator's wires — sum over those axes, refill with the (unnormalised) all-plus state."""
+    num_wires = len(op_wires)
+    prefactor = 2 ** (1 - num_wires)
+    sum_axes = [w + is_state_batched for w in op_wires]
+    collapsed = np.sum(state, axis=tuple(sum_axes))
+    if num_wires == state.ndim - is_state_batched:
+        new_shape = (-1,) + (1,) * num_wires if is_state_batched else (1,) * num_wires
+        return prefactor * np.reshape(collapsed, new_shape) - state
+    all_plus = np.full([2] * num_wires, prefactor).astype(state.dtype)
+    source = list(range(np.ndim(collapsed), np.ndim(state)))
+    return np.moveaxis(np.tensordot(collapsed, all_plus, axes=0), source, sum_axes) - state
+
+
 def apply_operation(op, state, is_state_batched=False):
     """Dispatcher — apply_operation.py:258-324 (singledispatch) and the registered kernels."""
     name = op.name
     n_dim = state.ndim
     if name in ("Identity", "Snapshot", "Barrier"):                       # :501
         return state
+    if name == "GroverOperator" and len(op.wires) >= 9:                   # :836-846
+        return _apply_grover_without_matrix(state, list(op.wires), is_state_batched)
     if name == "GlobalPhase":                                             # :507-517
         phase = np.exp(-1j * np.asarray(op.data[0], dtype=complex))
         if phase.ndim > 0:

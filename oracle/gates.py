@@ -127,6 +127,9 @@ def _scalar_matrix(op, theta):
     if name == "MultiControlledX":  # controlled_ops.py:1284
         cv = op.hyperparameters.get("control_values", None)
         return controlled(PX, len(op.wires) - 1, cv)
+    if name == "GroverOperator":  # templates/subroutines/grover.py: 2|s><s| - I
+        dim = 2 ** len(op.wires)
+        return np.full((dim, dim), 2.0 / dim, dtype=complex) - np.eye(dim)
     if name in ("QubitUnitary", "Hermitian"):
         return np.asarray(theta[0], dtype=complex)
     if name == "DiagonalQubitUnitary":

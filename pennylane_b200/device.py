@@ -94,6 +94,15 @@ def stopping_condition(op) -> bool:
         return True
     if op.name in ("MidMeasureMP", "Conditional"):
         return False
+    if op.name == "GroverOperator":
+        return len(op.wires) < 9          # apply_operation.py:845: matrix below nine wires
+    base = getattr(op, "base", None)
+    if op.name.startswith("C(") and base is not None:
+        # default_qubit.py:118 ("C(gate)" for every base gate): controls are masks for the
+        # kernels, only the base block is dense
+        return (bool(getattr(base, "has_matrix", False)) and len(base.wires) <= 2
+                and len(op.control_wires) <= 16 and getattr(base, "batch_size", None) is None) \
+            or (bool(getattr(op, "has_matrix", False)) and len(op.wires) <= _MAX_MATRIX_WIRES)
     return bool(getattr(op, "has_matrix", False)) and len(op.wires) <= _MAX_MATRIX_WIRES
 
 

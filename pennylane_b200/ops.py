@@ -516,6 +516,42 @@ class MultiControlledX(Operator):
         return MultiControlledX(wires=self.wires, control_values=self.control_values)
 
 
+class GroverOperator(Operator):
+    """templates/subroutines/grover.py:29 — the diffusion operator ``G = 2|s><s| - I`` on
+    ``wires`` (|s> = uniform superposition).  The reference applies it matrix-free on nine or
+    more wires (apply_operation.py:836-880: sum over the operator's axes, refill with the
+    all-plus state); here those widths go through the decomposition
+    ``H^k (2|0><0| - I) H^k`` — Hadamards that fuse into neighbouring blocks, one multiply
+    controlled phase that touches only 2^-k of the state, and a global phase."""
+
+    has_decomposition = True
+
+    def __init__(self, wires=None, work_wires=None, id=None):
+        super().__init__(wires=wires, id=id)
+        if len(self.wires) < 2:
+            raise ValueError("GroverOperator must have at least two wires. "
+                             f"Got {len(self.wires)} wires.")
+        self.hyperparameters["n_wires"] = len(self.wires)
+        self.hyperparameters["work_wires"] = _wires_tuple(work_wires) if work_wires is not None else ()
+
+    def matrix(self, wire_order=None):
+        dim = 1 << len(self.wires)
+        mat = np.full((dim, dim), 2.0 / dim, dtype=complex) - np.eye(dim)
+        return mat if wire_order is None else expand_matrix(mat, self.wires, wire_order)
+
+    def decomposition(self):
+        w = self.wires
+        t = w[-1]
+        flip0 = [PauliX(wires=t), Controlled(PauliZ(wires=t), control_wires=w[:-1],
+                                             control_values=[False] * (len(w) - 1)), PauliX(wires=t)]
+        had = [Hadamard(wires=x) for x in w]
+        # 2|0><0| - I = -(I - 2|0><0|): the flip of |0..0> followed by a global -1 = exp(-i pi)
+        return had + flip0 + had + [GlobalPhase(np.pi, wires=w)]
+
+    def adjoint(self):
+        return GroverOperator(wires=self.wires)
+
+
 # =============================================================================================
 # Parametrised single-qubit gates — pennylane/ops/qubit/parametric_ops_single_qubit.py
 # =============================================================================================

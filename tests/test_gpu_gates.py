@@ -203,3 +203,25 @@ def test_gate_sequence_matches_oracle_circuit():
     sv, _ = get_final_state(tape)
     ref, _ = o_sim.get_final_state(tape)
     assert np.max(np.abs(sv.to_numpy() - ref)) < 1e-12
+
+
+@pytest.mark.parametrize("fusion", [0, 1])
+def test_grover_operator_matrix_and_decomposed_widths(fusion):
+    """GroverOperator (apply_operation.py:836-880): below nine wires through its matrix, from nine
+    wires on matrix-free — here as H^k (2|0><0| - I) H^k — against the oracle's restatement of the
+    reference kernel."""
+    import pennylane_b200 as qb
+    from oracle import simulate as o_sim
+    from pennylane_b200 import ops as q
+
+    n = 13
+    rng = np.random.default_rng(17)
+    prep = [q.RY(rng.uniform(0, 6), wires=i) for i in range(n)] + \
+           [q.CNOT(wires=[i, (i + 1) % n]) for i in range(n)] + [q.RZ(rng.uniform(0, 6), wires=i) for i in range(n)]
+    for wires in ([0, 1], [4, 2, 9], list(range(9)), [12, 0, 3, 4, 5, 6, 7, 8, 9, 11], list(range(n))):
+        tape = qb.QuantumScript(prep + [q.GroverOperator(wires=wires), q.RX(0.3, wires=wires[0])], [qb.state()])
+        dev = qb.B200Qubit(wires=n, fusion=fusion)
+        (ptape,), _ = dev.preprocess(tape)
+        got = dev.execute(ptape)
+        ref = np.asarray(o_sim.simulate(tape)).reshape(-1)
+        assert np.max(np.abs(np.asarray(got).reshape(-1) - ref)) < 1e-12, wires

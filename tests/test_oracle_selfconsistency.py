@@ -91,3 +91,40 @@ def test_oracle_multicontrolledx_wide_path():
     op = q.MultiControlledX(wires=[3, 0, 9, 1, 7, 4, 2, 8, 6, 5], control_values=cv)
     ref = (q.matrix(op, wire_order=range(n)) @ state.reshape(-1)).reshape(state.shape)
     assert np.allclose(apply_operation(op, state), ref, atol=1e-14)
+
+
+# ---- GroverOperator: apply_operation.py:836-880 ----------------------------------------------------
+def test_grover_known_answer_and_matrix_free_branch():
+    """test_apply_operation.py:391-412 (two-qubit known answer) and :1168-1300 (the matrix-free
+    kernel on >= 9 wires against the dense matrix; full and partial wire sets, batched)."""
+    import numpy as np
+    from oracle.apply_operation import apply_operation
+    from pennylane_b200 import ops as q
+
+    initial = np.array([[0.04624539 + 0.3895457j, 0.22399401 + 0.53870339j],
+                        [-0.483054 + 0.2468498j, -0.02772249 - 0.45901669j]])
+    for wire in (0, 1):
+        op = q.GroverOperator(wires=[wire, 1 - wire])
+        new = apply_operation(op, initial)
+        expected = 2 * (np.ones_like(initial) / 2) * (initial.sum() / 2) - initial
+        assert np.allclose(new, expected)
+    rng = np.random.default_rng(3)
+    for op_wires, n, batch in ((list(range(9)), 9, None), ([10, 0, 3, 4, 5, 6, 7, 8, 9], 11, None),
+                               (list(range(9)), 10, 2)):
+        shape = ([batch] if batch else []) + [2] * n
+        state = rng.normal(size=shape) + 1j * rng.normal(size=shape)
+        op = q.GroverOperator(wires=op_wires)
+        got = apply_operation(op, state, is_state_batched=bool(batch))
+        k = len(op_wires)
+        # dense reference: 2|s><s| - I on the operator's axes
+        axes = [w + bool(batch) for w in op_wires]
+        mean = state.sum(axis=tuple(axes), keepdims=True) / (1 << k)
+        assert np.allclose(got, 2 * mean - state)
+    # the decomposition the CUDA device uses for wide operators equals the matrix
+    op = q.GroverOperator(wires=[2, 0, 1])
+    state = rng.normal(size=[2] * 3) + 1j * rng.normal(size=[2] * 3)
+    ref = apply_operation(op, state)
+    dec = state
+    for sub in op.decomposition():
+        dec = apply_operation(sub, dec)
+    assert np.allclose(dec, ref, atol=1e-14)
