@@ -162,6 +162,14 @@ int b200q_apply_tile(void* state, int n, int dtype, int64_t batch, const int* ti
                      int L, const void* ops_host, int nops, const void* mats_host, int nmat,
                      void* work, size_t work_bytes, void* stream);
 
+/* out_dev[batch] = Re <psi| H |psi> for a CSR matrix H (2^k x 2^k, complex128 values, int64
+ * indptr / indices, all on the device) acting on the k state bits tbits[0..k) (tbits[0] = most
+ * significant bit of the matrix index).  Replaces measure.py:74-118 (csr_dot_products, scipy
+ * branch: SparseHamiltonian) without expanding H to the full register. */
+int b200q_expval_csr(const void* state, int n, int dtype, int64_t batch, const int* tbits, int k,
+                     const int64_t* indptr_dev, const int64_t* indices_dev, const void* data_dev,
+                     double* out_dev, void* work, size_t work_bytes, void* stream);
+
 /* Register-tiled fused segment (the production fused path; b200q_apply_tile is the small-state
  * fallback).  ONE read + ONE write of vec0 (and of vec1 when given) applies `nops` records:
  * every thread keeps 2^RB amplitudes in registers, a segment is a sequence of ROUNDS (which tile

@@ -197,9 +197,31 @@ def sum_of_terms_method(mp, state, is_state_batched=False):   # measure.py:142-1
                            is_state_batched) for c, o in zip(cs, os_))
 
 
+def csr_dot_products_sparse(mp, state, is_state_batched=False):   # measure.py:100-118 (scipy branch)
+    from scipy.sparse import csr_matrix
+
+    total_wires = state.ndim - is_state_batched
+    Hmat = mp.obs.sparse_matrix(wire_order=list(range(total_wires)))
+    if is_state_batched:
+        st = state.reshape(state.shape[0], -1)
+        bra = csr_matrix(np.conj(st))
+        ket = csr_matrix(st)
+        new_bra = bra.dot(Hmat)
+        res = np.asarray(new_bra.multiply(ket).sum(axis=1)).reshape(-1)
+    else:
+        st = state.flatten()
+        bra = csr_matrix(np.conj(st))
+        ket = csr_matrix(st[..., None])
+        new_ket = csr_matrix.dot(Hmat, ket)
+        res = csr_matrix.dot(bra, new_ket).toarray()[0]
+    return np.real(np.squeeze(res))
+
+
 def get_measurement_function(mp, state):          # measure.py:165-221
     if mp.kind in ("expval",) and mp.obs is not None:
         name = mp.obs.name
+        if name == "SparseHamiltonian":                                  # :198-199
+            return csr_dot_products_sparse
         if name == "Hermitian":
             return full_dot_products
         if name in ("LinearCombination", "Hamiltonian"):

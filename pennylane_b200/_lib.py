@@ -55,6 +55,7 @@ SIGNATURES = {
     "b200q_rtile_geometry": (_i, [_i, _i, _ip, _ip, _ip]),
     "b200q_apply_rtile": (_i, [_p, _p, _i, _i, _i64, _ip, _i, _i, _p, _i, _p, _i, _i, _i, _u64, _d,
                                _p, _p, _sz, _p]),
+    "b200q_expval_csr": (_i, [_p, _i, _i, _i64, _ip, _i, _p, _p, _p, _p, _p, _sz, _p]),
     "b200q_apply_rtile_bcast": (_i, [_p, _p, _i, _i, _i64, _ip, _i, _i, _p, _i, _p, _i, _i, _i, _u64,
                                      _d, _p, _p, _sz, _p]),
     "b200q_adjoint_step": (_i, [_p, _i, _i, _i, _ip, _i, _ip, _ip, _i, _p, _p, _p, _p, _sz, _p]),

@@ -836,6 +836,40 @@ int b200q_apply_rtile(void* vec0, void* vec1, int n, int dtype, int64_t batch, c
                         work, work_bytes, (cudaStream_t)stream);
 }
 
+int b200q_expval_csr(const void* state, int n, int dtype, int64_t batch, const int* tbits, int k,
+                     const int64_t* indptr_dev, const int64_t* indices_dev, const void* data_dev,
+                     double* out_dev, void* work, size_t work_bytes, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  B200Q_REQUIRE(state && tbits && indptr_dev && indices_dev && data_dev && out_dev,
+                "expval_csr: null argument");
+  B200Q_REQUIRE(n >= 1 && n <= B200Q_MAX_BITS && k >= 1 && k <= n && batch >= 1,
+                "expval_csr: bad sizes n=%d k=%d", n, k);
+  const unsigned ncta = reduce_ncta();
+  B200Q_REQUIRE(work && work_bytes >= kTermRegion + (size_t)batch * ncta * sizeof(double),
+                "expval_csr: workspace too small");
+  CsrArgs a;
+  memset(&a, 0, sizeof(a));
+  a.n = n; a.k = k;
+  for (int j = 0; j < k; ++j) {
+    B200Q_REQUIRE(tbits[j] >= 0 && tbits[j] < n && !((a.tmask >> tbits[j]) & 1), "expval_csr: bad bit %d", tbits[j]);
+    a.tbits[j] = (int8_t)tbits[j];
+    a.tmask |= 1ull << tbits[j];
+  }
+  double* partials = (double*)((char*)work + kTermRegion);
+  dim3 grid(ncta, (unsigned)batch);
+  if (dtype == B200Q_DTYPE_C128)
+    k_expval_csr<double><<<grid, 256, 0, s>>>((const cx<double>*)state, a, (const long long*)indptr_dev,
+                                              (const long long*)indices_dev, (const double2*)data_dev, partials);
+  else if (dtype == B200Q_DTYPE_C64)
+    k_expval_csr<float><<<grid, 256, 0, s>>>((const cx<float>*)state, a, (const long long*)indptr_dev,
+                                             (const long long*)indices_dev, (const double2*)data_dev, partials);
+  else { set_error("unknown dtype %d", dtype); return 2; }
+  B200Q_LAUNCH_CHECK();
+  k_final_reduce<<<(unsigned)batch, 256, 0, s>>>(partials, out_dev, (int)ncta, 1, (int)batch, 1.0);
+  B200Q_LAUNCH_CHECK();
+  return 0;
+}
+
 int b200q_apply_rtile_bcast(void* vec0, void* vec1, int n, int dtype, int64_t batch,
                             const int* tile_bits, int T, int L, const void* ops_host, int nops,
                             const void* mats_host, int nmat, int nslots, int write0,

@@ -270,6 +270,48 @@ k_expval_offdiag(const cx<T>* __restrict__ state, const int n, const uint64_t xm
   if (threadIdx.x == 0) partials[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = acc;
 }
 
+// ---- <psi| H |psi> for a CSR matrix on k of the n wires (SparseHamiltonian) --------------------
+// measure.py:74-118 (csr_dot_products, scipy branch) builds the 2^n x 2^n matrix H (x) I and two
+// sparse products; here H stays 2^k x 2^k: amplitude i contributes
+//   conj(psi_i) * sum_e H[r(i), c_e] * psi_{i with its target bits replaced by c_e},
+// r(i) = the k target bits of i (MSB = first wire of the observable).  Fixed-order reduction.
+struct CsrArgs {
+  int n, k;
+  int8_t tbits[B200Q_MAX_BITS];     // state bit of matrix-index bit (k-1-j)  <- tbits[j]
+  uint64_t tmask;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_expval_csr(const cx<T>* __restrict__ state, const CsrArgs a, const long long* __restrict__ indptr,
+             const long long* __restrict__ indices, const double2* __restrict__ data,
+             double* __restrict__ partials) {
+  __shared__ double sh[32];
+  const cx<T>* st = state + ((uint64_t)blockIdx.y << a.n);
+  const uint64_t N = 1ull << a.n;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  double acc = 0.0;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride) {
+    uint64_t r = 0;
+    for (int j = 0; j < a.k; ++j) r |= ((i >> a.tbits[j]) & 1ull) << (a.k - 1 - j);
+    const cx<T> b = st[i];
+    const uint64_t rest = i & ~a.tmask;
+    double sr = 0.0, si = 0.0;                       // (H psi)_i
+    for (long long e = indptr[r]; e < indptr[r + 1]; ++e) {
+      const uint64_t c = (uint64_t)indices[e];
+      uint64_t j2 = rest;
+      for (int j = 0; j < a.k; ++j) j2 |= ((c >> (a.k - 1 - j)) & 1ull) << a.tbits[j];
+      const cx<T> x = st[j2];
+      const double2 h = data[e];
+      sr += h.x * (double)x.x - h.y * (double)x.y;
+      si += h.x * (double)x.y + h.y * (double)x.x;
+    }
+    acc += (double)b.x * sr + (double)b.y * si;      // Re(conj(b) * (H psi)_i)
+  }
+  acc = block_sum(acc, sh);
+  if (threadIdx.x == 0) partials[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = acc;
+}
+
 // ---- <a|b> (complex) and ||a||^2 ------------------------------------------------------------------
 // partials layout: [2][batch][ncta]  (real plane, imaginary plane)
 template <typename T>

@@ -1143,6 +1143,54 @@ class Hermitian(Operator):
         return [QubitUnitary(v.conj().T, wires=self.wires)]
 
 
+class SparseHamiltonian(Operator):
+    """ops/qubit/observables.py:279 — an observable given as a scipy CSR matrix on ``wires``
+    (measured through the CSR reduction, measure.py:74-118; no dense matrix, no Pauli form)."""
+
+    has_matrix = False
+    is_hermitian = True
+    num_params = 1
+
+    def __init__(self, H, wires=None, id=None):
+        import scipy.sparse as sp
+
+        if not sp.issparse(H):
+            raise TypeError("Observable must be a scipy sparse csr_matrix.")
+        self.wires = _wires_tuple(wires)
+        H = sp.csr_matrix(H)
+        if H.shape != (1 << len(self.wires),) * 2:
+            raise ValueError(f"Sparse Matrix must be of shape {(1 << len(self.wires),) * 2}.")
+        self.data = (H,)
+        self.id = id
+        self.hyperparameters = {}
+
+    name = "SparseHamiltonian"
+    batch_size = None
+    pauli_rep = None
+
+    def sparse_matrix(self, wire_order=None):
+        import scipy.sparse as sp
+
+        H = self.data[0]
+        if wire_order is None or list(wire_order) == list(self.wires):
+            return H
+        # observables.py:330-336: kron with identities, then permute to wire_order
+        wire_order = list(wire_order)
+        extra = [w for w in wire_order if w not in self.wires]
+        full = sp.kron(H, sp.identity(1 << len(extra), format="csr"), format="csr") if extra else H
+        cur = list(self.wires) + extra
+        n = len(cur)
+        idx = np.arange(1 << n)
+        perm = np.zeros_like(idx)
+        for pos, w in enumerate(wire_order):              # bit of w in the new order <- old order
+            old = cur.index(w)
+            perm |= ((idx >> (n - 1 - pos)) & 1) << (n - 1 - old)
+        return full[perm][:, perm].tocsr()
+
+    def matrix(self, wire_order=None):
+        return np.asarray(self.sparse_matrix(wire_order).toarray())
+
+
 class Projector(Operator):
     """observables.py:412 — ``|b><b|`` for a basis-state bit string (or a state vector)."""
     num_params = 1

@@ -101,6 +101,9 @@ def measure(mp, sv: StateVector, is_state_batched: bool = False):
         p = rot.probs(wires)
         return p
     if kind == "expval":
+        if getattr(obs, "name", "") == "SparseHamiltonian":          # measure.py:198-199
+            r = sv.expval_csr(obs.sparse_matrix(), list(obs.wires))
+            return r if is_state_batched else np.float64(r[0])
         ps = _pauli_rep(obs)
         if ps is not None:
             return np.float64(_expval_pauli(sv, ps)) if not is_state_batched else _expval_pauli(sv, ps)

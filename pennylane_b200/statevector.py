@@ -419,6 +419,28 @@ class StateVector:
                                    self.stream))
         return out
 
+    def expval_csr(self, H, wires: Sequence[int]) -> np.ndarray:
+        """<psi| H |psi> per batch element for a scipy CSR matrix ``H`` (2^k x 2^k) on ``wires``
+        (measure.py:74-118, SparseHamiltonian) — H is NOT expanded to the full register."""
+        import scipy.sparse as sp
+
+        torch = _torch()
+        H = sp.csr_matrix(H)
+        k = len(wires)
+        if H.shape != (1 << k, 1 << k):
+            raise ValueError(f"sparse matrix of shape {H.shape} does not act on {k} wires")
+        H.sort_indices()
+        dev = self.device
+        indptr = torch.from_numpy(np.ascontiguousarray(H.indptr, dtype=np.int64)).to(dev)
+        indices = torch.from_numpy(np.ascontiguousarray(H.indices, dtype=np.int64)).to(dev)
+        data = torch.from_numpy(np.ascontiguousarray(H.data, dtype=np.complex128)).to(dev)
+        w, wb = self.workspace()
+        check(self.lib.b200q_expval_csr(
+            self.ptr, self.n, self.dtype_code, self.batch, int_array(self.bits(wires)), k,
+            C.c_void_p(indptr.data_ptr()), C.c_void_p(indices.data_ptr()), C.c_void_p(data.data_ptr()),
+            C.c_void_p(self._scal.data_ptr()), w, wb, self.stream))
+        return self._scal[: self.batch].cpu().numpy().copy()
+
     def expval_pauli_sentence(self, ps, wire_map=None) -> np.ndarray:
         """<psi| sum_t c_t P_t |psi> for a Pauli sentence (mapping word -> coeff).
         Returns a float (or (B,) array when batched)."""

@@ -128,3 +128,33 @@ def test_grover_known_answer_and_matrix_free_branch():
     for sub in op.decomposition():
         dec = apply_operation(sub, dec)
     assert np.allclose(dec, ref, atol=1e-14)
+
+
+# ---- SparseHamiltonian: measure.py:74-118 (scipy branch) ------------------------------------------
+def test_sparse_hamiltonian_expval_oracle_and_wire_expansion():
+    """test_measure.py:125-190 measures the same Hamiltonian as LinearCombination, SparseHamiltonian
+    and Hermitian and expects one value; here: the oracle's CSR branch against the dense
+    contraction, with the observable on a permuted subset of the wires and on a batch."""
+    import numpy as np
+    import scipy.sparse as sp
+    from types import SimpleNamespace
+    from oracle import measure as o_meas
+    from pennylane_b200 import ops as q
+    from pennylane_b200.ops import expand_matrix
+
+    rng = np.random.default_rng(12)
+    n, wires = 6, [4, 1, 3]
+    A = sp.random(8, 8, density=0.4, random_state=3) + 1j * sp.random(8, 8, density=0.4, random_state=4)
+    H = (A + A.conj().T).tocsr()
+    obs = q.SparseHamiltonian(H, wires=wires)
+    dense_full = expand_matrix(H.toarray(), wires, list(range(n)))
+    assert np.allclose(obs.sparse_matrix(wire_order=list(range(n))).toarray(), dense_full)
+    for batch in (None, 3):
+        shape = ([batch] if batch else []) + [2] * n
+        st = rng.normal(size=shape) + 1j * rng.normal(size=shape)
+        st /= np.sqrt((np.abs(st) ** 2).sum(axis=tuple(range(int(bool(batch)), st.ndim)), keepdims=True))
+        mp = SimpleNamespace(kind="expval", obs=obs, wires=obs.wires)
+        got = o_meas.measure(mp, st, bool(batch))
+        flat = st.reshape(batch or 1, -1)
+        ref = np.real(np.einsum("bi,ij,bj->b", flat.conj(), dense_full, flat))
+        assert np.allclose(got, ref if batch else ref[0], atol=1e-13)
