@@ -68,6 +68,15 @@ int b200q_apply_phase(void* state, int n, int dtype, int64_t batch, const int* c
                       const int* ctrl_vals, int nc, double phase_re, double phase_im,
                       const void* phase_dev, void* stream);
 
+/* Mid-circuit measurement collapse, apply_operation.py:478-495 (projector, `state / norm`,
+ * optional reset) as one sweep: amplitudes with (bit == sample) are multiplied by `scale`
+ * (the host passes 1 / sqrt(p_sample), p from b200q_probs on that bit) and, when reset != 0 and
+ * sample == 1, moved to the bit == 0 half; the other half is zeroed.  Unbatched states only
+ * (the reference raises for batched ones, apply_operation.py:441-442).
+ * Algorithmic bytes: S/2 read + S written. */
+int b200q_collapse(void* state, int n, int dtype, int bit, int sample, int reset, double scale,
+                   void* stream);
+
 /* amp *= popcount(i & mask) odd ? p1 : p0.  RZ / IsingZZ / MultiRZ / PauliRot("Z..Z") of any
  * width (ops/qubit/parametric_ops_multi_qubit.py:93).  phases_dev (nullable): per-batch
  * (p0, p1) pairs of the state's dtype. */

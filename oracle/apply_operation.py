@@ -153,10 +153,57 @@ def _apply_grover_without_matrix(state, op_wires, is_state_batched):
     return np.moveaxis(np.tensordot(collapsed, all_plus, axes=0), source, sum_axes) - state
 
 
-def apply_operation(op, state, is_state_batched=False):
+def _qubit_unitary(matrix, wires):
+    from types import SimpleNamespace
+    return SimpleNamespace(name="QubitUnitary", wires=tuple(wires), data=(matrix,),
+                           hyperparameters={}, batch_size=None)
+
+
+def apply_conditional(op, state, is_state_batched=False, mid_measurements=None, rng=None):
+    """apply_operation.py:355-411 (numpy branch)."""
+    if op.meas_val.concretize(mid_measurements):
+        return apply_operation(op.base, state, is_state_batched=is_state_batched,
+                               mid_measurements=mid_measurements, rng=rng)
+    return state
+
+
+def apply_mid_measure(op, state, is_state_batched=False, mid_measurements=None, rng=None):
+    """apply_operation.py:415-497 (numpy branch): P(0) from the norm of the bit-0 slice,
+    ``binomial(1, 1 - P0)``, projector and reset as 2x2 ``QubitUnitary`` sweeps."""
+    if is_state_batched:
+        raise ValueError("MidMeasure cannot be applied to batched states.")          # :441-442
+    wire = list(op.wires)
+    axis = wire[0]
+    slices = [slice(None)] * np.ndim(state)
+    slices[axis] = 0
+    prob0 = np.real(np.linalg.norm(state[tuple(slices)])) ** 2                       # :450
+    norm = np.sum(prob0, axis=-1)                                                     # :453
+    eps = 10 * np.finfo(state.dtype).eps
+    if (norm - 1) > eps:
+        raise ValueError(f"probabilities greater than 1. Got norm {norm}.")
+    if norm > 1:
+        prob0 = prob0 / norm
+    binomial_fn = np.random.binomial if rng is None else rng.binomial                # :468
+    sample = binomial_fn(1, 1 - prob0)
+    assert mid_measurements is not None
+    mid_measurements[op] = sample                                                     # :473
+    matrix = np.array([[(sample + 1) % 2, 0.0], [0.0, (sample) % 2]])                # :477
+    state = apply_operation(_qubit_unitary(matrix, wire), state, is_state_batched)
+    state = state / np.linalg.norm(state)                                             # :484
+    element = op.reset and sample == 1                                                # :488
+    matrix = np.array([[(element + 1) % 2, (element) % 2],
+                       [(element) % 2, (element + 1) % 2]], dtype=float)
+    return apply_operation(_qubit_unitary(matrix, wire), state, is_state_batched)
+
+
+def apply_operation(op, state, is_state_batched=False, mid_measurements=None, rng=None):
     """Dispatcher — apply_operation.py:258-324 (singledispatch) and the registered kernels."""
     name = op.name
     n_dim = state.ndim
+    if name == "MidMeasureMP":
+        return apply_mid_measure(op, state, is_state_batched, mid_measurements, rng)
+    if name.startswith("Conditional") and hasattr(op, "meas_val"):
+        return apply_conditional(op, state, is_state_batched, mid_measurements, rng)
     if name in ("Identity", "Snapshot", "Barrier"):                       # :501
         return state
     if name == "GroverOperator" and len(op.wires) >= 9:                   # :836-846

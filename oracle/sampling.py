@@ -164,10 +164,14 @@ def shot_bins(shot_vector):
             lower += s
 
 
-def measure_with_samples(mps, state, shots, is_state_batched=False, rng=None):   # :205-273
+def measure_with_samples(mps, state, shots, is_state_batched=False, rng=None,
+                         mid_measurements=None):                                  # :205-273
     """``shots``: object with ``total_shots``, ``shot_vector`` [(shots, copies)...],
     ``has_partitioned_shots``."""
-    groups, indices = _group_measurements(list(mps))
+    mps = list(mps)
+    if mid_measurements:                                                         # :235-236
+        mps = mps[0: len(mps) - len(mid_measurements)]
+    groups, indices = _group_measurements(mps)
     all_res = []
     for group in groups:
         mp0 = group[0]
@@ -179,6 +183,8 @@ def measure_with_samples(mps, state, shots, is_state_batched=False, rng=None):  
                 group, state, shots, is_state_batched, rng))
     flat_indices = [i for idx in indices for i in idx]
     sorted_res = tuple(res for _, res in sorted(enumerate(all_res), key=lambda r: flat_indices[r[0]]))
+    if mid_measurements:                                                         # :266-267
+        sorted_res += tuple(mid_measurements.values())
     if shots.has_partitioned_shots:
         sorted_res = tuple(zip(*sorted_res))
     return sorted_res

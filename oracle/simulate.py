@@ -29,28 +29,33 @@ def _op_batch(op):
     return bs
 
 
-def get_final_state(circuit):                               # simulate.py:174-242
+def get_final_state(circuit, mid_measurements=None, rng=None):   # simulate.py:174-242
     ops = list(circuit.operations)
     prep = ops[0] if ops and _is_prep(ops[0]) else None
     op_wires = sorted({w for op in ops for w in op.wires})
     state = create_initial_state(len(op_wires), prep)
     is_state_batched = bool(prep is not None and _op_batch(prep) is not None)
     for op in ops[bool(prep):]:
-        state = apply_operation(op, state, is_state_batched=is_state_batched)
+        state = apply_operation(op, state, is_state_batched=is_state_batched,
+                                mid_measurements=mid_measurements, rng=rng)
         is_state_batched = is_state_batched or (_op_batch(op) is not None)
     for _ in range(circuit.num_wires - len(op_wires)):
         state = np.stack([state, np.zeros_like(state)], axis=-1)
     return state, is_state_batched
 
 
-def measure_final_state(circuit, state, is_state_batched, rng=None):   # simulate.py:246-304
+def measure_final_state(circuit, state, is_state_batched, rng=None, mid_measurements=None):
+    """simulate.py:246-304."""
     if not circuit.shots:
+        if mid_measurements is not None:
+            raise TypeError("Native mid-circuit measurements are only supported with finite shots.")
         if len(circuit.measurements) == 1:
             return measure(circuit.measurements[0], state, is_state_batched)
         return tuple(measure(mp, state, is_state_batched) for mp in circuit.measurements)
     rng = np.random.default_rng(rng)
     results = measure_with_samples(circuit.measurements, state, circuit.shots,
-                                   is_state_batched=is_state_batched, rng=rng)
+                                   is_state_batched=is_state_batched, rng=rng,
+                                   mid_measurements=mid_measurements)
     if len(circuit.measurements) == 1:
         if circuit.shots.has_partitioned_shots:
             return tuple(res[0] for res in results)
@@ -58,6 +63,20 @@ def measure_final_state(circuit, state, is_state_batched, rng=None):   # simulat
     return results
 
 
+def simulate_one_shot_native_mcm(circuit, rng=None):        # simulate.py:947-990
+    mid_measurements = {}
+    state, is_state_batched = get_final_state(circuit, mid_measurements=mid_measurements, rng=rng)
+    return measure_final_state(circuit, state, is_state_batched, rng=rng,
+                               mid_measurements=mid_measurements)
+
+
 def simulate(circuit, rng=None):                            # simulate.py:308-393
+    has_mcm = any(op.name == "MidMeasureMP" for op in circuit.operations)
+    if has_mcm:                                             # :354-381, one-shot method
+        # the device hands ONE Generator to every shot (default_qubit.py:798)
+        rng = np.random.default_rng(rng)
+        aux_circ = circuit.copy(shots=[1])
+        return tuple(simulate_one_shot_native_mcm(aux_circ, rng=rng)
+                     for _ in range(circuit.shots.total_shots))
     state, is_state_batched = get_final_state(circuit)
     return measure_final_state(circuit, state, is_state_batched, rng=rng)

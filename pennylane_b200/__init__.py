@@ -6,9 +6,10 @@ kernel reached through the C ABI in ``include/b200q.h``.  With PennyLane install
 engine registers as ``qml.device("b200.qubit")`` (``pennylane_b200.pl_plugin``); without it the
 operator / tape / measurement mirror classes in this package drive it directly.
 """
-from . import measurements, ops, pauli
+from . import mcm, measurements, one_shot, ops, pauli
 from ._lib import B200QError, LIB_PATH
 from .device import B200Qubit, DeviceError, ExecutionConfig, QuantumFunctionError, device
+from .mcm import cond, measure
 from .measurements import counts, expval, probs, sample, state, var
 from .statevector import StateVector
 from .tape import QuantumScript, QuantumTape, Shots
@@ -17,6 +18,7 @@ __version__ = "0.1.0"
 
 __all__ = [
     "B200Qubit", "device", "ExecutionConfig", "DeviceError", "QuantumFunctionError", "StateVector",
-    "QuantumScript", "QuantumTape", "Shots", "ops", "measurements", "pauli",
+    "QuantumScript", "QuantumTape", "Shots", "ops", "measurements", "pauli", "mcm", "one_shot",
+    "measure", "cond",
     "expval", "var", "probs", "sample", "counts", "state", "B200QError", "LIB_PATH",
 ]

@@ -582,6 +582,21 @@ int b200q_apply_phase(void* state, int n, int dtype, int64_t batch, const int* c
   return 0;
 }
 
+int b200q_collapse(void* state, int n, int dtype, int bit, int sample, int reset, double scale,
+                   void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  B200Q_REQUIRE(n >= 1 && bit >= 0 && bit < n, "collapse: bit %d outside a %d-qubit state", bit, n);
+  B200Q_REQUIRE(sample == 0 || sample == 1, "collapse: sample must be 0 or 1, got %d", sample);
+  const unsigned grid = grid_for(1ull << (n - 1), 256, 8);
+  if (dtype == B200Q_DTYPE_C128)
+    k_collapse<double><<<grid, 256, 0, s>>>((double2*)state, n, bit, sample, reset != 0, scale);
+  else if (dtype == B200Q_DTYPE_C64)
+    k_collapse<float><<<grid, 256, 0, s>>>((float2*)state, n, bit, sample, reset != 0, scale);
+  else { set_error("unknown dtype %d", dtype); return 2; }
+  B200Q_LAUNCH_CHECK();
+  return 0;
+}
+
 int b200q_apply_parity_phase(void* state, int n, int dtype, int64_t batch, uint64_t mask,
                              double p0_re, double p0_im, double p1_re, double p1_im,
                              const void* phases_dev, void* stream) {

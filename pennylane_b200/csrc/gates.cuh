@@ -268,6 +268,36 @@ k_pauli_rot(cx<T>* __restrict__ state, const int n, const int pivot, const uint6
 }
 
 // ---------------------------------------------------------------------------------------
+// Mid-circuit measurement collapse (apply_operation.py:478-495): project bit `q` on `sample`,
+// rescale the surviving half by 1/||P psi||, and (reset && sample == 1) move it to the
+// bit = 0 half — the reference's projector sweep, `state / norm` sweep and reset sweep in one
+// pass that reads only the surviving half: S/2 read + S written.
+//   src  = half that survives          (bit == sample)
+//   keep = where it lands              (bit == sample, or 0 when reset)
+//   zero = the other half
+// ---------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_collapse(cx<T>* __restrict__ state, const int n, const int q, const int sample,
+           const int reset, const double scale) {
+  const uint64_t half = 1ull << (n - 1);
+  const uint64_t bitq = 1ull << q;
+  const uint64_t src_or = sample ? bitq : 0ull;
+  const uint64_t keep_or = (sample && !reset) ? bitq : 0ull;
+  const uint64_t zero_or = keep_or ^ bitq;
+  const T sc = (T)scale;
+  const int8_t pos = (int8_t)q;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < half; g += stride) {
+    const uint64_t i = insert_zero_bits(g, &pos, 1);
+    cx<T> v = state[i | src_or];
+    v.x *= sc; v.y *= sc;
+    state[i | keep_or] = v;
+    state[i | zero_or] = make_cx<T>((T)0, (T)0);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // State initialisation: |index> for every batch element (initialize_state.py:43-44).
 // ---------------------------------------------------------------------------------------
 template <typename T>

@@ -25,6 +25,7 @@ import numpy as np
 
 from . import adjoint as _adjoint
 from . import simulate as _sim
+from .one_shot import dynamic_one_shot
 from .tape import QuantumScript
 
 
@@ -92,8 +93,10 @@ def stopping_condition(op) -> bool:
     if op.name in ("Snapshot", "Barrier", "Identity", "GlobalPhase", "MultiControlledX", "MultiRZ",
                    "PauliRot"):
         return True
-    if op.name in ("MidMeasureMP", "Conditional"):
-        return False
+    if op.name == "MidMeasureMP":
+        return True                       # default_qubit.py:145-146, allow_mcms (one-shot method)
+    if op.name.startswith("Conditional") and hasattr(op, "meas_val"):
+        return stopping_condition(op.base)
     if op.name == "GroverOperator":
         return len(op.wires) < 9          # apply_operation.py:845: matrix below nine wires
     base = getattr(op, "base", None)
@@ -108,8 +111,8 @@ def stopping_condition(op) -> bool:
 
 def adjoint_ops(op, trainable: bool = True) -> bool:
     """default_qubit.py:286-292."""
-    if op.name in ("MidMeasureMP", "Conditional"):
-        return False
+    if op.name == "MidMeasureMP" or op.name.startswith("Conditional"):
+        return False                      # default_qubit.py:288
     npar = len(op.data)
     return npar == 0 or not trainable or (npar == 1 and getattr(op, "has_generator", False))
 
@@ -154,6 +157,22 @@ def _decompose(tape: QuantumScript, accept, name: str, max_depth: int = 10) -> Q
         if t >= n_old_op_params:
             new_train.append(nidx + (t - n_old_op_params))
     return QuantumScript(new_ops, tape.measurements, shots=tape.shots, trainable_params=new_train)
+
+
+class _PreprocessedBatch(tuple):
+    """The tapes ``preprocess`` returns.  The reference returns a transform program whose
+    application yields ``(tapes, postprocessing)`` (device_api.py:269-339); this mirror returns the
+    tapes directly, so the one post-processing step the device pipeline owns — combining the
+    per-shot results of a one-shot mid-circuit-measurement tape (dynamic_one_shot.py:172-181) —
+    rides along as ``.postprocessing(results)``."""
+
+    def __new__(cls, tapes, posts):
+        self = super().__new__(cls, tapes)
+        self._posts = tuple(posts)
+        return self
+
+    def postprocessing(self, results):
+        return tuple(r if p is None else p(r) for r, p in zip(results, self._posts))
 
 
 class B200Qubit:
@@ -287,14 +306,27 @@ class B200Qubit:
         config = self.setup_execution_config(execution_config)
         single = isinstance(circuits, QuantumScript)
         tapes = [circuits] if single else list(circuits)
-        out = []
+        out, posts = [], []
         for t in tapes:
             self._validate(t)
             t = _decompose(t, lambda op, _tr: stopping_condition(op), self.name)
-            if config.gradient_method == "adjoint":
+            post = None
+            if any(op.name == "MidMeasureMP" for op in t.operations):
+                # default_qubit.py:632-664 with mcm_method "one-shot" (the default with shots,
+                # :744); the analytic default is "deferred", a transform above this boundary
+                if not t.shots:
+                    raise DeviceError(
+                        "Mid-circuit measurements on b200.qubit run natively per shot "
+                        "(mcm_method='one-shot') and need finite shots; apply defer_measurements "
+                        "to the tape for analytic execution.")
+                if config.gradient_method == "adjoint":
+                    raise DeviceError("Finite shots are not supported with adjoint + b200.qubit")
+                t, post = dynamic_one_shot(t)
+            elif config.gradient_method == "adjoint":
                 t = self._adjoint_preprocess(t)
             out.append(t)
-        return tuple(out), config
+            posts.append(post)
+        return _PreprocessedBatch(out, posts), config
 
     # ---- execution -----------------------------------------------------------------------------
     def _as_batch(self, circuits):

@@ -16,6 +16,12 @@ class MeasurementProcess:
     def __init__(self, obs=None, wires=None):
         if obs is not None and wires is not None:
             raise ValueError("Cannot set the wires if an observable is provided.")
+        # a MeasurementValue (mid-circuit measurement outcome) is carried as ``mv``, never as
+        # the observable (pennylane/core/measurements: ``MeasurementProcess.mv``)
+        self.mv = None
+        if getattr(obs, "name", None) == "MeasurementValue":
+            self.mv, obs = obs, None
+            wires = self.mv.wires
         self.obs = obs
         if obs is not None:
             self.wires = tuple(obs.wires)
@@ -27,12 +33,15 @@ class MeasurementProcess:
             self.wires = tuple(wires)
 
     def __repr__(self):
-        inner = repr(self.obs) if self.obs is not None else f"wires={list(self.wires)}"
+        inner = repr(self.obs) if self.obs is not None else (
+            f"mcm wires={list(self.wires)}" if self.mv is not None else f"wires={list(self.wires)}")
         return f"{self.kind}({inner})"
 
     def map_wires(self, wire_map):
         new = self.__class__.__new__(self.__class__)
         new.__dict__.update(self.__dict__)
+        if self.mv is not None:
+            new.mv = self.mv.map_wires(wire_map)
         if self.obs is not None:
             new.obs = self.obs.map_wires(wire_map)
             new.wires = tuple(new.obs.wires)

@@ -11,6 +11,7 @@ from __future__ import annotations
 
 import numpy as np
 
+from .mcm import is_conditional, is_mcm
 from .pauli import PauliSentence, PauliWord
 from .statevector import StateVector
 
@@ -19,8 +20,11 @@ def _is_prep(op) -> bool:
     return hasattr(op, "state_vector")
 
 
-def get_final_state(circuit, dtype=np.complex128, device=None, buffer=None, fusion: int = 0):
+def get_final_state(circuit, dtype=np.complex128, device=None, buffer=None, fusion: int = 0,
+                    mid_measurements=None, rng=None):
     """Run the gate loop (simulate.py:214-235).  ``circuit`` must be in standard wire order.
+    ``mid_measurements`` (a dict, filled in place) and ``rng`` are needed only when the tape
+    holds ``MidMeasure`` operations.
 
     Returns ``(StateVector, is_state_batched)``.  Measurement-only wires are simply extra
     low-order qubits left in |0> (the reference pads them afterwards, simulate.py:237-240).
@@ -43,14 +47,39 @@ def get_final_state(circuit, dtype=np.complex128, device=None, buffer=None, fusi
         vec = np.asarray(prep.state_vector(wire_order=list(range(n))))
         # single-precision StatePrep gives a complex64 simulation (initialize_state.py:47-51)
         sv.set_state(vec)
-    gates = ops_[bool(prep):]
-    if fusion and gates:
-        # host fusion pass + tile kernel: one state sweep per segment (compiler.py)
-        sv.apply_operations_fused(gates, level=fusion)
-    else:
-        for op in gates:
-            sv.apply_operation(op)
+    apply_gates(sv, ops_[bool(prep):], fusion, mid_measurements, rng)
     return sv, sv.batch > 1
+
+
+def apply_gates(sv: StateVector, gates, fusion: int = 0, mid_measurements=None, rng=None):
+    """The gate loop of simulate.py:213-235.  Mid-circuit measurements split the gate list:
+    the unitary runs between them go through the fused path (or gate by gate), a ``MidMeasure``
+    is one probs sweep + one collapse sweep, and a ``Conditional`` is decided on the host from
+    the sampled values (apply_operation.py:355-411) — its base gate simply joins the current
+    run when the condition holds."""
+    run = []
+
+    def flush():
+        if not run:
+            return
+        if fusion:
+            # host fusion pass + tile kernel: one state sweep per segment (compiler.py)
+            sv.apply_operations_fused(list(run), level=fusion)
+        else:
+            for g in run:
+                sv.apply_operation(g)
+        run.clear()
+
+    for op in gates:
+        if is_mcm(op):
+            flush()
+            sv.apply_mid_measure(op, mid_measurements, rng)
+        elif is_conditional(op):
+            if op.meas_val.concretize(mid_measurements):
+                run.append(op.base)
+        else:
+            run.append(op)
+    flush()
 
 
 # ---------------------------------------------------------------------------------------------
@@ -243,9 +272,14 @@ def _measure_sum(mps, sv, shots, rng, exact):
     return [unsq] if shots.has_partitioned_shots else [unsq[0]]
 
 
-def measure_with_samples(mps, sv: StateVector, shots, rng, exact: bool = True):
+def measure_with_samples(mps, sv: StateVector, shots, rng, exact: bool = True,
+                         mid_measurements=None):
     """sampling.py:205-273."""
-    groups, indices = _group_measurements(list(mps))
+    mps = list(mps)
+    if mid_measurements:
+        # the last N measurements are the sampled MCMs of the one-shot tape (sampling.py:235-236)
+        mps = mps[: len(mps) - len(mid_measurements)]
+    groups, indices = _group_measurements(mps)
     all_res = []
     for group in groups:
         mp0 = group[0]
@@ -256,20 +290,25 @@ def measure_with_samples(mps, sv: StateVector, shots, rng, exact: bool = True):
             all_res.extend(_measure_group(group, sv, shots, rng, exact))
     flat_indices = [i for idx in indices for i in idx]
     sorted_res = tuple(r for _, r in sorted(enumerate(all_res), key=lambda t: flat_indices[t[0]]))
+    if mid_measurements:
+        sorted_res += tuple(mid_measurements.values())          # sampling.py:266-267
     if shots.has_partitioned_shots:
         sorted_res = tuple(zip(*sorted_res))
     return sorted_res
 
 
 def measure_final_state(circuit, sv: StateVector, is_state_batched: bool, rng=None,
-                        exact_sampling: bool = True):
+                        exact_sampling: bool = True, mid_measurements=None):
     """simulate.py:246-304."""
     if not circuit.shots:
+        if mid_measurements is not None:
+            raise TypeError("Native mid-circuit measurements are only supported with finite shots.")
         if len(circuit.measurements) == 1:
             return measure(circuit.measurements[0], sv, is_state_batched)
         return tuple(measure(mp, sv, is_state_batched) for mp in circuit.measurements)
     rng = np.random.default_rng(rng)
-    results = measure_with_samples(circuit.measurements, sv, circuit.shots, rng, exact_sampling)
+    results = measure_with_samples(circuit.measurements, sv, circuit.shots, rng, exact_sampling,
+                                   mid_measurements=mid_measurements)
     if len(circuit.measurements) == 1:
         if circuit.shots.has_partitioned_shots:
             return tuple(res[0] for res in results)
@@ -277,15 +316,80 @@ def measure_final_state(circuit, sv: StateVector, is_state_batched: bool, rng=No
     return results
 
 
+def simulate_one_shot_native_mcm(circuit, sv: StateVector, gates, rng, exact_sampling: bool = True,
+                                 fusion: int = 0):
+    """simulate.py:947-990: one shot of a tape with native mid-circuit measurements.  ``sv``
+    already holds the state in front of ``gates`` (the part of the tape from its first
+    ``MidMeasure`` on)."""
+    mid_measurements = {}
+    apply_gates(sv, gates, fusion, mid_measurements, rng)
+    return measure_final_state(circuit, sv, False, rng=rng, exact_sampling=exact_sampling,
+                               mid_measurements=mid_measurements)
+
+
+def _simulate_native_mcm(circuit, rng, dtype, device, exact_sampling, fusion):
+    """The one-shot loop of simulate.py:356-381 (``mcm_method="one-shot"``): every shot re-runs
+    the tape with ``shots=[1]`` and returns its own result tuple; ``dynamic_one_shot``'s
+    post-processing (above the device boundary) combines them.
+
+    The reference re-simulates the whole tape per shot.  Everything in front of the first
+    ``MidMeasure`` is shot-independent, so it is simulated ONCE here and each shot starts from a
+    device-to-device copy of that state; the random stream is consumed in the same order (the
+    prefix draws nothing)."""
+    if not circuit.shots:
+        raise TypeError("Native mid-circuit measurements are only supported with finite shots.")
+    from .tape import Shots
+
+    rng = np.random.default_rng(rng)
+    ops_ = list(circuit.operations)
+    first = next(i for i, op in enumerate(ops_) if is_mcm(op))
+    base, batched = _prefix_state(ops_[:first], circuit.num_wires, dtype, device, fusion)
+    if batched:
+        raise ValueError("MidMeasure cannot be applied to batched states.")
+    rest = ops_[first:]
+    aux = _OneShotView(circuit, Shots([1]))
+    work = base.clone()
+    results = []
+    for i in range(circuit.shots.total_shots):
+        if i:
+            work.data.copy_(base.data)
+        results.append(simulate_one_shot_native_mcm(aux, work, rest, rng, exact_sampling, fusion))
+    return tuple(results)
+
+
+class _OneShotView:
+    """``circuit.copy(shots=[1])`` (simulate.py:359) without copying the tape."""
+
+    def __init__(self, circuit, shots):
+        self._c = circuit
+        self.shots = shots
+
+    def __getattr__(self, name):
+        return getattr(self._c, name)
+
+
+def _prefix_state(ops_, n, dtype, device, fusion):
+    prep = ops_[0] if ops_ and _is_prep(ops_[0]) else None
+    sv = StateVector(n, dtype=dtype, device=device)
+    if prep is not None:
+        sv.set_state(np.asarray(prep.state_vector(wire_order=list(range(n)))))
+    apply_gates(sv, ops_[bool(prep):], fusion)
+    return sv, sv.batch > 1
+
+
 def simulate(circuit, rng=None, dtype=np.complex128, device=None, exact_sampling: bool = True,
              state_cache=None, fusion: int = 0):
-    """simulate.py:308-393 (without native mid-circuit measurements)."""
+    """simulate.py:308-393.  Tapes with ``MidMeasure`` operations take the native one-shot
+    path (:356-381; tree-traversal is not built)."""
     circuit = circuit.map_to_standard_wires()
+    if any(is_mcm(op) for op in circuit.operations):
+        return _simulate_native_mcm(circuit, rng, dtype, device, exact_sampling, fusion)
     sv, batched = get_final_state(circuit, dtype=dtype, device=device, fusion=fusion)
     if state_cache is not None:
         state_cache[circuit.hash] = sv
     return measure_final_state(circuit, sv, batched, rng=rng, exact_sampling=exact_sampling)
 
 
-__all__ = ["get_final_state", "measure", "measure_with_samples", "measure_final_state",
-           "simulate", "sample_state", "PauliWord"]
+__all__ = ["get_final_state", "apply_gates", "measure", "measure_with_samples",
+           "measure_final_state", "simulate", "simulate_one_shot_native_mcm", "sample_state",
+           "PauliWord"]

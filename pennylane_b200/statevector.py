@@ -255,11 +255,55 @@ class StateVector:
                                              ny, 0.0, 0.0, C.c_void_p(dev.data_ptr()), self.stream))
         self._keepalive = dev
 
+    # ---- mid-circuit measurement (apply_operation.py:355-497) ---------------------------------
+    def collapse(self, wire: int, sample: int, reset: bool, scale: float):
+        """Project ``wire`` on ``sample``, multiply the survivors by ``scale`` and optionally
+        reset the wire to |0> — one sweep (``b200q_collapse``)."""
+        check(self.lib.b200q_collapse(self.ptr, self.n, self.dtype_code, self.bit(wire),
+                                      int(sample), int(bool(reset)), float(scale), self.stream))
+
+    def apply_mid_measure(self, op, mid_measurements: dict, rng=None):
+        """``apply_mid_measure`` (apply_operation.py:415-497): sample the wire with the host
+        Generator (``rng.binomial(1, 1 - p0)``, the same draw the reference makes), record it in
+        ``mid_measurements`` and collapse + renormalise + reset on the device."""
+        if self.batch > 1:
+            raise ValueError("MidMeasure cannot be applied to batched states.")
+        if mid_measurements is None:
+            raise AssertionError("mid_measurements dictionary is required for MidMeasure")
+        wire = op.wires[0]
+        p = self.probs([wire])                                   # one read sweep: (p0, p1)
+        # :450 prob0 = real(norm(slice))**2 — sqrt then square, like the reference
+        prob0 = float(np.sqrt(p[0])) ** 2
+        eps = 10 * np.finfo(self.np_dtype).eps                   # :452-457
+        if (prob0 - 1) > eps:
+            raise ValueError(f"probabilities greater than 1. Got norm {prob0}.")
+        if prob0 > 1:
+            prob0 = prob0 / prob0
+        binomial = np.random.binomial if rng is None else rng.binomial
+        sample = int(binomial(1, 1 - prob0))
+        mid_measurements[op] = sample
+        # :478-485 projector then state / norm(state); numpy's complex / real multiplies by the
+        # reciprocal.  A zero-probability branch (cannot be drawn by a Bernoulli with p = 0 or 1)
+        # would give inf, as 0 / 0 does in the reference.
+        norm = float(np.sqrt(p[sample]))
+        with np.errstate(divide="ignore"):
+            scale = float(np.float64(1.0) / np.float64(norm))
+        self.collapse(wire, sample, bool(getattr(op, "reset", False)), scale)
+        return sample
+
     # ---- operator dispatch (apply_operation.py:258-351 singledispatch, re-done for kernels) --
-    def apply_operation(self, op):
+    def apply_operation(self, op, mid_measurements=None, rng=None):
         """Apply one operator (ours or a duck-typed PennyLane one) in place."""
         name = op.name
         wires = list(op.wires)
+        if name == "MidMeasureMP":
+            self.apply_mid_measure(op, mid_measurements, rng)
+            return
+        if name.startswith("Conditional") and hasattr(op, "meas_val"):
+            # apply_conditional, apply_operation.py:355-411
+            if op.meas_val.concretize(mid_measurements):
+                self.apply_operation(op.base, mid_measurements=mid_measurements, rng=rng)
+            return
         if name in ("Identity", "Barrier", "WireCut", "Snapshot"):
             return
         if name == "GlobalPhase":
