@@ -196,15 +196,45 @@ def apply_mid_measure(op, state, is_state_batched=False, mid_measurements=None, 
     return apply_operation(_qubit_unitary(matrix, wire), state, is_state_batched)
 
 
-def apply_operation(op, state, is_state_batched=False, mid_measurements=None, rng=None):
+def apply_snapshot(op, state, is_state_batched=False, debugger=None, tape_shots=None, rng=None):
+    """apply_operation.py:883-917."""
+    if debugger is None or not debugger.active:
+        return state
+    from .measure import measure
+    from .sampling import measure_with_samples
+
+    measurement = op.hyperparameters["measurement"]
+    shots = op.hyperparameters["shots"]
+    if isinstance(shots, str) and shots == "workflow":
+        shots = tape_shots
+    if shots:
+        snapshot = measure_with_samples([measurement], state, shots, is_state_batched, rng)[0]
+    else:
+        snapshot = measure(measurement, state, is_state_batched)
+    tag = op.hyperparameters["tag"]
+    if tag is None:
+        debugger.snapshots[len(debugger.snapshots)] = snapshot
+    elif tag not in debugger.snapshots:
+        debugger.snapshots[tag] = snapshot
+    elif isinstance(debugger.snapshots[tag], list):
+        debugger.snapshots[tag].append(snapshot)
+    else:
+        debugger.snapshots[tag] = [debugger.snapshots[tag], snapshot]
+    return state
+
+
+def apply_operation(op, state, is_state_batched=False, mid_measurements=None, rng=None,
+                    debugger=None, tape_shots=None):
     """Dispatcher — apply_operation.py:258-324 (singledispatch) and the registered kernels."""
     name = op.name
     n_dim = state.ndim
+    if name == "Snapshot":
+        return apply_snapshot(op, state, is_state_batched, debugger, tape_shots, rng)
     if name == "MidMeasureMP":
         return apply_mid_measure(op, state, is_state_batched, mid_measurements, rng)
     if name.startswith("Conditional") and hasattr(op, "meas_val"):
         return apply_conditional(op, state, is_state_batched, mid_measurements, rng)
-    if name in ("Identity", "Snapshot", "Barrier"):                       # :501
+    if name in ("Identity", "Barrier"):                                   # :501
         return state
     if name == "GroverOperator" and len(op.wires) >= 9:                   # :836-846
         return _apply_grover_without_matrix(state, list(op.wires), is_state_batched)

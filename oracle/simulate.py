@@ -29,7 +29,7 @@ def _op_batch(op):
     return bs
 
 
-def get_final_state(circuit, mid_measurements=None, rng=None):   # simulate.py:174-242
+def get_final_state(circuit, mid_measurements=None, rng=None, debugger=None):   # simulate.py:174-242
     ops = list(circuit.operations)
     prep = ops[0] if ops and _is_prep(ops[0]) else None
     op_wires = sorted({w for op in ops for w in op.wires})
@@ -37,7 +37,8 @@ def get_final_state(circuit, mid_measurements=None, rng=None):   # simulate.py:1
     is_state_batched = bool(prep is not None and _op_batch(prep) is not None)
     for op in ops[bool(prep):]:
         state = apply_operation(op, state, is_state_batched=is_state_batched,
-                                mid_measurements=mid_measurements, rng=rng)
+                                mid_measurements=mid_measurements, rng=rng, debugger=debugger,
+                                tape_shots=circuit.shots)
         is_state_batched = is_state_batched or (_op_batch(op) is not None)
     for _ in range(circuit.num_wires - len(op_wires)):
         state = np.stack([state, np.zeros_like(state)], axis=-1)
@@ -63,20 +64,21 @@ def measure_final_state(circuit, state, is_state_batched, rng=None, mid_measurem
     return results
 
 
-def simulate_one_shot_native_mcm(circuit, rng=None):        # simulate.py:947-990
+def simulate_one_shot_native_mcm(circuit, rng=None, debugger=None):   # simulate.py:947-990
     mid_measurements = {}
-    state, is_state_batched = get_final_state(circuit, mid_measurements=mid_measurements, rng=rng)
+    state, is_state_batched = get_final_state(circuit, mid_measurements=mid_measurements, rng=rng,
+                                              debugger=debugger)
     return measure_final_state(circuit, state, is_state_batched, rng=rng,
                                mid_measurements=mid_measurements)
 
 
-def simulate(circuit, rng=None):                            # simulate.py:308-393
+def simulate(circuit, rng=None, debugger=None):             # simulate.py:308-393
     has_mcm = any(op.name == "MidMeasureMP" for op in circuit.operations)
     if has_mcm:                                             # :354-381, one-shot method
         # the device hands ONE Generator to every shot (default_qubit.py:798)
         rng = np.random.default_rng(rng)
         aux_circ = circuit.copy(shots=[1])
-        return tuple(simulate_one_shot_native_mcm(aux_circ, rng=rng)
+        return tuple(simulate_one_shot_native_mcm(aux_circ, rng=rng, debugger=debugger)
                      for _ in range(circuit.shots.total_shots))
-    state, is_state_batched = get_final_state(circuit)
+    state, is_state_batched = get_final_state(circuit, rng=rng, debugger=debugger)
     return measure_final_state(circuit, state, is_state_batched, rng=rng)

@@ -159,6 +159,27 @@ def _decompose(tape: QuantumScript, accept, name: str, max_depth: int = 10) -> Q
     return QuantumScript(new_ops, tape.measurements, shots=tape.shots, trainable_params=new_train)
 
 
+class Debugger:
+    """pennylane/debugging/snapshot.py:35-58 (``_SnapshotDebugger``): while the context is
+    active the device records every ``Snapshot`` it meets in ``snapshots``."""
+
+    def __init__(self, dev=None):
+        self.snapshots = {}
+        self.active = dev is None          # a free-standing debugger (tests) is active at once
+        self.device = dev
+        if dev is not None:
+            dev._debugger = self
+
+    def __enter__(self):
+        self.active = True
+        return self
+
+    def __exit__(self, *exc):
+        self.active = False
+        if self.device is not None:
+            self.device._debugger = None
+
+
 class _PreprocessedBatch(tuple):
     """The tapes ``preprocess`` returns.  The reference returns a transform program whose
     application yields ``(tapes, postprocessing)`` (device_api.py:269-339); this mirror returns the
@@ -220,6 +241,7 @@ class B200Qubit:
         self._torch_device = device
         self._debugger = None
         self._state_cache = None
+        self._debugger = None
         self.tracker = Tracker()
 
     def __repr__(self):
@@ -357,7 +379,8 @@ class B200Qubit:
         return _sim.simulate(
             circuit, rng=opts.get("rng", self._rng), dtype=opts.get("c_dtype", self._c_dtype),
             device=self._torch_device, exact_sampling=opts.get("exact_sampling", self._exact_sampling),
-            state_cache=self._state_cache, fusion=opts.get("fusion", self._fusion))
+            state_cache=self._state_cache, fusion=opts.get("fusion", self._fusion),
+            debugger=self._debugger)
 
     def execute(self, circuits, execution_config: ExecutionConfig | None = None):
         batch, single = self._as_batch(circuits)

@@ -1678,6 +1678,51 @@ def tensor_product_wires(*ops_):
     return tuple(itertools.chain.from_iterable(o.wires for o in ops_))
 
 
+class Snapshot(Operator):
+    """Debugger snapshot (pennylane/ops/meta.py:158-300): records ``measurement`` of the state at
+    this point of the circuit into the device's debugger (apply_operation.py:883-917); a no-op
+    without an active debugger."""
+
+    num_params = 0
+    has_matrix = False
+
+    def __init__(self, tag=None, measurement=None, shots="workflow"):
+        from .measurements import MeasurementProcess, StateMP
+        from .tape import Shots
+
+        if tag is not None and not isinstance(tag, (str, int)):
+            raise ValueError("Snapshot tags can only be of type 'str'")
+        if measurement is None:
+            measurement = StateMP()
+        if not isinstance(measurement, MeasurementProcess):
+            raise ValueError(f"The measurement {measurement.__class__.__name__} is not supported "
+                             f"as it is not an instance of {MeasurementProcess}")
+        if isinstance(measurement, StateMP) and isinstance(shots, str) and shots == "workflow":
+            shots = None                                   # always analytic with state
+        super().__init__(wires=measurement.wires)
+        self.hyperparameters = {
+            "tag": tag, "measurement": measurement,
+            "shots": shots if (isinstance(shots, str) and shots == "workflow") else Shots(shots)}
+
+    @property
+    def tag(self):
+        return self.hyperparameters["tag"]
+
+    def decomposition(self):
+        return []
+
+    def adjoint(self):
+        return Snapshot(**self.hyperparameters)
+
+    def map_wires(self, wire_map: dict):
+        return Snapshot(tag=self.tag, measurement=self.hyperparameters["measurement"].map_wires(wire_map),
+                        shots=self.hyperparameters["shots"])
+
+    def __repr__(self):
+        return (f"<Snapshot: tag={self.tag}, measurement={self.hyperparameters['measurement']}, "
+                f"shots={self.hyperparameters['shots']}>")
+
+
 __all__ = [n for n, v in list(globals().items())
            if isinstance(v, type) and issubclass(v, Operator)] + [
     "adjoint", "ctrl", "dot", "matrix", "generator_matrix", "operation_derivative",

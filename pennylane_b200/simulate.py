@@ -21,7 +21,7 @@ def _is_prep(op) -> bool:
 
 
 def get_final_state(circuit, dtype=np.complex128, device=None, buffer=None, fusion: int = 0,
-                    mid_measurements=None, rng=None):
+                    mid_measurements=None, rng=None, debugger=None, exact_sampling: bool = True):
     """Run the gate loop (simulate.py:214-235).  ``circuit`` must be in standard wire order.
     ``mid_measurements`` (a dict, filled in place) and ``rng`` are needed only when the tape
     holds ``MidMeasure`` operations.
@@ -47,11 +47,39 @@ def get_final_state(circuit, dtype=np.complex128, device=None, buffer=None, fusi
         vec = np.asarray(prep.state_vector(wire_order=list(range(n))))
         # single-precision StatePrep gives a complex64 simulation (initialize_state.py:47-51)
         sv.set_state(vec)
-    apply_gates(sv, ops_[bool(prep):], fusion, mid_measurements, rng)
+    apply_gates(sv, ops_[bool(prep):], fusion, mid_measurements, rng, debugger,
+                getattr(circuit, "shots", None), exact_sampling)
     return sv, sv.batch > 1
 
 
-def apply_gates(sv: StateVector, gates, fusion: int = 0, mid_measurements=None, rng=None):
+def apply_snapshot(op, sv: StateVector, debugger, tape_shots=None, rng=None, exact: bool = True):
+    """apply_operation.py:883-917: measure the current state into ``debugger.snapshots``."""
+    if debugger is None or not debugger.active:
+        return
+    measurement = op.hyperparameters["measurement"]
+    shots = op.hyperparameters["shots"]
+    if isinstance(shots, str) and shots == "workflow":
+        shots = tape_shots
+    batched = sv.batch > 1
+    if shots:
+        snapshot = measure_with_samples([measurement], sv, shots, np.random.default_rng(rng),
+                                        exact)[0]
+    else:
+        snapshot = measure(measurement, sv, batched)
+    tag = op.hyperparameters["tag"]
+    snaps = debugger.snapshots
+    if tag is None:
+        snaps[len(snaps)] = snapshot
+    elif tag not in snaps:
+        snaps[tag] = snapshot
+    elif isinstance(snaps[tag], list):
+        snaps[tag].append(snapshot)
+    else:
+        snaps[tag] = [snaps[tag], snapshot]
+
+
+def apply_gates(sv: StateVector, gates, fusion: int = 0, mid_measurements=None, rng=None,
+                debugger=None, tape_shots=None, exact: bool = True):
     """The gate loop of simulate.py:213-235.  Mid-circuit measurements split the gate list:
     the unitary runs between them go through the fused path (or gate by gate), a ``MidMeasure``
     is one probs sweep + one collapse sweep, and a ``Conditional`` is decided on the host from
@@ -77,6 +105,10 @@ def apply_gates(sv: StateVector, gates, fusion: int = 0, mid_measurements=None, 
         elif is_conditional(op):
             if op.meas_val.concretize(mid_measurements):
                 run.append(op.base)
+        elif op.name == "Snapshot":
+            if debugger is not None and debugger.active:
+                flush()
+                apply_snapshot(op, sv, debugger, tape_shots, rng, exact)
         else:
             run.append(op)
     flush()
@@ -317,17 +349,17 @@ def measure_final_state(circuit, sv: StateVector, is_state_batched: bool, rng=No
 
 
 def simulate_one_shot_native_mcm(circuit, sv: StateVector, gates, rng, exact_sampling: bool = True,
-                                 fusion: int = 0):
+                                 fusion: int = 0, debugger=None):
     """simulate.py:947-990: one shot of a tape with native mid-circuit measurements.  ``sv``
     already holds the state in front of ``gates`` (the part of the tape from its first
     ``MidMeasure`` on)."""
     mid_measurements = {}
-    apply_gates(sv, gates, fusion, mid_measurements, rng)
+    apply_gates(sv, gates, fusion, mid_measurements, rng, debugger, circuit.shots, exact_sampling)
     return measure_final_state(circuit, sv, False, rng=rng, exact_sampling=exact_sampling,
                                mid_measurements=mid_measurements)
 
 
-def _simulate_native_mcm(circuit, rng, dtype, device, exact_sampling, fusion):
+def _simulate_native_mcm(circuit, rng, dtype, device, exact_sampling, fusion, debugger=None):
     """The one-shot loop of simulate.py:356-381 (``mcm_method="one-shot"``): every shot re-runs
     the tape with ``shots=[1]`` and returns its own result tuple; ``dynamic_one_shot``'s
     post-processing (above the device boundary) combines them.
@@ -342,7 +374,9 @@ def _simulate_native_mcm(circuit, rng, dtype, device, exact_sampling, fusion):
 
     rng = np.random.default_rng(rng)
     ops_ = list(circuit.operations)
-    first = next(i for i, op in enumerate(ops_) if is_mcm(op))
+    snap = debugger is not None and debugger.active       # snapshots are recorded per shot
+    first = next(i for i, op in enumerate(ops_)
+                 if is_mcm(op) or (snap and op.name == "Snapshot"))
     base, batched = _prefix_state(ops_[:first], circuit.num_wires, dtype, device, fusion)
     if batched:
         raise ValueError("MidMeasure cannot be applied to batched states.")
@@ -353,7 +387,8 @@ def _simulate_native_mcm(circuit, rng, dtype, device, exact_sampling, fusion):
     for i in range(circuit.shots.total_shots):
         if i:
             work.data.copy_(base.data)
-        results.append(simulate_one_shot_native_mcm(aux, work, rest, rng, exact_sampling, fusion))
+        results.append(simulate_one_shot_native_mcm(aux, work, rest, rng, exact_sampling, fusion,
+                                                    debugger))
     return tuple(results)
 
 
@@ -378,13 +413,16 @@ def _prefix_state(ops_, n, dtype, device, fusion):
 
 
 def simulate(circuit, rng=None, dtype=np.complex128, device=None, exact_sampling: bool = True,
-             state_cache=None, fusion: int = 0):
+             state_cache=None, fusion: int = 0, debugger=None):
     """simulate.py:308-393.  Tapes with ``MidMeasure`` operations take the native one-shot
     path (:356-381; tree-traversal is not built)."""
     circuit = circuit.map_to_standard_wires()
     if any(is_mcm(op) for op in circuit.operations):
-        return _simulate_native_mcm(circuit, rng, dtype, device, exact_sampling, fusion)
-    sv, batched = get_final_state(circuit, dtype=dtype, device=device, fusion=fusion)
+        return _simulate_native_mcm(circuit, rng, dtype, device, exact_sampling, fusion, debugger)
+    if debugger is not None and debugger.active and circuit.shots:
+        rng = np.random.default_rng(rng)        # snapshots and final sampling share one stream
+    sv, batched = get_final_state(circuit, dtype=dtype, device=device, fusion=fusion, rng=rng,
+                                  debugger=debugger, exact_sampling=exact_sampling)
     if state_cache is not None:
         state_cache[circuit.hash] = sv
     return measure_final_state(circuit, sv, batched, rng=rng, exact_sampling=exact_sampling)

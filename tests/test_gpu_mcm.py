@@ -229,3 +229,72 @@ def test_prefix_is_simulated_once(monkeypatch):
     n_prefix = next(i for i, op in enumerate(tape.operations) if op.name == "MidMeasureMP")
     # per shot at most the 6 unitary gates behind the first measurement (+ diagonalising gates)
     assert calls["n"] <= n_prefix + 10 * 12
+
+
+# ---- Snapshot: tests/devices/qubit/test_apply_operation.py:771-873 on the device ---------------------
+_SNAP_STATE = np.array([[0.04624539 + 0.3895457j, 0.22399401 + 0.53870339j],
+                        [-0.483054 + 0.2468498j, -0.02772249 - 0.45901669j]])
+
+
+def test_snapshot_known_answers():
+    from oracle.measure import measure as oracle_measure
+    from pennylane_b200 import StateVector, measurements as M, ops
+    from pennylane_b200.device import Debugger
+    from pennylane_b200.simulate import apply_gates
+
+    sv = _sv(_SNAP_STATE)
+    apply_gates(sv, [ops.Snapshot()])                                   # no debugger: nothing
+    assert np.array_equal(_get(sv), _SNAP_STATE)
+    dbg = Debugger()
+    apply_gates(sv, [ops.Snapshot(), ops.Snapshot("abcd")], debugger=dbg)
+    assert list(dbg.snapshots) == [0, "abcd"] and dbg.snapshots[0].shape == (4,)
+    assert np.array_equal(dbg.snapshots[0], _SNAP_STATE.ravel())
+    assert np.array_equal(dbg.snapshots["abcd"], _SNAP_STATE.ravel())
+    for mp in (M.expval(ops.PauliX(0)), M.var(ops.PauliZ(1)), M.probs(wires=[0])):
+        dbg = Debugger()
+        apply_gates(sv, [ops.Snapshot(measurement=mp)], debugger=dbg)
+        assert np.allclose(dbg.snapshots[0], oracle_measure(mp, _SNAP_STATE), rtol=1e-12, atol=1e-15)
+    dbg = Debugger()
+    one = StateVector(1)
+    apply_gates(one, [ops.Snapshot("tag", M.sample(wires=0), shots=50)], debugger=dbg)
+    assert dbg.snapshots["tag"].shape == (50, 1) and not dbg.snapshots["tag"].any()
+    dbg = Debugger()
+    two = StateVector(1, batch=2)
+    two.set_state(np.array([[1.0, 0.0], [0.0, 0.1]], dtype=complex))
+    apply_gates(two, [ops.Snapshot()], debugger=dbg)
+    assert np.array_equal(dbg.snapshots[0], np.array([[1.0, 0.0], [0.0, 0.1]]))
+
+
+@pytest.mark.parametrize("fusion", [0, 1])
+def test_snapshots_through_the_device_match_oracle(fusion):
+    """Snapshots inside a fused run split it; state / expval / shot snapshots and the final
+    samples equal the oracle's under the same seed."""
+    import pennylane_b200 as pb
+    from oracle.simulate import simulate as oracle_simulate
+    from pennylane_b200 import QuantumScript, measurements as M, ops
+    from pennylane_b200.device import Debugger
+
+    n = 6
+    rng = np.random.default_rng(4)
+    gates = []
+    for layer in range(3):
+        gates += [ops.RY(rng.uniform(0, 6), wires=w) for w in range(n)]
+        gates += [ops.CNOT(wires=[w, (w + 1) % n]) for w in range(n)]
+        gates.append(ops.Snapshot(f"s{layer}"))
+        gates.append(ops.Snapshot("e", M.expval(ops.PauliZ(0) @ ops.PauliZ(1)), shots=None))
+        gates.append(ops.Snapshot("shots", M.sample(wires=[0, 2])))
+    tape = QuantumScript(gates, [M.sample(wires=list(range(n)))], shots=20)
+    dev = pb.device("b200.qubit", seed=8, fusion=fusion)
+    with Debugger(dev) as dbg:
+        res = dev.execute(tape)
+    assert dev._debugger is None
+    ref_dbg = Debugger()
+    ref = oracle_simulate(tape, rng=np.random.default_rng(8), debugger=ref_dbg)
+    assert np.array_equal(res, ref)
+    assert set(dbg.snapshots) == set(ref_dbg.snapshots) == {"s0", "s1", "s2", "e", "shots"}
+    for k in ("s0", "s1", "s2"):
+        assert np.max(np.abs(dbg.snapshots[k] - ref_dbg.snapshots[k])) < 1e-12
+    assert np.allclose(dbg.snapshots["e"], ref_dbg.snapshots["e"], atol=1e-12)
+    assert len(dbg.snapshots["shots"]) == 3
+    for a, b in zip(dbg.snapshots["shots"], ref_dbg.snapshots["shots"]):
+        assert a.shape == (20, 2) and np.array_equal(a, b)

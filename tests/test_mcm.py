@@ -196,3 +196,50 @@ def test_one_shot_shot_vector_and_passthrough():
     assert same is plain and post("x") == "x"
     with pytest.raises(ValueError, match="finite shots"):
         dynamic_one_shot(QuantumScript([mv.measurements[0]], [M.expval(mv)]))
+
+
+# ---- Snapshot: tests/devices/qubit/test_apply_operation.py:771-873 -----------------------------------
+_SNAP_STATE = np.array([[0.04624539 + 0.3895457j, 0.22399401 + 0.53870339j],
+                        [-0.483054 + 0.2468498j, -0.02772249 - 0.45901669j]])
+
+
+def test_snapshot_known_answers_oracle():
+    from oracle.measure import measure as oracle_measure
+    from pennylane_b200.device import Debugger
+
+    assert apply_operation(ops.Snapshot(), _SNAP_STATE) is _SNAP_STATE          # :774-786
+    dbg = Debugger()
+    new = apply_operation(ops.Snapshot(), _SNAP_STATE, debugger=dbg)            # :788-806
+    assert np.allclose(new, _SNAP_STATE) and list(dbg.snapshots) == [0]
+    assert dbg.snapshots[0].shape == (4,) and np.allclose(dbg.snapshots[0], _SNAP_STATE.ravel())
+    dbg = Debugger()
+    apply_operation(ops.Snapshot("abcd"), _SNAP_STATE, debugger=dbg)            # :808-827
+    assert list(dbg.snapshots) == ["abcd"] and dbg.snapshots["abcd"].shape == (4,)
+    for mp in (M.expval(ops.PauliX(0)), M.var(ops.PauliZ(1)), M.probs(wires=[0])):   # :829-850
+        dbg = Debugger()
+        apply_operation(ops.Snapshot(measurement=mp), _SNAP_STATE, debugger=dbg)
+        assert np.array_equal(dbg.snapshots[0], oracle_measure(mp, _SNAP_STATE))
+    dbg = Debugger()                                                            # :852-861
+    apply_operation(ops.Snapshot("tag", M.sample(wires=0), shots=50),
+                    np.array([1.0, 0.0], dtype=complex), debugger=dbg)
+    assert dbg.snapshots["tag"].shape == (50, 1)
+    dbg = Debugger()                                                            # :863-873
+    batched = np.array([[1.0, 0.0], [0.0, 0.1]], dtype=complex)
+    apply_operation(ops.Snapshot(), batched, is_state_batched=True, debugger=dbg)
+    assert set(dbg.snapshots) == {0} and np.array_equal(dbg.snapshots[0], batched)
+    # repeated tags collect into a list (apply_operation.py:908-915)
+    dbg = Debugger()
+    for _ in range(3):
+        apply_operation(ops.Snapshot("t", M.probs(wires=[1])), _SNAP_STATE, debugger=dbg)
+    assert isinstance(dbg.snapshots["t"], list) and len(dbg.snapshots["t"]) == 3
+
+
+def test_snapshot_operator_rules():
+    snap = ops.Snapshot()
+    assert not snap.hyperparameters["shots"] and snap.hyperparameters["measurement"].kind == "state"
+    assert ops.Snapshot(measurement=M.expval(ops.PauliZ("a"))).hyperparameters["shots"] == "workflow"
+    assert ops.Snapshot("t", M.probs(wires=["a"])).map_wires({"a": 0}).wires == (0,)
+    with pytest.raises(ValueError, match="tags can only be"):
+        ops.Snapshot(tag=1.5)
+    with pytest.raises(ValueError, match="not supported"):
+        ops.Snapshot(measurement=ops.PauliZ(0))
