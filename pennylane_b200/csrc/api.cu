@@ -226,7 +226,9 @@ static int probs_t(const void* state, int n, int64_t batch, const int* bits, int
       a.sum_mask |= 1ull << q;
     }
   }
-  int lg = std::max(0, std::min(14 - a.n_outer, a.n_sum_hi));
+  // ~2^17 warp tasks: an order of magnitude more than resident warps (148 SMs x 64), so the
+  // grid-stride tail costs a few percent instead of up to one task in two
+  int lg = std::max(0, std::min(17 - a.n_outer, a.n_sum_hi - 4));
   const size_t avail = (work && work_bytes > kTermRegion) ? work_bytes - kTermRegion : 0;
   while (lg > 0 && ((uint64_t)batch << (m + lg)) * sizeof(double) > avail) --lg;
   a.lg_nsplit = lg;
@@ -236,8 +238,13 @@ static int probs_t(const void* state, int n, int64_t batch, const int* bits, int
   k_probs_marginal<T><<<grid, 256, 0, s>>>((const cx<T>*)state, partials, a);
   B200Q_LAUNCH_CHECK();
   if (lg > 0) {
-    dim3 g2((unsigned)(((1ull << m) + 255) / 256), (unsigned)batch);
-    k_sum_splits<<<g2, 256, 0, s>>>(partials, out, m, lg);
+    if (m <= 10 && lg >= 8) {
+      dim3 g2(1u << m, (unsigned)batch);
+      k_sum_splits_cta<<<g2, 256, 0, s>>>(partials, out, m, lg);
+    } else {
+      dim3 g2((unsigned)(((1ull << m) + 255) / 256), (unsigned)batch);
+      k_sum_splits<<<g2, 256, 0, s>>>(partials, out, m, lg);
+    }
     B200Q_LAUNCH_CHECK();
   }
   return 0;

@@ -86,13 +86,21 @@ k_probs_marginal(const cx<T>* __restrict__ state, double* __restrict__ partials,
     const uint64_t r0 = split * per_split;
     uint64_t sub = 0;
     for (int j = 0; j < a.n_sum_hi; ++j) sub |= ((r0 >> j) & 1ull) << a.sum_pos[j];
-    double acc = 0.0;
+    // two accumulators, eight loads in flight per lane; (r even) + (r odd) in a fixed order
+    double acc = 0.0, acc1 = 0.0;
 #pragma unroll 4
-    for (uint64_t r = 0; r < per_split; ++r) {
+    for (uint64_t r = 0; r + 1 < per_split; r += 2) {
+      const uint64_t idx0 = base | sub | (uint64_t)lane;
+      sub = ((sub | ~a.sum_mask) + 1ull) & a.sum_mask;
+      const uint64_t idx1 = base | sub | (uint64_t)lane;
+      sub = ((sub | ~a.sum_mask) + 1ull) & a.sum_mask;
+      if (lane_ok) { acc += abs2_exact(st[idx0]); acc1 += abs2_exact(st[idx1]); }
+    }
+    if (per_split & 1ull) {
       const uint64_t idx = base | sub | (uint64_t)lane;
       if (lane_ok) acc += abs2_exact(st[idx]);
-      sub = ((sub | ~a.sum_mask) + 1ull) & a.sum_mask;
     }
+    acc += acc1;
     // reduce over summed lane bits (fixed xor order: bit 4 down to bit 0)
 #pragma unroll
     for (int b = 4; b >= 0; --b)
@@ -122,6 +130,20 @@ k_sum_splits(const double* __restrict__ partials, double* __restrict__ out, cons
 // ---- final reduction of per-CTA partials ----------------------------------------------------
 // partials: [nlaunch][rows][ncta] doubles; out[row] = scale * sum over (launch, cta) in index
 // order (one CTA per row: strided accumulation then block_sum => fixed order).
+// Same sum for few bins and many splits: one CTA per bin, strided accumulation then block_sum
+// (fixed order), instead of one thread walking 2^lg_nsplit partials.
+__global__ void __launch_bounds__(256)
+k_sum_splits_cta(const double* __restrict__ partials, double* __restrict__ out, const int m,
+                 const int lg_nsplit) {
+  __shared__ double sh[32];
+  const double* p = partials + ((uint64_t)blockIdx.y << (m + lg_nsplit));
+  double acc = 0.0;
+  for (uint64_t s = threadIdx.x; s < (1ull << lg_nsplit); s += blockDim.x)
+    acc += p[(s << m) + blockIdx.x];
+  acc = block_sum(acc, sh);
+  if (threadIdx.x == 0) out[((uint64_t)blockIdx.y << m) + blockIdx.x] = acc;
+}
+
 __global__ void __launch_bounds__(256)
 k_final_reduce(const double* __restrict__ partials, double* __restrict__ out, const int ncta,
                const int nlaunch, const int rows, const double scale) {

@@ -47,6 +47,7 @@ class _MP:
         if self.kind is None:
             raise qml.DeviceError(f"Measurement {mp} is not supported on b200.qubit")
         self.obs = mp.obs
+        self.mv = getattr(mp, "mv", None)     # sampled mid-circuit value of a one-shot tape
         self.wires = tuple(mp.wires)
 
     def diagonalizing_gates(self):
@@ -57,6 +58,9 @@ class _MP:
 
     def process_samples(self, samples, wire_order):
         return self._mp.process_samples(samples, qml.wires.Wires(list(wire_order)))
+
+
+_sim.MEASUREMENT_ADAPTER = _MP
 
 
 class _Tape:
@@ -140,16 +144,39 @@ class B200QubitDevice(Device):
         opts.setdefault("fusion", self._fusion)
         opts.setdefault("exact_sampling", self._exact)
         updated["device_options"] = opts
+        # _setup_mcm_config, default_qubit.py:740-760: one-shot with shots, deferred without;
+        # tree-traversal is not built on this device
+        mcm = config.mcm_config
+        method = mcm.mcm_method
+        if method is None:
+            method = "one-shot" if getattr(circuit, "shots", None) else "deferred"
+        if method not in ("deferred", "one-shot"):
+            raise qml.DeviceError(f"mcm_method {method} not supported on b200.qubit. "
+                                  "Supported methods are 'deferred' and 'one-shot'.")
+        if mcm.postselect_mode == "fill-shots" and method != "deferred":
+            raise qml.DeviceError(
+                "Using postselect_mode='fill-shots' is only supported with mcm_method='deferred'.")
+        updated["mcm_config"] = replace(mcm, mcm_method=method)
         return replace(config, **updated)
 
     def preprocess_transforms(self, execution_config=None):
         config = execution_config or ExecutionConfig()
         prog = TransformProgram()
-        prog.add_transform(qml.defer_measurements, allow_postselect=False)
+        one_shot = config.mcm_config.mcm_method == "one-shot"      # default_qubit.py:632-664
+        if one_shot:
+            accept = stopping_condition                 # MidMeasure / Conditional applied natively
+        else:
+            prog.add_transform(qml.defer_measurements, allow_postselect=False)
+
+            def accept(op):
+                return op.name != "MidMeasureMP" and stopping_condition(op)
         prog.add_transform(validate_device_wires, self.wires, name=self.name)
-        prog.add_transform(decompose, stopping_condition=stopping_condition, name=self.name)
+        prog.add_transform(decompose, stopping_condition=accept, name=self.name)
         prog.add_transform(validate_measurements, name=self.name)
         prog.add_transform(validate_observables, lambda o: True, name=self.name)
+        if one_shot:
+            prog.add_transform(qml.transforms.dynamic_one_shot,
+                               postselect_mode=config.mcm_config.postselect_mode)
         if config.gradient_method == "adjoint":         # _add_adjoint_transforms :315-349
             name = "adjoint + b200.qubit"
             prog.add_transform(no_sampling, name=name)
@@ -168,7 +195,8 @@ class B200QubitDevice(Device):
 
     def execute(self, circuits, execution_config=None):
         rng, dt, fusion, exact = self._opts(execution_config)
-        return tuple(_sim.simulate(_Tape(c), rng=rng, dtype=dt, exact_sampling=exact, fusion=fusion)
+        return tuple(_sim.simulate(_Tape(c), rng=rng, dtype=dt, exact_sampling=exact, fusion=fusion,
+                                   debugger=self._debugger)
                      for c in circuits)
 
     def compute_derivatives(self, circuits, execution_config=None):

@@ -52,11 +52,17 @@ def get_final_state(circuit, dtype=np.complex128, device=None, buffer=None, fusi
     return sv, sv.batch > 1
 
 
+#: set by ``pl_plugin`` to wrap PennyLane measurement processes met inside ``Snapshot`` operators
+MEASUREMENT_ADAPTER = None
+
+
 def apply_snapshot(op, sv: StateVector, debugger, tape_shots=None, rng=None, exact: bool = True):
     """apply_operation.py:883-917: measure the current state into ``debugger.snapshots``."""
     if debugger is None or not debugger.active:
         return
     measurement = op.hyperparameters["measurement"]
+    if not hasattr(measurement, "kind") and MEASUREMENT_ADAPTER is not None:
+        measurement = MEASUREMENT_ADAPTER(measurement)       # a genuine PennyLane measurement
     shots = op.hyperparameters["shots"]
     if isinstance(shots, str) and shots == "workflow":
         shots = tape_shots
