@@ -68,6 +68,17 @@ int b200q_apply_phase(void* state, int n, int dtype, int64_t batch, const int* c
                       const int* ctrl_vals, int nc, double phase_re, double phase_im,
                       const void* phase_dev, void* stream);
 
+/* One block of a reduced density matrix, pennylane/math/quantum.py:386-487 (`reduce_statevector`,
+ * the einsum behind qml.density_matrix / purity / vn_entropy / mutual_info):
+ *   G[ai, bi] = sum_r psi[A, ai, r] * conj(psi[B, bi, r])
+ * over all bits r that are neither inner nor outer.  inner_bits (mi <= 2, matrix MSB first) index
+ * the block; outer_bits (mo, MSB first) are fixed to row_assign (A) and col_assign (B).
+ * out_dev: 2 * 4^mi doubles, (re, im) interleaved, row-major.  One unbatched state per call.
+ * Algorithmic bytes: S / 2^mo when A == B, else 2 S / 2^mo. */
+int b200q_gram_block(const void* state, int n, int dtype, const int* inner_bits, int mi,
+                     const int* outer_bits, int mo, uint64_t row_assign, uint64_t col_assign,
+                     double* out_dev, void* work, size_t work_bytes, void* stream);
+
 /* Mid-circuit measurement collapse, apply_operation.py:478-495 (projector, `state / norm`,
  * optional reset) as one sweep: amplitudes with (bit == sample) are multiplied by `scale`
  * (the host passes 1 / sqrt(p_sample), p from b200q_probs on that bit) and, when reset != 0 and

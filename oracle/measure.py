@@ -69,6 +69,65 @@ def eigvals(obs):
     return np.linalg.eigvalsh(observable_matrix(obs, list(obs.wires)))
 
 
+def reduce_statevector(state, indices):
+    """pennylane/math/quantum.py:386-487: ``einsum`` of the state with its conjugate over the
+    traced wires, then the permutation to the requested wire order (``_permute_dense_matrix``).
+    ``state``: ``(2^n,)`` or ``(B, 2^n)``."""
+    from string import ascii_letters
+
+    state = np.asarray(state, dtype="complex128")
+    batched = state.ndim == 2
+    dim = state.shape[-1]
+    num_wires = int(np.log2(dim))
+    consecutive = list(range(num_wires))
+    st = np.reshape(state, [state.shape[0] if batched else 1] + [2] * num_wires)
+    indices1 = ascii_letters[1: num_wires + 1]
+    indices2 = "".join(ascii_letters[num_wires + i + 1] if i in indices else ascii_letters[i + 1]
+                       for i in consecutive)
+    target = "".join([ascii_letters[i + 1] for i in sorted(indices)]
+                     + [ascii_letters[num_wires + i + 1] for i in sorted(indices)])
+    dm = np.einsum(f"a{indices1},a{indices2}->a{target}", st, np.conj(st), optimize="greedy")
+    k = len(indices)
+    dm = np.reshape(dm, (-1, 2 ** k, 2 ** k))
+    # _permute_dense_matrix: from sorted(indices) to the requested order
+    srt = sorted(indices)
+    if list(indices) != srt:
+        perm = [srt.index(w) for w in indices]
+        t = np.reshape(dm, [dm.shape[0]] + [2] * (2 * k))
+        axes = [0] + [1 + p for p in perm] + [1 + k + p for p in perm]
+        dm = np.reshape(np.transpose(t, axes), (-1, 2 ** k, 2 ** k))
+    return dm if batched else dm[0]
+
+
+def _compute_vn_entropy(density_matrix, base=None):   # math/quantum.py:632-663
+    div_base = np.log(base) if base else 1
+    evs = np.linalg.eigvalsh(density_matrix)
+    evs = np.where(evs > 0, evs, 1.0)
+    return np.sum(-evs * np.log(evs), axis=-1) / div_base
+
+
+def density_process_state(mp, flat):
+    """measurements/purity.py:50-54, vn_entropy.py:65-67, mutual_info.py:92-100 and
+    ``DensityMatrixMP.process_state``.  The reference first forms the full density matrix
+    (``dm_from_state_vector``) and reduces it with ``reduce_dm``; tracing |psi><psi| over the
+    complement is the same contraction ``reduce_statevector`` does, which keeps this oracle
+    usable beyond a dozen wires."""
+    if mp.kind == "mutual_info":
+        w0, w1 = (list(w) for w in mp._wires)
+        base = getattr(mp, "log_base", None)
+        return (_compute_vn_entropy(reduce_statevector(flat, w0), base)
+                + _compute_vn_entropy(reduce_statevector(flat, w1), base)
+                - _compute_vn_entropy(reduce_statevector(flat, sorted(w0 + w1)), base))
+    rho = reduce_statevector(flat, list(mp.wires))
+    if mp.kind == "density_matrix":
+        return rho
+    if mp.kind == "purity":                                # math/quantum.py:563-589
+        if rho.ndim > 2:
+            return np.real(np.einsum("abc,acb->a", rho, rho))
+        return np.real(np.einsum("ab,ba", rho, rho))
+    return _compute_vn_entropy(rho, getattr(mp, "log_base", None))
+
+
 def state_diagonalizing_gates(mp, state, is_state_batched=False):   # measure.py:52-71
     if mp.obs is not None:
         for op in diagonalizing_gates(mp.obs):
@@ -80,6 +139,8 @@ def state_diagonalizing_gates(mp, state, is_state_batched=False):   # measure.py
         return probs_process_state(flat, wires, total)
     if mp.kind == "state":
         return flat
+    if mp.kind in ("density_matrix", "purity", "vn_entropy", "mutual_info"):
+        return density_process_state(mp, flat)
     prob = probs_process_state(flat, wires, total)
     ev = np.asarray(eigvals(mp.obs), dtype="float64")
     if mp.kind == "expval":                                  # expval.py:81-118
@@ -236,7 +297,8 @@ def get_measurement_function(mp, state):          # measure.py:165-221
                 return csr_dot_products
             if not _has_diag_gates(mp.obs):
                 return csr_dot_products
-    if mp.kind in ("expval", "var", "probs", "state"):
+    if mp.kind in ("expval", "var", "probs", "state", "density_matrix", "purity", "vn_entropy",
+                   "mutual_info"):
         if mp.obs is None or _has_diag_gates(mp.obs):
             return state_diagonalizing_gates
         if mp.kind == "expval":

@@ -36,6 +36,7 @@ SIGNATURES = {
     "b200q_apply_matrix": (_i, [_p, _i, _i, _i64, _ip, _i, _ip, _ip, _i, _p, _p, _i64, _p]),
     "b200q_apply_diag": (_i, [_p, _i, _i, _i64, _ip, _i, _p, _p, _i64, _p]),
     "b200q_apply_phase": (_i, [_p, _i, _i, _i64, _ip, _ip, _i, _d, _d, _p, _p]),
+    "b200q_gram_block": (_i, [_p, _i, _i, _ip, _i, _ip, _i, _u64, _u64, _p, _p, _sz, _p]),
     "b200q_collapse": (_i, [_p, _i, _i, _i, _i, _i, _d, _p]),
     "b200q_apply_parity_phase": (_i, [_p, _i, _i, _i64, _u64, _d, _d, _d, _d, _p, _p]),
     "b200q_apply_pauli_rot": (_i, [_p, _i, _i, _i64, _u64, _u64, _i, _d, _d, _p, _p]),

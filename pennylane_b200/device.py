@@ -297,7 +297,8 @@ class B200Qubit:
                     f"Cannot run circuit(s) on {self.name} as they contain wires not found on "
                     f"the device: {extra}")
         for m in tape.measurements:
-            if tape.shots and m.kind == "state":
+            if tape.shots and m.kind in ("state", "density_matrix", "purity", "vn_entropy",
+                                         "mutual_info"):
                 raise DeviceError(f"Measurement {m} not accepted with finite shots on {self.name}")
             if not tape.shots and m.kind in ("sample", "counts"):
                 raise DeviceError(f"Measurement {m} not accepted for analytic simulation on "

@@ -145,6 +145,61 @@ class StateMP(MeasurementProcess):
     kind = "state"
 
 
+class DensityMatrixMP(MeasurementProcess):
+    """``qml.density_matrix(wires)`` (measurements/state.py ``DensityMatrixMP``): the reduced
+    density matrix over ``wires`` via ``reduce_statevector`` (math/quantum.py:386-487)."""
+    kind = "density_matrix"
+
+
+class PurityMP(MeasurementProcess):
+    """measurements/purity.py:50-54: tr(rho_wires^2)."""
+    kind = "purity"
+
+
+class VnEntropyMP(MeasurementProcess):
+    """measurements/vn_entropy.py:65-67: -tr(rho log rho) / log(base)."""
+    kind = "vn_entropy"
+
+    def __init__(self, wires=None, log_base=None):
+        super().__init__(wires=wires)
+        self.log_base = log_base
+
+
+class MutualInfoMP(MeasurementProcess):
+    """measurements/mutual_info.py:92-100: S(A) + S(B) - S(AB)."""
+    kind = "mutual_info"
+
+    def __init__(self, wires0, wires1, log_base=None):
+        w0 = tuple(wires0) if hasattr(wires0, "__iter__") and not isinstance(wires0, str) else (wires0,)
+        w1 = tuple(wires1) if hasattr(wires1, "__iter__") and not isinstance(wires1, str) else (wires1,)
+        if set(w0) & set(w1):
+            raise ValueError("Subsystems for computing mutual information must not overlap.")
+        super().__init__(wires=w0 + w1)
+        self._wires = (w0, w1)
+        self.log_base = log_base
+
+    def map_wires(self, wire_map):
+        new = super().map_wires(wire_map)
+        new._wires = tuple(tuple(wire_map.get(w, w) for w in ws) for ws in self._wires)
+        return new
+
+
+def density_matrix(wires):
+    return DensityMatrixMP(wires=wires)
+
+
+def purity(wires):
+    return PurityMP(wires=wires)
+
+
+def vn_entropy(wires, log_base=None):
+    return VnEntropyMP(wires=wires, log_base=log_base)
+
+
+def mutual_info(wires0, wires1, log_base=None):
+    return MutualInfoMP(wires0, wires1, log_base=log_base)
+
+
 def expval(op):
     return ExpectationMP(obs=op)
 

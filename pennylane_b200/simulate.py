@@ -167,6 +167,8 @@ def measure(mp, sv: StateVector, is_state_batched: bool = False):
         wires = list(mp.wires) if len(mp.wires) else list(range(sv.n))
         p = rot.probs(wires)
         return p
+    if kind in ("density_matrix", "purity", "vn_entropy", "mutual_info"):
+        return _measure_density(mp, sv, is_state_batched)
     if kind == "expval":
         if getattr(obs, "name", "") == "SparseHamiltonian":          # measure.py:198-199
             r = sv.expval_csr(obs.sparse_matrix(), list(obs.wires))
@@ -198,6 +200,36 @@ def measure(mp, sv: StateVector, is_state_batched: bool = False):
             return _expval_pauli(sv, _real_sentence(ps2)) - _expval_pauli(sv, ps) ** 2
         raise NotImplementedError(f"variance of {obs} is not supported")
     raise NotImplementedError(f"analytic measurement {kind} is not supported")
+
+
+def _entropy(rho, base):
+    """math/quantum.py:632-663 (``_compute_vn_entropy``): eigvalsh, non-positive eigenvalues
+    dropped, ``entr`` = -x log x summed, divided by log(base)."""
+    evs = np.linalg.eigvalsh(rho)
+    evs = np.where(evs > 0, evs, 1.0)
+    div = np.log(base) if base else 1
+    return np.sum(-evs * np.log(evs), axis=-1) / div
+
+
+def _measure_density(mp, sv: StateVector, is_state_batched: bool):
+    """``qml.density_matrix`` / ``purity`` / ``vn_entropy`` / ``mutual_info``
+    (measurements/purity.py:50-54, vn_entropy.py:65-67, mutual_info.py:92-100).  The reference
+    expands the state into the full 4^n density matrix and traces it down; here
+    ``StateVector.reduced_dm`` reads the statevector and only 2^m x 2^m matrices reach the host."""
+    kind = mp.kind
+    if kind == "mutual_info":
+        w0, w1 = (list(w) for w in mp._wires)
+        base = getattr(mp, "log_base", None)
+        s0 = _entropy(sv.reduced_dm(w0), base)
+        s1 = _entropy(sv.reduced_dm(w1), base)
+        s01 = _entropy(sv.reduced_dm(sorted(w0 + w1)), base)
+        return s0 + s1 - s01
+    rho = sv.reduced_dm(list(mp.wires))
+    if kind == "density_matrix":
+        return rho
+    if kind == "purity":                       # math/quantum.py:563-589: Re tr(rho rho)
+        return np.real(np.einsum("...ab,...ba->...", rho, rho))
+    return _entropy(rho, getattr(mp, "log_base", None))
 
 
 def _real_sentence(ps):

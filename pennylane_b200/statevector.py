@@ -463,6 +463,49 @@ class StateVector:
                                    self.stream))
         return out
 
+    def reduced_dm(self, wires: Sequence[int]) -> np.ndarray:
+        """Reduced density matrix over ``wires`` (in that order), complex128, shape
+        ``(2^m, 2^m)`` or ``(batch, 2^m, 2^m)`` — ``reduce_statevector``
+        (pennylane/math/quantum.py:386-487) without ever forming more than the result.
+
+        The last two wires are the in-thread block of ``b200q_gram_block``; the others are
+        enumerated here as (row, column >= row) outer assignments, the lower triangle follows
+        from Hermiticity."""
+        torch = _torch()
+        wires = list(wires)
+        m = len(wires)
+        if len(set(wires)) != m or any(w < 0 or w >= self.n for w in wires):
+            raise ValueError(f"reduced_dm: bad wires {wires}")
+        mi = min(m, 2)
+        mo = m - mi
+        outer, inner = wires[:mo], wires[mo:]
+        ib, ob = int_array(self.bits(inner)), int_array(self.bits(outer))
+        D = 1 << mi
+        pairs = [(a, b) for a in range(1 << mo) for b in range(a, 1 << mo)]
+        out = torch.empty((self.batch, len(pairs), 2 * D * D), dtype=torch.float64,
+                          device=self.device)
+        w, wb = self.workspace()
+        esz = self.np_dtype.itemsize
+        for bi in range(self.batch):
+            base = self.data.data_ptr() + bi * (esz << self.n)
+            for k, (a, b) in enumerate(pairs):
+                check(self.lib.b200q_gram_block(
+                    C.c_void_p(base), self.n, self.dtype_code, ib, mi, ob, mo, a, b,
+                    C.c_void_p(out[bi, k].data_ptr()), w, wb, self.stream))
+        blocks = out.cpu().numpy().reshape(self.batch, len(pairs), D, D, 2)
+        blocks = blocks[..., 0] + 1j * blocks[..., 1]
+        rho = np.empty((self.batch, 1 << mo, D, 1 << mo, D), dtype=np.complex128)
+        for k, (a, b) in enumerate(pairs):
+            if a == b:
+                # a diagonal block is Hermitian up to the rounding of its fused multiply-adds:
+                # symmetrise, so the result is exactly Hermitian with a real diagonal
+                blocks[:, k] = 0.5 * (blocks[:, k] + np.conj(np.swapaxes(blocks[:, k], -1, -2)))
+            rho[:, a, :, b, :] = blocks[:, k]
+            if a != b:
+                rho[:, b, :, a, :] = np.conj(np.swapaxes(blocks[:, k], -1, -2))
+        rho = rho.reshape(self.batch, 1 << m, 1 << m)
+        return rho if self.batch > 1 else rho[0]
+
     def expval_csr(self, H, wires: Sequence[int]) -> np.ndarray:
         """<psi| H |psi> per batch element for a scipy CSR matrix ``H`` (2^k x 2^k) on ``wires``
         (measure.py:74-118, SparseHamiltonian) — H is NOT expanded to the full register."""

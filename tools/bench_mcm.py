@@ -4,6 +4,7 @@
 * the two sweeps of one native ``MidMeasure`` at N qubits, complex128 — the single-wire
   probability reduction (``b200q_probs``, S read) and ``b200q_collapse`` (S/2 read + S written)
   — CUDA-event timed on the launching stream, against MEASURED_PEAKS.json's HBM GB/s;
+* ``StateVector.reduced_dm`` (``b200q_gram_block``) for one, two and four kept wires;
 * one-shot throughput (shots/s) of a dynamic circuit at M qubits — an entangling prefix, four
   measurements with conditional gates, all-wire terminal sample — with the prefix simulated once
   (ours) and with the prefix re-simulated every shot (what the reference's loop does,
@@ -89,6 +90,13 @@ def main():
         sv.reset()
         for w in range(0, N, 3):
             sv.apply_operation(ops.Hadamard(w))
+    # reduced density matrices (b200q_gram_block): S per launch for m <= 2; m = 4 is 4 diagonal
+    # blocks over S/4 and 6 off-diagonal ones over S/2 = 4 S
+    for wires, nbytes in (([0], S), ([N - 1], S), ([0, N // 2], S), ([N - 2, N - 1], S),
+                          ([0, 1, N // 2, N - 1], 4 * S)):
+        t = _time(stream, lambda: sv.reduced_dm(wires), 3)
+        kernels["reduced_dm_wires_" + "_".join(map(str, wires))] = {
+            "bytes": nbytes, "ms": t * 1e3, "gbps": nbytes / t / 1e9, "frac": nbytes / t / 1e9 / peak}
     out["kernels"] = {"qubits": N, **kernels}
     del sv
     torch.cuda.empty_cache()
