@@ -34,7 +34,9 @@ from . import simulate as _sim
 from .device import adjoint_observables, adjoint_ops, stopping_condition
 
 _KIND = {"ExpectationMP": "expval", "VarianceMP": "var", "ProbabilityMP": "probs",
-         "SampleMP": "sample", "CountsMP": "counts", "StateMP": "state"}
+         "SampleMP": "sample", "CountsMP": "counts", "StateMP": "state",
+         "DensityMatrixMP": "density_matrix", "PurityMP": "purity", "VnEntropyMP": "vn_entropy",
+         "MutualInfoMP": "mutual_info"}
 
 
 class _MP:
@@ -48,6 +50,8 @@ class _MP:
             raise qml.DeviceError(f"Measurement {mp} is not supported on b200.qubit")
         self.obs = mp.obs
         self.mv = getattr(mp, "mv", None)     # sampled mid-circuit value of a one-shot tape
+        self.log_base = getattr(mp, "log_base", None)
+        self._wires = getattr(mp, "_wires", None)      # MutualInfoMP: the two subsystems
         self.wires = tuple(mp.wires)
 
     def diagonalizing_gates(self):

@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Target for ncu: the two sweeps of a native MidMeasure at N qubits (default 28), complex128 —
 the single-wire marginal (k_probs_marginal + split sum) and k_collapse — on a high, a middle and
-the lowest state bit; one launch each after a warm-up."""
+the lowest state bit, then the reduced-density-matrix kernel (k_gram_block) on two and three
+kept wires; one launch each after a warm-up."""
 import os
 import sys
 
@@ -20,5 +21,7 @@ for rep in range(2):
         p = sv.probs_device([wire])
         sv.collapse(wire, 0, False, 1.0)
         del p
+    sv.reduced_dm([0, n - 1])          # k_gram_block<MI=2, same>
+    sv.reduced_dm([3, 0, n - 1])       # + the off-diagonal block variant
 torch.cuda.synchronize()
 print("done")
