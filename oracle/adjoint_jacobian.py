@@ -42,6 +42,27 @@ def _op_param_layout(tape):
     return layout, idx
 
 
+def adjoint_jacobian_state(tape):                          # adjoint_jacobian.py:43-73
+    """Forward-mode Jacobian of the state itself: one derivative state per trainable parameter,
+    carried through the rest of the circuit."""
+    from .simulate import create_initial_state
+
+    ops = list(tape.operations)
+    has_prep = bool(ops) and hasattr(ops[0], "state_vector")
+    state = create_initial_state(tape.num_wires, ops[0] if has_prep else None)
+    jacobian = []
+    param_idx = int(has_prep)
+    for op in ops[has_prep:]:
+        jacobian = [apply_operation(op, jac) for jac in jacobian]
+        if len(op.data) == 1:
+            if param_idx in tape.trainable_params:
+                d_op_matrix = operation_derivative(op)
+                jacobian.append(apply_operation(_unitary(d_op_matrix, op.wires), state))
+            param_idx += 1
+        state = apply_operation(op, state)
+    return tuple(jac.flatten() for jac in jacobian)
+
+
 def adjoint_jacobian(tape, state):                         # adjoint_jacobian.py:77-149
     n = tape.num_wires
     ket = state

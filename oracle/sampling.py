@@ -109,7 +109,9 @@ def _group_measurements(mps):                  # sampling.py:46-98
         return [mps], [[0]]
     pauli, other, other_idx, no_obs, no_obs_idx = [], [], [], [], []
     for i, mp in enumerate(mps):
-        if mp.obs is None:
+        if mp.kind == "shadow":                                           # :68-70
+            other.append([mp]); other_idx.append([i])
+        elif mp.obs is None:
             no_obs.append(mp); no_obs_idx.append(i)
         elif _pauli_word_of(mp.obs) is not None and mp.obs.name not in ("LinearCombination", "Sum", "Hamiltonian"):
             pauli.append((i, mp))
@@ -178,6 +180,8 @@ def measure_with_samples(mps, state, shots, is_state_batched=False, rng=None,
         if mp0.kind == "expval" and mp0.obs is not None and mp0.obs.name in (
                 "LinearCombination", "Hamiltonian", "Sum"):
             all_res.extend(_measure_sum_with_samples(group, state, shots, is_state_batched, rng))
+        elif mp0.kind == "shadow":
+            all_res.extend(_measure_classical_shadow(group, state, shots, rng))
         else:
             all_res.extend(_measure_with_samples_diagonalizing_gates(
                 group, state, shots, is_state_batched, rng))
@@ -188,6 +192,59 @@ def measure_with_samples(mps, state, shots, is_state_batched=False, rng=None,
     if shots.has_partitioned_shots:
         sorted_res = tuple(zip(*sorted_res))
     return sorted_res
+
+
+def classical_shadow_process_state_with_shots(mp, state, shots, rng=None):
+    """measurements/classical_shadow.py:142-257 (``ClassicalShadowMP.process_state_with_shots``):
+    the same stacked-state einsum walk over the measured wires."""
+    from string import ascii_letters
+
+    mapped_wires = list(mp.wires)
+    n_qubits = len(mapped_wires)
+    num_dev_qubits = len(state.shape)
+    recipe_rng = np.random.RandomState(mp.seed)
+    recipes = recipe_rng.randint(0, 3, size=(shots, n_qubits))
+    bit_rng = np.random.default_rng(rng)
+    X = np.array([[0, 1], [1, 0]], dtype=complex)
+    Y = np.array([[0, -1j], [1j, 0]])
+    Z = np.array([[1, 0], [0, -1]], dtype=complex)
+    H = np.array([[1, 1], [1, -1]], dtype=complex) / np.sqrt(2)
+    rz = np.array([[np.exp(-0.5j * (-np.pi / 2)), 0], [0, np.exp(0.5j * (-np.pi / 2))]])
+    obs_list = np.stack([X, Y, Z])
+    diag_list = np.stack([H, H @ rz, np.eye(2, dtype=complex)])
+    obs = obs_list[recipes]
+    diagonalizers = diag_list[recipes]
+    unmeasured = [i for i in range(num_dev_qubits) if i not in mapped_wires]
+    transposed_state = np.transpose(state, axes=mapped_wires + unmeasured)
+    outcomes = np.zeros((shots, n_qubits))
+    stacked_state = np.repeat(transposed_state[np.newaxis, ...], shots, axis=0)
+    for active_qubit in range(n_qubits):
+        num_remaining = num_dev_qubits - active_qubit
+        conj_first = ascii_letters[num_remaining]
+        stacked_dim = ascii_letters[num_remaining + 1]
+        state_str = f"{stacked_dim}{ascii_letters[:num_remaining]}"
+        conj_state_str = f"{stacked_dim}{conj_first}{ascii_letters[1:num_remaining]}"
+        target_str = f"{stacked_dim}a{conj_first}"
+        first_qubit_state = np.einsum(f"{state_str},{conj_state_str}->{target_str}",
+                                      stacked_state, np.conj(stacked_state))
+        probs = (np.einsum("abc,acb->a", first_qubit_state, obs[:, active_qubit]) + 1) / 2
+        samples = bit_rng.random(size=probs.shape) > np.real(probs)
+        outcomes[:, active_qubit] = samples
+        rotated_state = np.einsum("ab...,acb->ac...", stacked_state, diagonalizers[:, active_qubit])
+        stacked_state = rotated_state[np.arange(shots), samples.astype(np.int8)]
+        sum_indices = tuple(range(1, num_remaining))
+        state_squared = np.abs(stacked_state) ** 2
+        norms = np.sqrt(np.sum(state_squared, sum_indices, keepdims=True))
+        stacked_state /= norms
+    return np.stack([outcomes, recipes]).astype(np.int8)
+
+
+def _measure_classical_shadow(mps, state, shots, rng):                       # sampling.py:338-374
+    mp = mps[0]
+    if shots.has_partitioned_shots:
+        return [tuple(classical_shadow_process_state_with_shots(mp, state, s, rng)
+                      for s, copies in shots.shot_vector for _ in range(copies))]
+    return [classical_shadow_process_state_with_shots(mp, state, shots.total_shots, rng)]
 
 
 def _measure_with_samples_diagonalizing_gates(mps, state, shots, is_state_batched, rng):  # :276-335

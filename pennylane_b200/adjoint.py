@@ -320,12 +320,45 @@ def _reverse_sweep(tape, sweep: _Sweep, n_rows_out: int):
     return vals, filled, trainable
 
 
+def _adjoint_jacobian_state(tape, dtype=np.complex128, device=None):
+    """adjoint_jacobian.py:43-73: the Jacobian of the STATE — one derivative statevector per
+    trainable parameter, each carried through the remaining gates.  Memory is
+    ``(1 + n_trainable) * S`` by construction (the reference holds the same list), so this is a
+    small-circuit tool; every sweep is a kernel call on a device-resident vector."""
+    from .statevector import StateVector
+
+    ops_ = list(tape.operations)
+    has_prep = bool(ops_) and hasattr(ops_[0], "state_vector")
+    n = tape.num_wires
+    state = StateVector(n, dtype=dtype, device=device)
+    if has_prep:
+        state.set_state(np.asarray(ops_[0].state_vector(wire_order=list(range(n)))))
+    jacobian = []
+    param_idx = int(has_prep)
+    trainable = set(tape.trainable_params)
+    for op in ops_[has_prep:]:
+        for jac in jacobian:
+            jac.apply_operation(op)
+        if len(op.data) == 1:
+            if param_idx in trainable:
+                d_op_matrix = _ops.operation_derivative(op)
+                new = state.clone()
+                new.apply_matrix(np.asarray(d_op_matrix), list(op.wires))
+                jacobian.append(new)
+            param_idx += 1
+        state.apply_operation(op)
+    return tuple(j.to_numpy().reshape(-1) for j in jacobian)
+
+
 def adjoint_jacobian(tape, dtype=np.complex128, device=None, return_state: bool = False,
                      fusion: int = 0):
     """adjoint_jacobian.py:77-149.  Runs the forward pass itself (directly into row 0 of the
     sweep buffer).  Returns the Jacobian in the reference's nested-tuple layout; with
     ``return_state`` also a ``StateVector`` copy of the final state taken before the sweep."""
     tape = tape.map_to_standard_wires()
+    if tape.measurements and tape.measurements[0].kind == "state":        # :110-111
+        jac = _adjoint_jacobian_state(tape, dtype, device)
+        return (jac, None) if return_state else jac
     obs = [m.obs for m in tape.measurements]
     if any(o is None for o in obs) or any(m.kind != "expval" for m in tape.measurements):
         raise ValueError("adjoint differentiation supports expectation values only")

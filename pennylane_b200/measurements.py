@@ -184,6 +184,20 @@ class MutualInfoMP(MeasurementProcess):
         return new
 
 
+class ClassicalShadowMP(MeasurementProcess):
+    """measurements/classical_shadow.py: random single-qubit Pauli measurements, one basis
+    choice per shot and wire; ``seed`` fixes the recipes (``np.random.RandomState(seed)``, :171)."""
+    kind = "shadow"
+
+    def __init__(self, wires, seed=None):
+        super().__init__(wires=wires)
+        self.seed = seed
+
+
+def classical_shadow(wires, seed=None):
+    return ClassicalShadowMP(wires, seed=seed)
+
+
 def density_matrix(wires):
     return DensityMatrixMP(wires=wires)
 

@@ -267,7 +267,9 @@ def _group_measurements(mps):
         return [list(mps)], [[0]]
     pauli, other, other_idx, no_obs, no_obs_idx = [], [], [], [], []
     for i, mp in enumerate(mps):
-        if mp.obs is None:
+        if mp.kind == "shadow":                        # sampling.py:68-70: a group of its own
+            other.append([mp]); other_idx.append([i])
+        elif mp.obs is None:
             no_obs.append(mp); no_obs_idx.append(i)
         elif _pauli_word_of(mp.obs) is not None:
             pauli.append((i, mp))
@@ -342,6 +344,57 @@ def _measure_sum(mps, sv, shots, rng, exact):
     return [unsq] if shots.has_partitioned_shots else [unsq[0]]
 
 
+_SHADOW_OBS = np.array([[[0, 1], [1, 0]], [[0, -1j], [1j, 0]], [[1, 0], [0, -1]]], dtype=complex)
+_H = np.array([[1, 1], [1, -1]], dtype=complex) / np.sqrt(2)
+# classical_shadow.py:185-191: H, H RZ(-pi/2), I
+_SHADOW_DIAG = np.stack([_H, _H @ np.diag([np.exp(0.25j * np.pi), np.exp(-0.25j * np.pi)]),
+                         np.eye(2, dtype=complex)])
+
+
+def _classical_shadow(mp, sv: StateVector, shots: int, rng):
+    """``ClassicalShadowMP.process_state_with_shots`` (measurements/classical_shadow.py:142-257).
+
+    The reference stacks ``shots`` copies of the state (``shots * S`` bytes) and walks the wires:
+    single-wire density matrix, expectation of the recipe's Pauli, ``bit_rng.random(shots) >
+    probs``, collapse, renormalise.  Here one device-resident copy is walked per shot: the
+    single-wire density matrix is ``b200q_gram_block`` restricted to the part of the state where
+    the wires measured so far are 0, and "rotate into the recipe's basis, keep the sampled row,
+    renormalise" is one controlled 2x2 sweep that parks the survivor in the wire's |0> half — so
+    every step touches half of what the step before did, like the reference's shrinking stack.
+    The uniforms are drawn in the reference's order (all shots of wire 0, then wire 1, ...)."""
+    wires = list(mp.wires)
+    nq = len(wires)
+    recipes = np.random.RandomState(mp.seed).randint(0, 3, size=(shots, nq))   # :171-172
+    bit_rng = np.random.default_rng(rng)
+    uniforms = np.stack([bit_rng.random(size=shots) for _ in range(nq)], axis=1)
+    outcomes = np.zeros((shots, nq))
+    work = sv.clone()
+    for t in range(shots):
+        if t:
+            work.data.copy_(sv.data)
+        done = []
+        for q, w in enumerate(wires):
+            r = recipes[t, q]
+            rho = work.reduced_dm([w], fixed_zero=done)
+            prob = (np.einsum("bc,cb->", rho, _SHADOW_OBS[r]) + 1) / 2            # :239
+            sample = int(uniforms[t, q] > prob.real)
+            outcomes[t, q] = sample
+            p_s = prob.real if sample == 0 else 1 - prob.real
+            row = _SHADOW_DIAG[r][sample] / np.sqrt(p_s)
+            ctrl = done[-16:]
+            work.apply_matrix(np.array([row, [0, 0]]), [w], ctrl, [0] * len(ctrl))
+            done.append(w)
+    return np.stack([outcomes, recipes]).astype(np.int8)
+
+
+def _measure_classical_shadow(mps, sv, shots, rng):
+    """sampling.py:338-374."""
+    mp = mps[0]
+    if shots.has_partitioned_shots:
+        return [tuple(_classical_shadow(mp, sv, s, rng) for s in shots)]
+    return [_classical_shadow(mp, sv, shots.total_shots, rng)]
+
+
 def measure_with_samples(mps, sv: StateVector, shots, rng, exact: bool = True,
                          mid_measurements=None):
     """sampling.py:205-273."""
@@ -356,6 +409,8 @@ def measure_with_samples(mps, sv: StateVector, shots, rng, exact: bool = True,
         if mp0.kind == "expval" and mp0.obs is not None and mp0.obs.name in (
                 "LinearCombination", "Hamiltonian", "Sum"):
             all_res.extend(_measure_sum(group, sv, shots, rng, exact))
+        elif mp0.kind == "shadow":
+            all_res.extend(_measure_classical_shadow(group, sv, shots, rng))
         else:
             all_res.extend(_measure_group(group, sv, shots, rng, exact))
     flat_indices = [i for idx in indices for i in idx]

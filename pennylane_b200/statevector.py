@@ -463,23 +463,27 @@ class StateVector:
                                    self.stream))
         return out
 
-    def reduced_dm(self, wires: Sequence[int]) -> np.ndarray:
+    def reduced_dm(self, wires: Sequence[int], fixed_zero: Sequence[int] = ()) -> np.ndarray:
         """Reduced density matrix over ``wires`` (in that order), complex128, shape
         ``(2^m, 2^m)`` or ``(batch, 2^m, 2^m)`` — ``reduce_statevector``
         (pennylane/math/quantum.py:386-487) without ever forming more than the result.
 
         The last two wires are the in-thread block of ``b200q_gram_block``; the others are
         enumerated here as (row, column >= row) outer assignments, the lower triangle follows
-        from Hermiticity."""
+        from Hermiticity.  ``fixed_zero``: wires known to be |0> (already measured and reset);
+        only the 2^-len(fixed_zero) of the state where they are 0 is read."""
         torch = _torch()
         wires = list(wires)
         m = len(wires)
-        if len(set(wires)) != m or any(w < 0 or w >= self.n for w in wires):
-            raise ValueError(f"reduced_dm: bad wires {wires}")
+        fixed = list(fixed_zero)
+        if len(set(wires + fixed)) != m + len(fixed) or any(w < 0 or w >= self.n for w in wires + fixed):
+            raise ValueError(f"reduced_dm: bad wires {wires} / {fixed}")
         mi = min(m, 2)
         mo = m - mi
         outer, inner = wires[:mo], wires[mo:]
-        ib, ob = int_array(self.bits(inner)), int_array(self.bits(outer))
+        # fixed wires are the most significant outer bits: assignments below 2^mo leave them 0
+        ib, ob = int_array(self.bits(inner)), int_array(self.bits(fixed + outer))
+        n_outer = mo + len(fixed)
         D = 1 << mi
         pairs = [(a, b) for a in range(1 << mo) for b in range(a, 1 << mo)]
         out = torch.empty((self.batch, len(pairs), 2 * D * D), dtype=torch.float64,
@@ -490,7 +494,7 @@ class StateVector:
             base = self.data.data_ptr() + bi * (esz << self.n)
             for k, (a, b) in enumerate(pairs):
                 check(self.lib.b200q_gram_block(
-                    C.c_void_p(base), self.n, self.dtype_code, ib, mi, ob, mo, a, b,
+                    C.c_void_p(base), self.n, self.dtype_code, ib, mi, ob, n_outer, a, b,
                     C.c_void_p(out[bi, k].data_ptr()), w, wb, self.stream))
         blocks = out.cpu().numpy().reshape(self.batch, len(pairs), D, D, 2)
         blocks = blocks[..., 0] + 1j * blocks[..., 1]

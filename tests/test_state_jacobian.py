@@ -1,0 +1,59 @@
+"""``_adjoint_jacobian_state`` (adjoint_jacobian.py:43-73): the Jacobian of the state itself.
+Known answers: tests/devices/qubit/test_adjoint_jacobian.py:316-345."""
+import numpy as np
+import pytest
+
+from pennylane_b200 import QuantumScript, measurements as M, ops
+
+X, Y = 0.5, 0.6
+C_X, S_X, C_Y, S_Y = np.cos(X / 2), np.sin(X / 2), np.cos(Y / 2), np.sin(Y / 2)
+X_JAC = np.array([-0.5 * C_Y * S_X, -0.5 * S_Y * S_X, -0.5j * S_Y * C_X, -0.5j * C_X * C_Y])
+Y_JAC = np.array([-0.5 * C_X * S_Y, 0.5 * C_X * C_Y, -0.5j * S_X * C_Y, 0.5j * S_X * S_Y])
+
+
+def _tapes():
+    one = QuantumScript([ops.RX(1.2, wires=0)], [M.state()])
+    two = QuantumScript([ops.RX(X, wires=0), ops.RY(Y, wires=1), ops.CNOT(wires=[0, 1])], [M.state()])
+    return one, two
+
+
+def _layered(n=6, seed=0):
+    rng = np.random.default_rng(seed)
+    gates = [ops.StatePrep(np.eye(2 ** n)[3], wires=list(range(n)))]
+    for _ in range(2):
+        gates += [ops.RY(rng.uniform(0, 6), wires=w) for w in range(n)]
+        gates += [ops.IsingXX(rng.uniform(0, 6), wires=[w, (w + 1) % n]) for w in range(0, n, 2)]
+        gates += [ops.CNOT(wires=[w, (w + 1) % n]) for w in range(n)]
+        gates.append(ops.Rot(0.1, 0.2, 0.3, wires=0))         # three parameters: never differentiated
+    tape = QuantumScript(gates, [M.state()])
+    tape.trainable_params = [1, 2, 5, 7, 8, 13, 16]
+    return tape
+
+
+def test_oracle_known_answers():
+    from oracle.adjoint_jacobian import adjoint_jacobian_state
+
+    one, two = _tapes()
+    (jac,) = adjoint_jacobian_state(one)
+    assert np.allclose(jac, [-0.5 * np.sin(0.6), -0.5j * np.cos(0.6)])
+    x_jac, y_jac = adjoint_jacobian_state(two)
+    assert np.allclose(x_jac, X_JAC) and np.allclose(y_jac, Y_JAC)
+
+
+@pytest.mark.gpu
+def test_device_known_answers_and_oracle_parity():
+    from oracle.adjoint_jacobian import adjoint_jacobian_state
+    from pennylane_b200.adjoint import adjoint_jacobian
+
+    one, two = _tapes()
+    (jac,) = adjoint_jacobian(one)
+    assert np.allclose(jac, [-0.5 * np.sin(0.6), -0.5j * np.cos(0.6)])
+    x_jac, y_jac = adjoint_jacobian(two)
+    assert np.allclose(x_jac, X_JAC) and np.allclose(y_jac, Y_JAC)
+    tape = _layered()
+    got, ref = adjoint_jacobian(tape), adjoint_jacobian_state(tape)
+    assert len(got) == len(ref) == 7
+    for g, r in zip(got, ref):
+        assert g.shape == (64,) and np.max(np.abs(g - r)) < 1e-12
+    got32 = adjoint_jacobian(tape, dtype=np.complex64)
+    assert max(np.max(np.abs(g - r)) for g, r in zip(got32, ref)) < 1e-5
