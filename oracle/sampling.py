@@ -109,7 +109,7 @@ def _group_measurements(mps):                  # sampling.py:46-98
         return [mps], [[0]]
     pauli, other, other_idx, no_obs, no_obs_idx = [], [], [], [], []
     for i, mp in enumerate(mps):
-        if mp.kind == "shadow":                                           # :68-70
+        if mp.kind in ("shadow", "shadow_expval"):                        # :68-70
             other.append([mp]); other_idx.append([i])
         elif mp.obs is None:
             no_obs.append(mp); no_obs_idx.append(i)
@@ -180,7 +180,7 @@ def measure_with_samples(mps, state, shots, is_state_batched=False, rng=None,
         if mp0.kind == "expval" and mp0.obs is not None and mp0.obs.name in (
                 "LinearCombination", "Hamiltonian", "Sum"):
             all_res.extend(_measure_sum_with_samples(group, state, shots, is_state_batched, rng))
-        elif mp0.kind == "shadow":
+        elif mp0.kind in ("shadow", "shadow_expval"):
             all_res.extend(_measure_classical_shadow(group, state, shots, rng))
         else:
             all_res.extend(_measure_with_samples_diagonalizing_gates(
@@ -239,8 +239,64 @@ def classical_shadow_process_state_with_shots(mp, state, shots, rng=None):
     return np.stack([outcomes, recipes]).astype(np.int8)
 
 
+def _median_of_means(arr, num_batches, axis=0):            # shadows/classical_shadow.py:466-486
+    batch_size = int(np.ceil(arr.shape[0] / num_batches))
+    means = [np.mean(arr[i * batch_size: (i + 1) * batch_size], 0) for i in range(num_batches)]
+    return np.median(means, axis=axis)
+
+
+def _pauli_expval(bits, recipes, word):                    # shadows/classical_shadow.py:489-547
+    T, n = recipes.shape
+    b = word.shape[0]
+    bits, recipes = bits.astype(np.int64), recipes.astype(np.int64)
+    id_mask = word == -1
+    indices = np.equal(np.reshape(recipes, (T, 1, n)), np.reshape(word, (1, b, n)))
+    indices = np.logical_or(indices, np.tile(np.reshape(id_mask, (1, b, n)), (T, 1, 1)))
+    indices = np.all(indices, axis=2)
+    bits = np.where(id_mask, 0, np.tile(np.expand_dims(bits, 1), (1, b, 1)))
+    bits = np.sum(bits, axis=2) % 2
+    expvals = np.where(indices, 1 - 2 * bits, 0) * 3 ** np.count_nonzero(
+        np.logical_not(id_mask), axis=1)
+    return expvals.astype(np.float64)
+
+
+def shadow_expval_process_state_with_shots(mp, state, shots, rng=None):
+    """measurements/classical_shadow.py:490-514 with ``ClassicalShadow.expval``
+    (shadows/classical_shadow.py:238-250, 283-344)."""
+    from types import SimpleNamespace
+
+    wire_map = list(mp.wires)
+    bits, recipes = classical_shadow_process_state_with_shots(
+        SimpleNamespace(wires=mp.wires, seed=mp.seed), state, shots, rng=rng)
+    Hs = list(mp.H) if isinstance(mp.H, (list, tuple)) else [mp.H]
+    to_recipe = {"X": 0, "Y": 1, "Z": 2, "I": -1}
+    coeffs_and_words = []
+    for h in Hs:
+        cw = []
+        for pw, c in h.pauli_rep.items():
+            word = [-1] * bits.shape[1]
+            for i, ch in pw.items():
+                word[wire_map.index(i)] = to_recipe[ch]
+            cw.append((c, word))
+        coeffs_and_words.append(cw)
+    expvals = _pauli_expval(bits, recipes,
+                            np.array([word for cw in coeffs_and_words for _, word in cw]))
+    expvals = _median_of_means(expvals, mp.k, axis=0)
+    expvals = expvals * np.array([np.real(c) for cw in coeffs_and_words for c, _ in cw])
+    start, results = 0, []
+    for cw in coeffs_and_words:
+        results.append(np.sum(expvals[start: start + len(cw)]))
+        start += len(cw)
+    return np.squeeze(results)
+
+
 def _measure_classical_shadow(mps, state, shots, rng):                       # sampling.py:338-374
     mp = mps[0]
+    if mp.kind == "shadow_expval":
+        if shots.has_partitioned_shots:
+            return [tuple(shadow_expval_process_state_with_shots(mp, state, s, rng)
+                          for s, copies in shots.shot_vector for _ in range(copies))]
+        return [shadow_expval_process_state_with_shots(mp, state, shots.total_shots, rng)]
     if shots.has_partitioned_shots:
         return [tuple(classical_shadow_process_state_with_shots(mp, state, s, rng)
                       for s, copies in shots.shot_vector for _ in range(copies))]

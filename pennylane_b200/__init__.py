@@ -10,8 +10,8 @@ from . import mcm, measurements, one_shot, ops, pauli
 from ._lib import B200QError, LIB_PATH
 from .device import B200Qubit, DeviceError, ExecutionConfig, QuantumFunctionError, device
 from .mcm import cond, measure
-from .measurements import (counts, density_matrix, expval, mutual_info, probs, purity, sample,
-                           state, var, vn_entropy)
+from .measurements import (classical_shadow, counts, density_matrix, expval, mutual_info, probs, purity, sample,
+                           shadow_expval, state, var, vn_entropy)
 from .statevector import StateVector
 from .tape import QuantumScript, QuantumTape, Shots
 
@@ -22,5 +22,5 @@ __all__ = [
     "QuantumScript", "QuantumTape", "Shots", "ops", "measurements", "pauli", "mcm", "one_shot",
     "measure", "cond",
     "expval", "var", "probs", "sample", "counts", "state", "density_matrix", "purity",
-    "vn_entropy", "mutual_info", "B200QError", "LIB_PATH",
+    "vn_entropy", "mutual_info", "classical_shadow", "shadow_expval", "B200QError", "LIB_PATH",
 ]

@@ -300,7 +300,7 @@ class B200Qubit:
             if tape.shots and m.kind in ("state", "density_matrix", "purity", "vn_entropy",
                                          "mutual_info"):
                 raise DeviceError(f"Measurement {m} not accepted with finite shots on {self.name}")
-            if not tape.shots and m.kind in ("sample", "counts", "shadow"):
+            if not tape.shots and m.kind in ("sample", "counts", "shadow", "shadow_expval"):
                 raise DeviceError(f"Measurement {m} not accepted for analytic simulation on "
                                   f"{self.name}.")
 

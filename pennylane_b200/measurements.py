@@ -194,6 +194,30 @@ class ClassicalShadowMP(MeasurementProcess):
         self.seed = seed
 
 
+class ShadowExpvalMP(MeasurementProcess):
+    """measurements/classical_shadow.py:400-514: expectation value(s) of ``H`` estimated from a
+    classical shadow taken on the wires of ``H``; ``k`` = median-of-means batches."""
+    kind = "shadow_expval"
+
+    def __init__(self, H, seed=None, k=1):
+        hs = list(H) if isinstance(H, (list, tuple)) else [H]
+        wires = []
+        for h in hs:
+            wires += [w for w in h.wires if w not in wires]
+        super().__init__(wires=wires)
+        self.H, self.seed, self.k = H, seed, k
+
+    def map_wires(self, wire_map):
+        new = super().map_wires(wire_map)
+        new.H = [h.map_wires(wire_map) for h in self.H] if isinstance(self.H, (list, tuple)) \
+            else self.H.map_wires(wire_map)
+        return new
+
+
+def shadow_expval(H, k=1, seed=None):
+    return ShadowExpvalMP(H, seed=seed, k=k)
+
+
 def classical_shadow(wires, seed=None):
     return ClassicalShadowMP(wires, seed=seed)
 

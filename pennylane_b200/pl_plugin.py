@@ -36,7 +36,8 @@ from .device import adjoint_observables, adjoint_ops, stopping_condition
 _KIND = {"ExpectationMP": "expval", "VarianceMP": "var", "ProbabilityMP": "probs",
          "SampleMP": "sample", "CountsMP": "counts", "StateMP": "state",
          "DensityMatrixMP": "density_matrix", "PurityMP": "purity", "VnEntropyMP": "vn_entropy",
-         "MutualInfoMP": "mutual_info"}
+         "MutualInfoMP": "mutual_info", "ClassicalShadowMP": "shadow",
+         "ShadowExpvalMP": "shadow_expval"}
 
 
 class _MP:
@@ -51,6 +52,7 @@ class _MP:
         self.obs = mp.obs
         self.mv = getattr(mp, "mv", None)     # sampled mid-circuit value of a one-shot tape
         self.log_base = getattr(mp, "log_base", None)
+        self.seed, self.H, self.k = (getattr(mp, a, None) for a in ("seed", "H", "k"))
         self._wires = getattr(mp, "_wires", None)      # MutualInfoMP: the two subsystems
         self.wires = tuple(mp.wires)
 

@@ -267,7 +267,7 @@ def _group_measurements(mps):
         return [list(mps)], [[0]]
     pauli, other, other_idx, no_obs, no_obs_idx = [], [], [], [], []
     for i, mp in enumerate(mps):
-        if mp.kind == "shadow":                        # sampling.py:68-70: a group of its own
+        if mp.kind in ("shadow", "shadow_expval"):     # sampling.py:68-70: a group of its own
             other.append([mp]); other_idx.append([i])
         elif mp.obs is None:
             no_obs.append(mp); no_obs_idx.append(i)
@@ -387,12 +387,22 @@ def _classical_shadow(mp, sv: StateVector, shots: int, rng):
     return np.stack([outcomes, recipes]).astype(np.int8)
 
 
+def _shadow_expval(mp, sv: StateVector, shots: int, rng):
+    """``ShadowExpvalMP.process_state_with_shots`` (measurements/classical_shadow.py:490-514):
+    a shadow on the observable's wires, then the host estimator."""
+    from .shadows import shadow_expval
+
+    bits, recipes = _classical_shadow(mp, sv, shots, rng)
+    return shadow_expval(bits, recipes, mp.H, mp.k, wire_map=list(mp.wires))
+
+
 def _measure_classical_shadow(mps, sv, shots, rng):
     """sampling.py:338-374."""
     mp = mps[0]
+    fn = _shadow_expval if mp.kind == "shadow_expval" else _classical_shadow
     if shots.has_partitioned_shots:
-        return [tuple(_classical_shadow(mp, sv, s, rng) for s in shots)]
-    return [_classical_shadow(mp, sv, shots.total_shots, rng)]
+        return [tuple(fn(mp, sv, s, rng) for s in shots)]
+    return [fn(mp, sv, shots.total_shots, rng)]
 
 
 def measure_with_samples(mps, sv: StateVector, shots, rng, exact: bool = True,
@@ -409,7 +419,7 @@ def measure_with_samples(mps, sv: StateVector, shots, rng, exact: bool = True,
         if mp0.kind == "expval" and mp0.obs is not None and mp0.obs.name in (
                 "LinearCombination", "Hamiltonian", "Sum"):
             all_res.extend(_measure_sum(group, sv, shots, rng, exact))
-        elif mp0.kind == "shadow":
+        elif mp0.kind in ("shadow", "shadow_expval"):
             all_res.extend(_measure_classical_shadow(group, sv, shots, rng))
         else:
             all_res.extend(_measure_group(group, sv, shots, rng, exact))

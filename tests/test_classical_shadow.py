@@ -69,3 +69,45 @@ def test_device_shot_vector_and_many_wires():
     for t in range(20):
         if z[t].any():
             assert len(set(bits[t][z[t]])) == 1
+
+
+def _bell_tape(shots, k=1):
+    H = [ops.PauliZ(0) @ ops.PauliZ(1), ops.PauliX(0) @ ops.PauliX(1),
+         0.5 * (ops.PauliY(0) @ ops.PauliY(1)) + 2.0 * ops.PauliZ(2)]
+    gates = [ops.Hadamard(0), ops.CNOT(wires=[0, 1]), ops.RY(0.4, wires=2)]
+    return QuantumScript(gates, [M.shadow_expval(H, k=k, seed=13)], shots=shots)
+
+
+def test_shadow_expval_oracle_estimates_bell_state():
+    """Bell pair: <ZZ> = <XX> = 1, <YY> = -1 (tests/measurements/test_classical_shadow.py,
+    ``TestExpvalForward``: estimates within the shadow's statistical error)."""
+    from oracle.simulate import simulate as oracle_simulate
+
+    res = oracle_simulate(_bell_tape(4000), rng=np.random.default_rng(1))
+    assert np.allclose(res, [1.0, 1.0, -0.5 + 2.0 * np.cos(0.4)], atol=0.2)
+    res5 = oracle_simulate(_bell_tape(4000, k=5), rng=np.random.default_rng(1))
+    assert np.allclose(res5, [1.0, 1.0, -0.5 + 2.0 * np.cos(0.4)], atol=0.3)
+
+
+def test_host_estimator_equals_oracle_estimator():
+    from oracle.sampling import _median_of_means, _pauli_expval
+    from pennylane_b200.shadows import median_of_means, pauli_expval
+
+    rng = np.random.default_rng(0)
+    bits, recipes = rng.integers(0, 2, (50, 4)), rng.integers(0, 3, (50, 4))
+    words = np.array([[0, -1, 2, 1], [-1, -1, -1, 2], [2, 2, 2, 2]])
+    a, b = pauli_expval(bits, recipes, words), _pauli_expval(bits, recipes, words)
+    assert np.array_equal(a, b) and a.shape == (50, 3)
+    assert np.array_equal(median_of_means(a, 3), _median_of_means(b, 3))
+
+
+@pytest.mark.gpu
+def test_device_shadow_expval_equals_oracle():
+    from oracle.simulate import simulate as oracle_simulate
+    from pennylane_b200.simulate import simulate
+
+    for k in (1, 4):
+        got = simulate(_bell_tape(500, k), rng=np.random.default_rng(3))
+        ref = oracle_simulate(_bell_tape(500, k), rng=np.random.default_rng(3))
+        assert np.array_equal(got, ref)
+    assert np.allclose(got, [1.0, 1.0, -0.5 + 2.0 * np.cos(0.4)], atol=0.5)
