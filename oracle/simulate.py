@@ -29,6 +29,47 @@ def _op_batch(op):
     return bs
 
 
+class _FlexShots:                                           # simulate.py:104-117
+    def __init__(self, shots):
+        self.shot_vector = [(int(s), 1) for s in shots]
+        self.total_shots = sum(int(s) for s in shots)
+        self.has_partitioned_shots = len(self.shot_vector) > 1
+
+    def __bool__(self):
+        return True
+
+    def __iter__(self):
+        return iter(s for s, _ in self.shot_vector)
+
+
+def _postselection_postprocess(state, is_state_batched, shots, rng=None, postselect_mode=None):
+    """simulate.py:120-171."""
+    if is_state_batched:
+        raise ValueError("Cannot postselect on circuits with broadcasting.")
+    norm = np.linalg.norm(state)
+    if np.allclose(norm, 0.0):
+        if postselect_mode == "fill-shots" and shots:
+            raise RuntimeError("The probability of the postselected mid-circuit measurement "
+                               "outcome is 0.")
+        norm = 0.0
+    if shots:
+        binomial_fn = np.random.binomial if rng is None else rng.binomial
+        postselected = (list(shots) if postselect_mode == "fill-shots"
+                        else [int(binomial_fn(s, float(norm ** 2))) for s in shots])
+        shots = _FlexShots(postselected)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        state = state / norm
+    return state, shots
+
+
+class _ShotsView:
+    def __init__(self, circuit, shots):
+        self._c, self.shots = circuit, shots
+
+    def __getattr__(self, name):
+        return getattr(self._c, name)
+
+
 def get_final_state(circuit, mid_measurements=None, rng=None, debugger=None):   # simulate.py:174-242
     ops = list(circuit.operations)
     prep = ops[0] if ops and _is_prep(ops[0]) else None
@@ -39,6 +80,10 @@ def get_final_state(circuit, mid_measurements=None, rng=None, debugger=None):   
         state = apply_operation(op, state, is_state_batched=is_state_batched,
                                 mid_measurements=mid_measurements, rng=rng, debugger=debugger,
                                 tape_shots=circuit.shots)
+        if op.name == "Projector":                          # simulate.py:226-232
+            state, new_shots = _postselection_postprocess(state, is_state_batched, circuit.shots,
+                                                          rng=rng)
+            circuit._postselected_shots = new_shots
         is_state_batched = is_state_batched or (_op_batch(op) is not None)
     for _ in range(circuit.num_wires - len(op_wires)):
         state = np.stack([state, np.zeros_like(state)], axis=-1)
@@ -80,5 +125,10 @@ def simulate(circuit, rng=None, debugger=None):             # simulate.py:308-39
         aux_circ = circuit.copy(shots=[1])
         return tuple(simulate_one_shot_native_mcm(aux_circ, rng=rng, debugger=debugger)
                      for _ in range(circuit.shots.total_shots))
+    if circuit.shots and any(op.name == "Projector" for op in circuit.operations):
+        rng = np.random.default_rng(rng)
+    circuit = _ShotsView(circuit, circuit.shots)
     state, is_state_batched = get_final_state(circuit, rng=rng, debugger=debugger)
+    if getattr(circuit, "_postselected_shots", None) is not None:
+        circuit.shots = circuit._postselected_shots         # circuit._shots = new_shots, :232
     return measure_final_state(circuit, state, is_state_batched, rng=rng)

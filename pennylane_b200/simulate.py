@@ -84,8 +84,36 @@ def apply_snapshot(op, sv: StateVector, debugger, tape_shots=None, rng=None, exa
         snaps[tag] = [snaps[tag], snapshot]
 
 
+def _postselection_postprocess(sv: StateVector, shots, rng=None, postselect_mode=None):
+    """simulate.py:120-171: after a projector, renormalise and thin the shot budget out with
+    ``binomial(shots, |P psi|^2)`` (``hw-like``; ``fill-shots`` keeps it).  A zero norm gives a
+    NaN state, as the reference's division does."""
+    from .tape import FlexShots
+
+    if sv.batch > 1:
+        raise ValueError(
+            "Cannot postselect on circuits with broadcasting. Use the "
+            "qp.transforms.broadcast_expand transform to split a broadcasted "
+            "tape into multiple non-broadcasted tapes before executing if "
+            "postselection is used.")
+    norm = float(np.sqrt(sv.norm2()))
+    if np.allclose(norm, 0.0):
+        if postselect_mode == "fill-shots" and shots:
+            raise RuntimeError(
+                "The probability of the postselected mid-circuit measurement outcome is 0. "
+                "This leads to invalid results when using postselect_mode='fill-shots'.")
+        norm = 0.0
+    if shots:
+        binomial = np.random.binomial if rng is None else rng.binomial
+        shots = FlexShots(list(shots) if postselect_mode == "fill-shots"
+                          else [int(binomial(s, float(norm ** 2))) for s in shots])
+    with np.errstate(divide="ignore", invalid="ignore"):
+        sv.scale(np.complex128(np.float64(1.0) / np.float64(norm)) if norm else np.nan)
+    return shots
+
+
 def apply_gates(sv: StateVector, gates, fusion: int = 0, mid_measurements=None, rng=None,
-                debugger=None, tape_shots=None, exact: bool = True):
+                debugger=None, tape_shots=None, exact: bool = True, postselect_mode=None):
     """The gate loop of simulate.py:213-235.  Mid-circuit measurements split the gate list:
     the unitary runs between them go through the fused path (or gate by gate), a ``MidMeasure``
     is one probs sweep + one collapse sweep, and a ``Conditional`` is decided on the host from
@@ -115,6 +143,14 @@ def apply_gates(sv: StateVector, gates, fusion: int = 0, mid_measurements=None, 
             if debugger is not None and debugger.active:
                 flush()
                 apply_snapshot(op, sv, debugger, tape_shots, rng, exact)
+        elif op.name == "Projector":
+            # postselection on a mid-circuit measurement, simulate.py:226-232
+            if getattr(op, "batch_size", None) is not None:
+                raise ValueError("Cannot postselect on circuits with broadcasting.")
+            run.append(op)
+            flush()
+            tape_shots = _postselection_postprocess(sv, tape_shots, rng, postselect_mode)
+            sv.postselected_shots = tape_shots
         else:
             run.append(op)
     flush()
@@ -524,8 +560,12 @@ def simulate(circuit, rng=None, dtype=np.complex128, device=None, exact_sampling
         return _simulate_native_mcm(circuit, rng, dtype, device, exact_sampling, fusion, debugger)
     if debugger is not None and debugger.active and circuit.shots:
         rng = np.random.default_rng(rng)        # snapshots and final sampling share one stream
+    if circuit.shots and any(op.name == "Projector" for op in circuit.operations):
+        rng = np.random.default_rng(rng)        # the shot thinning and the sampling share a stream
     sv, batched = get_final_state(circuit, dtype=dtype, device=device, fusion=fusion, rng=rng,
                                   debugger=debugger, exact_sampling=exact_sampling)
+    if getattr(sv, "postselected_shots", None) is not None:
+        circuit = _OneShotView(circuit, sv.postselected_shots)     # circuit._shots = new_shots, :232
     if state_cache is not None:
         state_cache[circuit.hash] = sv
     return measure_final_state(circuit, sv, batched, rng=rng, exact_sampling=exact_sampling)

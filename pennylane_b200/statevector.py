@@ -570,6 +570,9 @@ class StateVector:
         torch = _torch()
         wires = list(range(self.n)) if wires is None else list(wires)
         m = len(wires)
+        if shots == 0:                      # every shot postselected away (simulate.py:159-167)
+            empty = np.zeros((0, m), dtype=np.int64)
+            return np.stack([empty] * self.batch) if self.batch > 1 else empty
         probs = self.probs_device(wires)
         outs = []
         need = ((1 << m) // 128 + (1 << m) // (128 * 2047) + 128) * 8 + (4 << 20)

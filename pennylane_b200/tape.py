@@ -80,6 +80,25 @@ class Shots:
                 lower += s
 
 
+class FlexShots(Shots):
+    """``_FlexShots`` (devices/qubit/simulate.py:104-117): shots that may be zero — what is left of
+    a shot budget after a postselecting projector (``_postselection_postprocess`` :159-167)."""
+
+    def __init__(self, shots=None):
+        if isinstance(shots, (int, np.integer)):
+            vec = [ShotCopies(int(shots), 1)]
+        else:
+            vec = []
+            for s in shots:
+                n, c = (int(s[0]), int(s[1])) if isinstance(s, (tuple, list)) else (int(s), 1)
+                if vec and vec[-1].shots == n:
+                    vec[-1] = ShotCopies(n, vec[-1].copies + c)
+                else:
+                    vec.append(ShotCopies(n, c))
+        self.shot_vector = tuple(vec)
+        self.total_shots = sum(s * c for s, c in vec)
+
+
 class QuantumScript:
     """An executable circuit: operations, measurements, shots, trainable parameter indices."""
 
