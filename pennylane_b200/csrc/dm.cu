@@ -17,7 +17,8 @@
 // the block in 2 * 4^mi FP64 registers.  Deterministic: grid-stride partial per thread, fixed
 // xor-tree per CTA, CTAs added in index order by a second kernel.
 // Algorithmic bytes per launch: S / 2^mo when A == B, 2 S / 2^mo otherwise; m <= 2 is one
-// launch over S.  The host fills the lower triangle by Hermiticity.
+// launch over S.  Diagonal blocks (A == B) accumulate their upper triangle only (real diagonal);
+// the host fills every lower triangle by Hermiticity.
 #include "common.cuh"
 #include "../../include/b200q.h"
 
@@ -72,8 +73,10 @@ k_gram_block(const cx<T>* __restrict__ st, double* __restrict__ partials, const 
     for (int i = 0; i < D; ++i)
 #pragma unroll
       for (int j = 0; j < D; ++j) {
+        if (SAME && j < i) continue;      // a diagonal block is Hermitian: upper triangle only
         // a_i * conj(b_j)
         gr[i][j] = fma(ar[i], br[j], gr[i][j]); gr[i][j] = fma(ai[i], bi[j], gr[i][j]);
+        if (SAME && j == i) continue;     // real diagonal
         gi[i][j] = fma(ai[i], br[j], gi[i][j]); gi[i][j] = fma(-ar[i], bi[j], gi[i][j]);
       }
   }
@@ -82,8 +85,10 @@ k_gram_block(const cx<T>* __restrict__ st, double* __restrict__ partials, const 
   for (int i = 0; i < D; ++i)
 #pragma unroll
     for (int j = 0; j < D; ++j) {
-      const double sr = block_sum(gr[i][j], sh);
-      const double si = block_sum(gi[i][j], sh);
+      // (SAME, j < i) entries were never accumulated: they stay 0 and the host mirrors the
+      // upper triangle
+      const double sr = (SAME && j < i) ? 0.0 : block_sum(gr[i][j], sh);
+      const double si = (SAME && j <= i) ? 0.0 : block_sum(gi[i][j], sh);
       if (threadIdx.x == 0) {
         partials[(size_t)(2 * (i * D + j)) * gridDim.x + blockIdx.x] = sr;
         partials[(size_t)(2 * (i * D + j) + 1) * gridDim.x + blockIdx.x] = si;

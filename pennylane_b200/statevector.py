@@ -501,9 +501,10 @@ class StateVector:
         rho = np.empty((self.batch, 1 << mo, D, 1 << mo, D), dtype=np.complex128)
         for k, (a, b) in enumerate(pairs):
             if a == b:
-                # a diagonal block is Hermitian up to the rounding of its fused multiply-adds:
-                # symmetrise, so the result is exactly Hermitian with a real diagonal
-                blocks[:, k] = 0.5 * (blocks[:, k] + np.conj(np.swapaxes(blocks[:, k], -1, -2)))
+                # the kernel accumulates only the upper triangle of a diagonal block (with a real
+                # diagonal): mirror it, so the result is exactly Hermitian
+                up = np.triu(blocks[:, k], 1)
+                blocks[:, k] = np.triu(blocks[:, k]) + np.conj(np.swapaxes(up, -1, -2))
             rho[:, a, :, b, :] = blocks[:, k]
             if a != b:
                 rho[:, b, :, a, :] = np.conj(np.swapaxes(blocks[:, k], -1, -2))
