@@ -498,15 +498,31 @@ def simulate_one_shot_native_mcm(circuit, sv: StateVector, gates, rng, exact_sam
                                mid_measurements=mid_measurements)
 
 
-def _simulate_native_mcm(circuit, rng, dtype, device, exact_sampling, fusion, debugger=None):
+class _Branch:
+    """A node of the outcome tree: the state reached by one sequence of mid-circuit outcomes,
+    parked in front of the next ``MidMeasure`` (or final), and that measurement's marginal."""
+    __slots__ = ("state", "p", "children")
+
+    def __init__(self, state, p=None):
+        self.state, self.p, self.children = state, p, {}
+
+
+def _simulate_native_mcm(circuit, rng, dtype, device, exact_sampling, fusion, debugger=None,
+                         cache_fraction: float = 0.5):
     """The one-shot loop of simulate.py:356-381 (``mcm_method="one-shot"``): every shot re-runs
     the tape with ``shots=[1]`` and returns its own result tuple; ``dynamic_one_shot``'s
     post-processing (above the device boundary) combines them.
 
-    The reference re-simulates the whole tape per shot.  Everything in front of the first
-    ``MidMeasure`` is shot-independent, so it is simulated ONCE here and each shot starts from a
-    device-to-device copy of that state; the random stream is consumed in the same order (the
-    prefix draws nothing)."""
+    The reference re-simulates the whole tape per shot.  Here
+    * everything in front of the first ``MidMeasure`` is shot-independent and simulated ONCE;
+    * the state a shot reaches depends only on its outcomes so far, so collapsed branch states
+      stay resident in HBM in a tree keyed by outcome (up to ``cache_fraction`` of the free
+      memory; beyond that a shot continues in a scratch buffer).  A shot whose branch is cached
+      costs its ``binomial`` draws on cached marginals plus the terminal sampling.
+    The host Generator is consumed exactly as in the reference's loop — one ``binomial`` per
+    measurement in tape order, then the terminal draws — so per-shot results are bit-identical
+    to the oracle's under the same seed (this is the one-shot method's stream, not
+    tree-traversal's, which the reference samples differently)."""
     if not circuit.shots:
         raise TypeError("Native mid-circuit measurements are only supported with finite shots.")
     from .tape import Shots
@@ -521,14 +537,66 @@ def _simulate_native_mcm(circuit, rng, dtype, device, exact_sampling, fusion, de
         raise ValueError("MidMeasure cannot be applied to batched states.")
     rest = ops_[first:]
     aux = _OneShotView(circuit, Shots([1]))
-    work = base.clone()
+    n_shots = circuit.shots.total_shots
     results = []
-    for i in range(circuit.shots.total_shots):
-        if i:
-            work.data.copy_(base.data)
-        results.append(simulate_one_shot_native_mcm(aux, work, rest, rng, exact_sampling, fusion,
-                                                    debugger))
+    if snap or any(op.name == "Projector" for op in rest) or cache_fraction <= 0:
+        # side effects per shot (snapshots, shot thinning): plain loop from the prefix state
+        work = base.clone()
+        for i in range(n_shots):
+            if i:
+                work.data.copy_(base.data)
+            results.append(simulate_one_shot_native_mcm(aux, work, rest, rng, exact_sampling,
+                                                        fusion, debugger))
+        return tuple(results)
+
+    mcms, segs = [], []
+    for op in rest:                                        # rest starts with a MidMeasure
+        if is_mcm(op):
+            mcms.append(op)
+            segs.append([])
+        else:
+            segs[-1].append(op)
+    state_bytes = base.data.numel() * base.data.element_size()
+    budget = max(0, int(_free_bytes(base.device) * cache_fraction) // state_bytes - 1)
+    root = _Branch(base, base.probs([mcms[0].wires[0]]))
+    work = None
+    for _ in range(n_shots):
+        mm, node, scratch = {}, root, None
+        for j, mcm in enumerate(mcms):
+            if scratch is not None:                        # off the cached tree
+                scratch.apply_mid_measure(mcm, mm, rng)
+                apply_gates(scratch, segs[j], fusion, mm, rng)
+                continue
+            sample, scale = StateVector.mid_measure_draw(node.p, node.state.np_dtype, rng)
+            mm[mcm] = sample
+            child = node.children.get(sample)
+            if child is None:
+                if budget > 0:
+                    budget -= 1
+                    target = node.state.clone()
+                else:
+                    if work is None:
+                        work = node.state.clone()
+                    else:
+                        work.data.copy_(node.state.data)
+                    target = scratch = work
+                target.collapse(mcm.wires[0], sample, bool(getattr(mcm, "reset", False)), scale)
+                apply_gates(target, segs[j], fusion, mm, rng)
+                if scratch is None:
+                    nxt = target.probs([mcms[j + 1].wires[0]]) if j + 1 < len(mcms) else None
+                    child = node.children[sample] = _Branch(target, nxt)
+            if child is not None:
+                node = child
+        final = scratch if scratch is not None else node.state
+        results.append(measure_final_state(aux, final, False, rng=rng,
+                                           exact_sampling=exact_sampling, mid_measurements=mm))
     return tuple(results)
+
+
+def _free_bytes(device):
+    import torch
+
+    return torch.cuda.mem_get_info(device)[0]
 
 
 class _OneShotView:

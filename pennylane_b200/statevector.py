@@ -272,24 +272,32 @@ class StateVector:
             raise AssertionError("mid_measurements dictionary is required for MidMeasure")
         wire = op.wires[0]
         p = self.probs([wire])                                   # one read sweep: (p0, p1)
+        sample, scale = self.mid_measure_draw(p, self.np_dtype, rng)
+        mid_measurements[op] = sample
+        self.collapse(wire, sample, bool(getattr(op, "reset", False)), scale)
+        return sample
+
+    @staticmethod
+    def mid_measure_draw(p, np_dtype, rng=None):
+        """The host half of ``apply_mid_measure`` (apply_operation.py:450-485) from the measured
+        wire's marginal ``p = (p0, p1)``: the reference's checks, its one ``binomial(1, 1 - p0)``
+        draw, and the factor ``1 / ||P psi||`` the collapse applies."""
         # :450 prob0 = real(norm(slice))**2 — sqrt then square, like the reference
         prob0 = float(np.sqrt(p[0])) ** 2
-        eps = 10 * np.finfo(self.np_dtype).eps                   # :452-457
+        eps = 10 * np.finfo(np_dtype).eps                        # :452-457
         if (prob0 - 1) > eps:
             raise ValueError(f"probabilities greater than 1. Got norm {prob0}.")
         if prob0 > 1:
             prob0 = prob0 / prob0
         binomial = np.random.binomial if rng is None else rng.binomial
         sample = int(binomial(1, 1 - prob0))
-        mid_measurements[op] = sample
         # :478-485 projector then state / norm(state); numpy's complex / real multiplies by the
         # reciprocal.  A zero-probability branch (cannot be drawn by a Bernoulli with p = 0 or 1)
         # would give inf, as 0 / 0 does in the reference.
         norm = float(np.sqrt(p[sample]))
         with np.errstate(divide="ignore"):
             scale = float(np.float64(1.0) / np.float64(norm))
-        self.collapse(wire, sample, bool(getattr(op, "reset", False)), scale)
-        return sample
+        return sample, scale
 
     # ---- operator dispatch (apply_operation.py:258-351 singledispatch, re-done for kernels) --
     def apply_operation(self, op, mid_measurements=None, rng=None):

@@ -298,3 +298,22 @@ def test_snapshots_through_the_device_match_oracle(fusion):
     assert len(dbg.snapshots["shots"]) == 3
     for a, b in zip(dbg.snapshots["shots"], ref_dbg.snapshots["shots"]):
         assert a.shape == (20, 2) and np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("fusion", [0, 1])
+def test_branch_cache_is_transparent(fusion):
+    """Cached branch states (default), no cache at all, and an exhausted cache (every new branch
+    in the scratch buffer) give identical per-shot results — and the oracle's."""
+    from oracle.simulate import simulate as oracle_simulate
+    from pennylane_b200.simulate import _simulate_native_mcm
+
+    tape = _dynamic_tape(8, shots=60, seed=5).map_to_standard_wires()
+    runs = [_simulate_native_mcm(tape, np.random.default_rng(9), np.complex128, None, True, fusion,
+                                 cache_fraction=f) for f in (0.5, 0.0, 1e-15)]
+    ref = oracle_simulate(tape, rng=np.random.default_rng(9))
+    for res in runs:
+        assert len(res) == 60
+        for g, r in zip(res, ref):
+            assert np.array_equal(np.asarray(g[0]), np.asarray(r[0]))
+            assert np.allclose(g[1], r[1]) and np.allclose(g[2], r[2])
+            assert [int(x) for x in g[3:]] == [int(x) for x in r[3:]]

@@ -7,7 +7,7 @@
 * ``StateVector.reduced_dm`` (``b200q_gram_block``) for one, two and four kept wires;
 * one-shot throughput (shots/s) of a dynamic circuit at M qubits — an entangling prefix, four
   measurements with conditional gates, all-wire terminal sample — with the prefix simulated once
-  (ours) and with the prefix re-simulated every shot (what the reference's loop does,
+  and collapsed branch states cached in HBM (ours) and with the prefix re-simulated every shot (what the reference's loop does,
   simulate.py:371-380), next to the oracle on the host at a smaller size.
 
     python tools/bench_mcm.py [N=30] [M=26] [shots=40]
@@ -116,7 +116,7 @@ def main():
     t_full = time.perf_counter() - t0
     out["one_shot"] = {"qubits": Mq, "shots": shots, "prefix_gates": n_prefix,
                        "gates_per_shot_after_first_mcm": len(tape.operations) - n_prefix,
-                       "shots_per_s_prefix_once": shots / t_cached,
+                       "shots_per_s_prefix_once_branch_cache": shots / t_cached,
                        "shots_per_s_full_tape_per_shot": shots / t_full}
 
     from oracle.simulate import simulate as oracle_simulate
