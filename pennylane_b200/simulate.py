@@ -518,7 +518,7 @@ def _simulate_native_mcm(circuit, rng, dtype, device, exact_sampling, fusion, de
     * the state a shot reaches depends only on its outcomes so far, so collapsed branch states
       stay resident in HBM in a tree keyed by outcome (up to ``cache_fraction`` of the free
       memory; beyond that a shot continues in a scratch buffer).  A shot whose branch is cached
-      costs its ``binomial`` draws on cached marginals plus the terminal sampling.
+      costs its ``binomial`` draws on cached marginals plus a search in the leaf's cached CDF.
     The host Generator is consumed exactly as in the reference's loop — one ``binomial`` per
     measurement in tape order, then the terminal draws — so per-shot results are bit-identical
     to the oracle's under the same seed (this is the one-shot method's stream, not
@@ -571,8 +571,10 @@ def _simulate_native_mcm(circuit, rng, dtype, device, exact_sampling, fusion, de
             mm[mcm] = sample
             child = node.children.get(sample)
             if child is None:
-                if budget > 0:
-                    budget -= 1
+                leaf = j + 1 == len(mcms)
+                cost = 2 if leaf else 1                    # a leaf also keeps its sampling CDF
+                if budget >= cost:
+                    budget -= cost
                     target = node.state.clone()
                 else:
                     if work is None:
@@ -583,7 +585,8 @@ def _simulate_native_mcm(circuit, rng, dtype, device, exact_sampling, fusion, de
                 target.collapse(mcm.wires[0], sample, bool(getattr(mcm, "reset", False)), scale)
                 apply_gates(target, segs[j], fusion, mm, rng)
                 if scratch is None:
-                    nxt = target.probs([mcms[j + 1].wires[0]]) if j + 1 < len(mcms) else None
+                    nxt = None if leaf else target.probs([mcms[j + 1].wires[0]])
+                    target.frozen = leaf                   # terminal draws reuse its CDF
                     child = node.children[sample] = _Branch(target, nxt)
             if child is not None:
                 node = child

@@ -65,6 +65,8 @@ class StateVector:
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         self.n = int(num_wires)
         self.np_dtype = np.dtype(dtype)
+        self.frozen = False                 # set on cached, never-again-written branch states
+        self._cdf_cache = {}
         if self.np_dtype not in (np.dtype(np.complex64), np.dtype(np.complex128)):
             raise ValueError("dtype must be complex64 or complex128")
         self.dtype_code = 1 if self.np_dtype == np.complex128 else 0
@@ -582,6 +584,24 @@ class StateVector:
         if shots == 0:                      # every shot postselected away (simulate.py:159-167)
             empty = np.zeros((0, m), dtype=np.int64)
             return np.stack([empty] * self.batch) if self.batch > 1 else empty
+        # A frozen state (a cached branch of the one-shot MCM tree: never written again) keeps
+        # the normalised CDF b200q_sample leaves behind; later draws are search + unpack only.
+        frozen = getattr(self, "frozen", False) and self.batch == 1
+        key = (tuple(wires), bool(exact))
+        if frozen and key in self._cdf_cache:
+            cdf, norm, has_nan = self._cdf_cache[key]
+            u = torch.from_numpy(rng.random(shots)).to(self.device)
+            if has_nan:
+                return np.zeros((shots, m), dtype=np.int64)
+            if abs(norm - 1.0) > 1e-6:
+                raise ValueError("probabilities do not sum to 1")
+            idx = torch.empty(shots, dtype=torch.int64, device=self.device)
+            bits = torch.empty((shots, m), dtype=torch.int64, device=self.device)
+            check(self.lib.b200q_search(C.c_void_p(cdf.data_ptr()), m, C.c_void_p(u.data_ptr()),
+                                        shots, C.c_void_p(idx.data_ptr()), self.stream))
+            check(self.lib.b200q_unpack_bits(C.c_void_p(idx.data_ptr()), shots, m,
+                                             C.c_void_p(bits.data_ptr()), self.stream))
+            return bits.cpu().numpy()
         probs = self.probs_device(wires)
         outs = []
         need = ((1 << m) // 128 + (1 << m) // (128 * 2047) + 128) * 8 + (4 << 20)
@@ -597,6 +617,8 @@ class StateVector:
                                         C.c_void_p(self._scal.data_ptr()),
                                         C.c_void_p(flags.data_ptr()), w, wb, self.stream))
             norm = float(self._scal[0].item())
+            if frozen:
+                self._cdf_cache[key] = (pb, norm, bool(int(flags.item())))
             if int(flags.item()):
                 # sampling.py:322-325 — NaN probabilities give all-zero samples
                 outs.append(np.zeros((shots, m), dtype=np.int64))
