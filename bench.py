@@ -385,6 +385,34 @@ def run_ours(args):
             per_gate[name] = {"kernel": kernel_of[name], "launches": len(plist), "gbps": gb, "frac": gb / peak}
         roofline["per_gate_kernels"] = per_gate
 
+        # Measurement-side kernels outside the expval of the step: the two sweeps of a native
+        # mid-circuit measurement (single-wire marginal: S read; collapse: S/2 read + S written,
+        # apply_operation.py:415-497) and a two-wire reduced density matrix (S read,
+        # math/quantum.py:386-487).  Same timing rule: CUDA events around a few launches.
+        S_bytes = 16.0 * 2 ** n
+        meas = {}
+        mprobes = {
+            "mid_measure_probs": ("k_probs_marginal<double>", S_bytes,
+                                  [lambda w=w: sv.probs_device([w]) for w in (0, n // 2)]),
+            "reduced_dm_2_wires": ("k_gram_block<double,2,same>", S_bytes,
+                                   [lambda: sv.reduced_dm([0, n // 2]), lambda: sv.reduced_dm([1, n - 1])]),
+            "mid_measure_collapse": ("k_collapse<double>", 1.5 * S_bytes,
+                                     [lambda w=w: sv.collapse(w, 0, False, 1.0) for w in (0, n // 2)]),
+        }
+        for name, (kern, byt, calls) in mprobes.items():
+            for c in calls:
+                c()
+            torch.cuda.synchronize()
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for c in calls:
+                c()
+            e1.record()
+            torch.cuda.synchronize()
+            gb = byt * len(calls) / (e0.elapsed_time(e1) * 1e-3) / 1e9
+            meas[name] = {"kernel": kern, "launches": len(calls), "gbps": gb, "frac": gb / peak}
+        roofline["measurement_kernels"] = meas
+
     # e2e: public API, host parameters in / host scalar out, wall clock
     dev = qb.B200Qubit(wires=n, seed=0, fusion=args.fusion_level if args.fusion == "on" else 0)
     par = np.random.default_rng(3).uniform(0, 2 * np.pi, (args.layers, n, 2))
