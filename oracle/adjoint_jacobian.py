@@ -138,7 +138,34 @@ def adjoint_jvp(tape, tangents, state):                    # adjoint_jacobian.py
     return tuple(np.array(t) for t in tangents_out)
 
 
+def adjoint_vjp_state(tape, cotangents, state):            # adjoint_jacobian.py:240-245, 378-419
+    """VJP of a tape that returns the state: bra = conj(cotangent), complex results."""
+    ket = state
+    bras = np.conj(np.asarray(cotangents).reshape(-1, *ket.shape))
+    bras = np.squeeze(bras, axis=0)
+    trainable = list(tape.trainable_params)
+    _, n_op_params = _op_param_layout(tape)
+    param_number = n_op_params - 1
+    trainable_param_number = len(trainable) - 1
+    out = np.empty(len(trainable), dtype=complex)
+    for op in reversed(tape.operations[tape.num_preps:]):
+        adj_op = _adjoint_op(op)
+        ket = apply_operation(adj_op, ket)
+        if len(op.data) == 1:
+            if param_number in trainable:
+                ket_temp = apply_operation(_unitary(operation_derivative(op), op.wires), ket)
+                out[trainable_param_number] = np.sum(np.conj(bras) * ket_temp)
+                trainable_param_number -= 1
+            param_number -= 1
+        else:
+            param_number -= len(op.data)
+        bras = apply_operation(adj_op, bras)
+    return tuple(out)
+
+
 def adjoint_vjp(tape, cotangents, state):                  # adjoint_jacobian.py:327-419 (unbatched)
+    if tape.measurements[0].kind == "state":
+        return adjoint_vjp_state(tape, cotangents, state)
     n = tape.num_wires
     ket = state
     obs = list(tape.observables)

@@ -347,7 +347,7 @@ def _adjoint_jacobian_state(tape, dtype=np.complex128, device=None):
                 jacobian.append(new)
             param_idx += 1
         state.apply_operation(op)
-    return tuple(j.to_numpy().reshape(-1) for j in jacobian)
+    return tuple(j.to_numpy().reshape(-1) for j in jacobian), state
 
 
 def adjoint_jacobian(tape, dtype=np.complex128, device=None, return_state: bool = False,
@@ -357,8 +357,8 @@ def adjoint_jacobian(tape, dtype=np.complex128, device=None, return_state: bool 
     ``return_state`` also a ``StateVector`` copy of the final state taken before the sweep."""
     tape = tape.map_to_standard_wires()
     if tape.measurements and tape.measurements[0].kind == "state":        # :110-111
-        jac = _adjoint_jacobian_state(tape, dtype, device)
-        return (jac, None) if return_state else jac
+        jac, final = _adjoint_jacobian_state(tape, dtype, device)
+        return (jac, final) if return_state else jac
     obs = [m.obs for m in tape.measurements]
     if any(o is None for o in obs) or any(m.kind != "expval" for m in tape.measurements):
         raise ValueError("adjoint differentiation supports expectation values only")
@@ -404,10 +404,46 @@ def adjoint_jvp(tape, tangents, dtype=np.complex128, device=None, fusion: int = 
     return tuple(np.array(t) for t in out)
 
 
+def _adjoint_vjp_state(tape, cotangents, dtype, device, fusion):
+    """``adjoint_vjp`` of a tape returning the state (adjoint_jacobian.py:240-245, 378-419): the
+    bra starts as the conjugated cotangent vector and the per-parameter results
+    ``<bra| dU |ket>`` stay complex."""
+    from .statevector import StateVector
+
+    n = tape.num_wires
+    ket, _ = get_final_state(tape, dtype=dtype, device=device, fusion=fusion)
+    bra = StateVector(n, dtype=dtype, device=device)
+    bra.set_state(np.conj(np.asarray(cotangents, dtype=np.complex128)).reshape(-1))
+    n_op_params, trainable = _param_bookkeeping(tape)
+    tset = set(trainable)
+    param_number = n_op_params - 1
+    tpn = len(trainable) - 1
+    out = np.zeros(len(trainable), dtype=np.complex128)
+    ops_ = list(tape.operations)
+    for op in reversed(ops_[tape.num_preps:]):
+        if op.name == "Snapshot":
+            continue
+        adj = _op_adjoint(op)
+        ket.apply_operation(adj)
+        if len(op.data) == 1:
+            if param_number in tset:
+                tmp = ket.clone()
+                tmp.apply_matrix(np.asarray(_ops.operation_derivative(op)), list(op.wires))
+                out[tpn] = bra.inner(tmp)
+                tpn -= 1
+            param_number -= 1
+        else:
+            param_number -= len(op.data)
+        bra.apply_operation(adj)
+    return tuple(out)
+
+
 def adjoint_vjp(tape, cotangents, dtype=np.complex128, device=None, fusion: int = 0):
     """adjoint_jacobian.py:327-419 (unbatched cotangents): the cotangents are folded into one
     effective observable so a single bra is swept regardless of the number of measurements."""
     tape = tape.map_to_standard_wires()
+    if tape.measurements and tape.measurements[0].kind == "state":
+        return _adjoint_vjp_state(tape, cotangents, dtype, device, fusion)
     obs = [m.obs for m in tape.measurements]
     cots = np.atleast_1d(np.asarray(cotangents, dtype=float))
     n_op_params, trainable = _param_bookkeeping(tape)

@@ -309,10 +309,15 @@ class B200Qubit:
         if tape.shots:
             raise DeviceError("Finite shots are not supported with adjoint + b200.qubit")
         tape = _decompose(tape, adjoint_ops, "adjoint + b200.qubit")
+        # default_qubit.py:243-283 (adjoint_state_measurements): all expectation values, or the
+        # state itself (what the reference turns every other observable-free measurement into)
+        state_only = len(tape.measurements) == 1 and tape.measurements[0].kind == "state"
         for m in tape.measurements:
+            if state_only:
+                break
             if m.kind != "expval":
                 raise DeviceError(f"Measurement {m} not accepted with adjoint + b200.qubit "
-                                  "(only expectation values).")
+                                  "(only expectation values, or the state alone).")
             if not adjoint_observables(m.obs):
                 raise DeviceError(f"Observable {m.obs} not supported with adjoint + b200.qubit")
         n_op_params = sum(len(op.data) for op in tape.operations)

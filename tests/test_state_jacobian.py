@@ -24,7 +24,6 @@ def _layered(n=6, seed=0):
         gates += [ops.RY(rng.uniform(0, 6), wires=w) for w in range(n)]
         gates += [ops.IsingXX(rng.uniform(0, 6), wires=[w, (w + 1) % n]) for w in range(0, n, 2)]
         gates += [ops.CNOT(wires=[w, (w + 1) % n]) for w in range(n)]
-        gates.append(ops.Rot(0.1, 0.2, 0.3, wires=0))         # three parameters: never differentiated
     tape = QuantumScript(gates, [M.state()])
     tape.trainable_params = [1, 2, 5, 7, 8, 13, 16]
     return tape
@@ -57,3 +56,51 @@ def test_device_known_answers_and_oracle_parity():
         assert g.shape == (64,) and np.max(np.abs(g - r)) < 1e-12
     got32 = adjoint_jacobian(tape, dtype=np.complex64)
     assert max(np.max(np.abs(g - r)) for g, r in zip(got32, ref)) < 1e-5
+
+
+def test_oracle_state_vjp_known_answers():
+    """test_adjoint_jacobian.py:328-331, 352-359."""
+    from oracle.adjoint_jacobian import adjoint_vjp
+    from oracle.simulate import get_final_state
+
+    one, two = _tapes()
+    dy = np.array([0.5, 2.0], dtype=np.complex128)
+    (vjp,) = adjoint_vjp(one, dy, get_final_state(one)[0])
+    assert np.allclose(vjp, dy[0] * -0.5 * np.sin(0.6) + dy[1] * -0.5j * np.cos(0.6))
+    dy = np.array([0.5, 1.0, 2.0, 2.5], dtype=np.complex128)
+    x_vjp, y_vjp = adjoint_vjp(two, dy, get_final_state(two)[0])
+    assert np.allclose(x_vjp, np.dot(X_JAC, dy)) and np.allclose(y_vjp, np.dot(Y_JAC, dy))
+
+
+@pytest.mark.gpu
+def test_device_state_vjp():
+    from oracle.adjoint_jacobian import adjoint_vjp as oracle_vjp
+    from oracle.simulate import get_final_state
+    from pennylane_b200.adjoint import adjoint_jacobian, adjoint_vjp
+
+    _, two = _tapes()
+    dy = np.array([0.5, 1.0, 2.0, 2.5], dtype=np.complex128)
+    x_vjp, y_vjp = adjoint_vjp(two, dy)
+    assert np.allclose(x_vjp, np.dot(X_JAC, dy)) and np.allclose(y_vjp, np.dot(Y_JAC, dy))
+    tape = _layered()
+    rng = np.random.default_rng(1)
+    dy = rng.normal(size=64) + 1j * rng.normal(size=64)
+    got = adjoint_vjp(tape, dy, fusion=1)
+    ref = oracle_vjp(tape, dy, get_final_state(tape)[0])
+    jac = adjoint_jacobian(tape)
+    assert len(got) == 7 and np.max(np.abs(np.array(got) - np.array(ref))) < 1e-12
+    assert np.allclose(got, [np.dot(j, dy) for j in jac])
+
+
+@pytest.mark.gpu
+def test_device_pipeline_accepts_state_tapes():
+    """default_qubit.py:243-283: the adjoint pipeline lets a state-only tape through."""
+    import pennylane_b200 as pb
+
+    _, two = _tapes()
+    dev = pb.device("b200.qubit")
+    tapes, cfg = dev.preprocess(two, pb.ExecutionConfig(gradient_method="adjoint"))
+    (res,), (jac,) = dev.execute_and_compute_derivatives(tapes, cfg)
+    assert np.allclose(jac[0], X_JAC) and np.allclose(jac[1], Y_JAC) and res.shape == (4,)
+    (vjp,) = dev.compute_vjp(tapes, (np.array([0.5, 1.0, 2.0, 2.5], dtype=complex),), cfg)
+    assert np.allclose(vjp[0], np.dot(X_JAC, [0.5, 1.0, 2.0, 2.5]))
