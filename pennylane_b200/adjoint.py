@@ -438,13 +438,58 @@ def _adjoint_vjp_state(tape, cotangents, dtype, device, fusion):
     return tuple(out)
 
 
+def _batched_cotangents(cotangents, n_meas):
+    """adjoint_jacobian.py:250-280: the ``(n_meas, B)`` cotangent array when the cotangents carry
+    a batch axis (scalar zeros of an inhomogeneous tuple padded to the batch shape), else None."""
+    if n_meas == 1:
+        c = np.expand_dims(np.asarray(cotangents, dtype=float), 0)
+        if c.ndim == 3 and c.shape[1] == 1:          # ((B,),) given as a one-element tuple
+            c = c[:, 0]
+        return c if c.ndim == 2 else None
+    inner = next((np.shape(c) for c in cotangents if np.shape(c) != ()), None)
+    if inner is None:
+        return None
+    rows = [np.zeros(inner) if (np.shape(c) == () and np.allclose(c, 0.0)) else np.asarray(c, dtype=float)
+            for c in cotangents]
+    return np.array(rows)
+
+
+def _adjoint_vjp_batched(tape, obs, cots, dtype, device, fusion):
+    """adjoint_jacobian.py:282-323, 395-419: one effective observable — one bra — per batch
+    entry, all swept together (the machinery ``adjoint_jacobian`` uses for several observables);
+    entries whose cotangents are all zero get zeros (:298-299, :408-409)."""
+    n_op_params, trainable = _param_bookkeeping(tape)
+    B = cots.shape[1]
+    if np.allclose(cots, 0.0):
+        return tuple(np.zeros((len(trainable), B)))
+    live, new_obs = [], []
+    for i, col in enumerate(cots.T):
+        keep = [(c, o) for c, o in zip(col, obs) if not np.allclose(c, 0.0)]
+        if keep:
+            live.append(i)
+            new_obs.append(_ops.dot([c for c, _ in keep], [o for _, o in keep]))
+    sweep = _Sweep(tape, dtype, device, len(live), fusion=fusion)
+    get_final_state(tape, dtype=dtype, device=device, buffer=sweep.vecs[0:1], fusion=fusion)
+    for k, o in enumerate(new_obs):
+        sweep.fill_bra_from_observable(k, o, 2.0)
+    vals, filled, trainable = _reverse_sweep(tape, sweep, len(live))
+    out = np.zeros((len(trainable), B))
+    for t in filled:
+        out[t, live] = vals[t]
+    return tuple(out)
+
+
 def adjoint_vjp(tape, cotangents, dtype=np.complex128, device=None, fusion: int = 0):
-    """adjoint_jacobian.py:327-419 (unbatched cotangents): the cotangents are folded into one
-    effective observable so a single bra is swept regardless of the number of measurements."""
+    """adjoint_jacobian.py:327-419: the cotangents are folded into one effective observable so a
+    single bra is swept regardless of the number of measurements (one bra per batch entry when
+    the cotangents are batched)."""
     tape = tape.map_to_standard_wires()
     if tape.measurements and tape.measurements[0].kind == "state":
         return _adjoint_vjp_state(tape, cotangents, dtype, device, fusion)
     obs = [m.obs for m in tape.measurements]
+    batched = _batched_cotangents(cotangents, len(obs))
+    if batched is not None:
+        return _adjoint_vjp_batched(tape, obs, batched, dtype, device, fusion)
     cots = np.atleast_1d(np.asarray(cotangents, dtype=float))
     n_op_params, trainable = _param_bookkeeping(tape)
     if np.allclose(cots, 0.0):

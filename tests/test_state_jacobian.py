@@ -104,3 +104,47 @@ def test_device_pipeline_accepts_state_tapes():
     assert np.allclose(jac[0], X_JAC) and np.allclose(jac[1], Y_JAC) and res.shape == (4,)
     (vjp,) = dev.compute_vjp(tapes, (np.array([0.5, 1.0, 2.0, 2.5], dtype=complex),), cfg)
     assert np.allclose(vjp[0], np.dot(X_JAC, [0.5, 1.0, 2.0, 2.5]))
+
+
+# ---- batched cotangents: tests/devices/qubit/test_adjoint_jacobian.py:566-700 ---------------------
+_X, _Y = 0.654, 1.221
+_OBS3 = lambda: [M.expval(ops.PauliZ(0)), M.expval(ops.PauliY(1)), M.expval(ops.PauliX(0))]
+_JAC3 = np.array([[-np.sin(_X), 0], [0, -np.cos(_Y)], [np.cos(_X), 0]])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cotangents", ((0, 1.23), (1.232, -2.098, 0.323, 1.112),
+                                        (5.212, -0.354, -2.575), (0.0, 0.0, 0.0)))
+@pytest.mark.parametrize("trainable", ([0], [0, 1]))
+def test_batched_cotangents_single_obs(cotangents, trainable):
+    from pennylane_b200.adjoint import adjoint_vjp
+
+    qs = QuantumScript([ops.RY(_X, wires=0), ops.RX(_Y, wires=1)], [M.expval(ops.PauliZ(0))],
+                       trainable_params=trainable)
+    actual = adjoint_vjp(qs, cotangents)
+    assert isinstance(actual, tuple) and len(actual) == len(trainable)
+    jac = np.array([[-np.sin(_X), 0]])[:, :len(trainable)]
+    assert np.allclose(actual, jac.T @ np.expand_dims(np.array(cotangents), 0), atol=1e-12)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cotangents", [
+    (np.array([1.0, 0.0, 0.0]), np.array([0.0, 1.0, 0.0]), np.array([0.0, 0.0, 1.0])),
+    (np.array([0.653, 0, 0]), np.array([0, 0.573, 0]), np.array([0, 0, 1.232])),
+    (np.array([0.653, -1.456]), np.array([0.498, 0.573]), np.array([0, 1.232])),
+    (np.array([0.653, 0, 0, -1.234]), np.array([-0.323, 0.573, -1.449, -0.573]),
+     np.array([0, 1, 1.232, 1.232])),
+    (np.array([0.0, 0, 0]), np.array([0.0, 0, 0]), np.array([0.0, 0, 0])),
+    (np.array([0.498, 0.573]), np.array([0.653, -1.456]), 0.0),          # :702-730 inhomogeneous
+    (np.array([0.498, 0.573, -1.456]), 0.0, 0.0)])
+@pytest.mark.parametrize("trainable", ([0], [0, 1]))
+def test_batched_cotangents_multi_obs(cotangents, trainable):
+    from pennylane_b200.adjoint import adjoint_vjp
+
+    qs = QuantumScript([ops.RY(_X, wires=0), ops.RX(_Y, wires=1)], _OBS3(),
+                       trainable_params=trainable)
+    actual = adjoint_vjp(qs, cotangents, fusion=1)
+    assert isinstance(actual, tuple) and len(actual) == len(trainable)
+    B = next(len(c) for c in cotangents if np.ndim(c))
+    dense = np.array([np.broadcast_to(c, (B,)) for c in cotangents], dtype=float)
+    assert np.allclose(actual, _JAC3[:, :len(trainable)].T @ dense, atol=1e-12)
