@@ -454,7 +454,7 @@ def _batched_cotangents(cotangents, n_meas):
     return np.array(rows)
 
 
-def _adjoint_vjp_batched(tape, obs, cots, dtype, device, fusion):
+def _adjoint_vjp_batched(tape, obs, cots, dtype, device, fusion, state=None):
     """adjoint_jacobian.py:282-323, 395-419: one effective observable — one bra — per batch
     entry, all swept together (the machinery ``adjoint_jacobian`` uses for several observables);
     entries whose cotangents are all zero get zeros (:298-299, :408-409)."""
@@ -469,7 +469,7 @@ def _adjoint_vjp_batched(tape, obs, cots, dtype, device, fusion):
             live.append(i)
             new_obs.append(_ops.dot([c for c, _ in keep], [o for _, o in keep]))
     sweep = _Sweep(tape, dtype, device, len(live), fusion=fusion)
-    get_final_state(tape, dtype=dtype, device=device, buffer=sweep.vecs[0:1], fusion=fusion)
+    _forward_into(sweep, tape, dtype, device, fusion, state)
     for k, o in enumerate(new_obs):
         sweep.fill_bra_from_observable(k, o, 2.0)
     vals, filled, trainable = _reverse_sweep(tape, sweep, len(live))
@@ -479,7 +479,18 @@ def _adjoint_vjp_batched(tape, obs, cots, dtype, device, fusion):
     return tuple(out)
 
 
-def adjoint_vjp(tape, cotangents, dtype=np.complex128, device=None, fusion: int = 0):
+def _forward_into(sweep, tape, dtype, device, fusion, state):
+    """Row 0 of the sweep buffer = the final state: copied from ``state`` (the device's
+    ``_state_cache`` entry of the forward execution, default_qubit.py:1021-1029) when given,
+    else computed by running the tape."""
+    if state is not None and state.n == tape.num_wires and state.batch == 1 \
+            and state.np_dtype == np.dtype(dtype):
+        sweep.vecs[0:1].view(-1).copy_(state.data.view(-1))
+    else:
+        get_final_state(tape, dtype=dtype, device=device, buffer=sweep.vecs[0:1], fusion=fusion)
+
+
+def adjoint_vjp(tape, cotangents, dtype=np.complex128, device=None, fusion: int = 0, state=None):
     """adjoint_jacobian.py:327-419: the cotangents are folded into one effective observable so a
     single bra is swept regardless of the number of measurements (one bra per batch entry when
     the cotangents are batched)."""
@@ -489,7 +500,7 @@ def adjoint_vjp(tape, cotangents, dtype=np.complex128, device=None, fusion: int 
     obs = [m.obs for m in tape.measurements]
     batched = _batched_cotangents(cotangents, len(obs))
     if batched is not None:
-        return _adjoint_vjp_batched(tape, obs, batched, dtype, device, fusion)
+        return _adjoint_vjp_batched(tape, obs, batched, dtype, device, fusion, state)
     cots = np.atleast_1d(np.asarray(cotangents, dtype=float))
     n_op_params, trainable = _param_bookkeeping(tape)
     if np.allclose(cots, 0.0):
@@ -497,7 +508,7 @@ def adjoint_vjp(tape, cotangents, dtype=np.complex128, device=None, fusion: int 
     keep = [(c, o) for c, o in zip(cots, obs) if not np.allclose(c, 0.0)]
     new_obs = _ops.dot([c for c, _ in keep], [o for _, o in keep])
     sweep = _Sweep(tape, dtype, device, 1, fusion=fusion)
-    get_final_state(tape, dtype=dtype, device=device, buffer=sweep.vecs[0:1], fusion=fusion)
+    _forward_into(sweep, tape, dtype, device, fusion, state)
     sweep.fill_bra_from_observable(0, new_obs, 2.0)
     vals, filled, trainable = _reverse_sweep(tape, sweep, 1)
     out = np.zeros(len(trainable))

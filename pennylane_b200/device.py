@@ -440,8 +440,14 @@ class B200Qubit:
         batch, single = self._as_batch(circuits)
         cotangents = (cotangents,) if single else tuple(cotangents)
         self._track(batch, "vjp_batches")
+        def _state(circuit):            # default_qubit.py:1021-1029: reuse the forward state
+            if not self._state_cache:
+                return None
+            return self._state_cache.get(circuit.map_to_standard_wires().hash)
+
         res = tuple(_adjoint.adjoint_vjp(c, t, dtype=self._dtype(execution_config),
-                                         device=self._torch_device, fusion=self._fusion)
+                                         device=self._torch_device, fusion=self._fusion,
+                                         state=_state(c))
                     for c, t in zip(batch, cotangents))
         return res[0] if single else res
 

@@ -148,3 +148,33 @@ def test_batched_cotangents_multi_obs(cotangents, trainable):
     B = next(len(c) for c in cotangents if np.ndim(c))
     dense = np.array([np.broadcast_to(c, (B,)) for c in cotangents], dtype=float)
     assert np.allclose(actual, _JAC3[:, :len(trainable)].T @ dense, atol=1e-12)
+
+
+@pytest.mark.gpu
+def test_compute_vjp_reuses_the_forward_state(monkeypatch):
+    """default_qubit.py:1021-1029: with ``use_device_jacobian_product`` the state of ``execute`` is
+    kept per tape hash and ``compute_vjp`` starts its reverse sweep from it."""
+    import pennylane_b200 as pb
+    from pennylane_b200 import adjoint as adj
+
+    rng = np.random.default_rng(0)
+    n = 8
+    gates = []
+    for _ in range(2):
+        gates += [ops.RY(rng.uniform(0, 6), wires=f"q{w}") for w in range(n)]
+        gates += [ops.CNOT(wires=[f"q{w}", f"q{(w + 1) % n}"]) for w in range(n)]
+    tape = QuantumScript(gates, [M.expval(ops.PauliZ("q0")), M.expval(ops.PauliX("q3"))])
+    dev = pb.device("b200.qubit")
+    cfg = pb.ExecutionConfig(gradient_method="adjoint", use_device_jacobian_product=True)
+    tapes, cfg = dev.preprocess(tape, cfg)
+    cots = ((0.3, -1.2),)
+    plain = pb.device("b200.qubit").compute_vjp(tapes, cots, cfg)          # no cache: own forward
+    dev.execute(tapes, cfg)
+    assert len(dev._state_cache) == 1
+
+    def boom(*a, **k):
+        raise AssertionError("forward pass re-run although the state was cached")
+
+    monkeypatch.setattr(adj, "get_final_state", boom)
+    cached = dev.compute_vjp(tapes, cots, cfg)
+    assert np.allclose(cached, plain, rtol=0, atol=1e-14)
