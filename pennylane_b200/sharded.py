@@ -656,6 +656,52 @@ class ShardedStateVector:
                 self.exchange(item)
         self.phys = list(program["final"])
 
+    def apply_mid_measure(self, op, mid_measurements: dict, rng=None):
+        """``apply_mid_measure`` (apply_operation.py:415-497) on the sharded state.  The marginal
+        of the measured wire is the ordered all-reduce of the ranks' partial marginals
+        (:meth:`probs`); every rank makes the reference's ``binomial`` draw on its own copy of the
+        same Generator; projector, ``1 / ||P psi||`` and reset are ONE 2x2 operator handed to the
+        planner — diagonal (no reset), so a global wire needs no communication; with a reset on a
+        global wire the planner swaps it local like for any other non-diagonal gate."""
+        from .statevector import StateVector
+
+        if self.batch > 1:
+            raise ValueError("MidMeasure cannot be applied to batched states.")
+        if mid_measurements is None:
+            raise AssertionError("mid_measurements dictionary is required for MidMeasure")
+        wire = op.wires[0]
+        p = self.probs([wire])
+        sample, scale = StateVector.mid_measure_draw(p, np.dtype(np.complex128), rng)
+        mid_measurements[op] = sample
+        if sample == 1 and getattr(op, "reset", False):
+            mat = np.zeros((2, 2), dtype=complex)
+            mat[0, 1] = scale
+            self.apply_operations([_ops.QubitUnitary(mat, wires=[wire])])
+        else:
+            diag = np.zeros(2, dtype=complex)
+            diag[sample] = scale
+            self.apply_operations([_ops.DiagonalQubitUnitary(diag, wires=[wire])])
+        return sample
+
+    def apply_gates(self, gates, mid_measurements=None, rng=None):
+        """The gate loop with mid-circuit measurements and conditionals (simulate.py:213-235,
+        apply_operation.py:355-411): unitary stretches go to the planner as before."""
+        run = []
+        for op in gates:
+            name = op.name
+            if name == "MidMeasureMP":
+                if run:
+                    self.apply_operations(run)
+                    run = []
+                self.apply_mid_measure(op, mid_measurements, rng)
+            elif name.startswith("Conditional") and hasattr(op, "meas_val"):
+                if op.meas_val.concretize(mid_measurements):
+                    run.append(op.base)
+            else:
+                run.append(op)
+        if run:
+            self.apply_operations(run)
+
     def apply_operations(self, ops_):
         bs = [getattr(o, "batch_size", None) for o in ops_]
         bs = [b for b in bs if b is not None]
@@ -961,6 +1007,39 @@ class ShardedStateVector:
 # ---------------------------------------------------------------------------------------------
 # circuit level
 # ---------------------------------------------------------------------------------------------
+def _simulate_sharded_one_shot(circuit, dist, rng, dtype, engine, fusion, exact_sampling, device):
+    """The one-shot loop of simulate.py:354-381 on the sharded state: per shot the tape is run
+    from |0..0> (as the reference does), mid-circuit values are drawn identically on every rank,
+    the terminal all-wire sample is one shot of the distributed sampler, and the sampled MCM
+    values close the result tuple (sampling.py:235-267)."""
+    if not circuit.shots:
+        raise TypeError("Native mid-circuit measurements are only supported with finite shots.")
+    rng = np.random.default_rng(rng)
+    n = circuit.num_wires
+    ops_ = list(circuit.operations)
+    wires = list(range(n))
+    sv = ShardedStateVector(n, dist, engine=engine, dtype=dtype, device=device, fusion=fusion)
+    prep = ops_[0] if ops_ and hasattr(ops_[0], "state_vector") else None
+    results = []
+    for _ in range(circuit.shots.total_shots):
+        if prep is not None:
+            sv.set_state(np.asarray(prep.state_vector(wire_order=wires)))
+        else:
+            sv.reset()
+        mm = {}
+        sv.apply_gates(ops_[bool(prep):], mm, rng)
+        mps = list(circuit.measurements)[: len(circuit.measurements) - len(mm)]
+        if any(mp.obs is not None for mp in mps):
+            raise NotImplementedError("sharded finite-shot measurement of an observable")
+        res = []
+        if mps:
+            samples = sv.sample(1, rng, None, exact_sampling)
+            res = [mp.process_samples(samples, wires) for mp in mps]
+        res += list(mm.values())
+        results.append(res[0] if len(circuit.measurements) == 1 else tuple(res))
+    return tuple(results)
+
+
 def simulate_sharded(circuit, dist, rng=None, dtype=np.complex128, engine=None, fusion=1,
                      exact_sampling=True, device=None, return_state=False):
     """The sharded mirror of simulate.py:308-393 for a tape in standard wire order: gate loop,
@@ -968,6 +1047,9 @@ def simulate_sharded(circuit, dist, rng=None, dtype=np.complex128, engine=None, 
     circuit = circuit.map_to_standard_wires()
     n = circuit.num_wires
     ops_ = list(circuit.operations)
+    if any(op.name == "MidMeasureMP" for op in ops_):
+        return _simulate_sharded_one_shot(circuit, dist, rng, dtype, engine, fusion,
+                                          exact_sampling, device)
     sv = ShardedStateVector(n, dist, engine=engine, dtype=dtype, device=device, fusion=fusion)
     if ops_ and hasattr(ops_[0], "state_vector"):
         sv.set_state(np.asarray(ops_[0].state_vector(wire_order=list(range(n)))))

@@ -79,6 +79,17 @@ def _check_all(dist, n, seed, fusion, world_note=""):
         eng.probs_inplace_device = lambda: orig(chunk_bits=max(3, sv2.nl - 3))   # several chunks
         got2 = sv2.sample(2000, np.random.default_rng(seed), None, True, consume=True)
         out[f"samples_consume_{kind}"] = 0.0 if np.array_equal(got2, refs) else 1.0
+    # native mid-circuit measurements (one-shot loop) on the sharded state: measured bits and
+    # terminal samples of every shot equal the oracle's under the same seed
+    from test_sharded_gloo import _mcm_tape
+
+    tape = _mcm_tape(n, seed, 8)
+    got = simulate_sharded(tape, dist, rng=np.random.default_rng(seed), fusion=fusion)
+    ref = o_sim.simulate(tape, rng=np.random.default_rng(seed))
+    same = len(got) == len(ref) == 8 and all(
+        np.array_equal(np.asarray(a[0]).reshape(-1), np.asarray(b[0]).reshape(-1))
+        and [int(x) for x in a[1:]] == [int(x) for x in b[1:]] for a, b in zip(got, ref))
+    out["mcm_one_shot"] = 0.0 if same else 1.0
     return out
 
 

@@ -236,6 +236,40 @@ def w_simulate(rank, world, n, seed):
     return abs(got[0] - ref[0]), float(np.max(np.abs(got[1] - ref[1])))
 
 
+def _mcm_tape(n, seed, shots):
+    import pennylane_b200 as qb
+    from pennylane_b200 import ops as q
+    from pennylane_b200.mcm import cond, measure
+
+    m0, m1, m2 = measure(0), measure(1, reset=True), measure(n - 1, reset=True)
+    ops_ = _hea(n, 2, seed) + [
+        m0.measurements[0], cond(m0, q.RX(0.7, wires=0)), cond(m0, q.Hadamard(wires=n - 2)),
+        q.CNOT(wires=[0, n - 1]), m1.measurements[0], cond(m0 & m1, q.RY(1.1, wires=1)),
+        q.CNOT(wires=[1, 2]), m2.measurements[0], cond(~m2, q.PauliX(wires=0))]
+    return qb.QuantumScript(ops_, [qb.sample(wires=range(n)), qb.sample(m0), qb.sample(m1),
+                                   qb.sample(m2)], shots=shots)
+
+
+def w_mcm(rank, world, n, seed, shots):
+    """One-shot dynamic circuit on the sharded state vs the oracle's one-shot loop, same seed:
+    measurements on a global wire (wire 0), with reset on a global and on a local wire, and
+    conditionals feeding gates on global and local wires."""
+    import pennylane_b200 as qb
+    from np_engine import NumpyEngine
+    from oracle import simulate as o_sim
+    from pennylane_b200 import ops as q
+    from pennylane_b200.mcm import cond, measure
+    from pennylane_b200.sharded import simulate_sharded
+
+    g = world.bit_length() - 1
+    tape = _mcm_tape(n, seed, shots)
+    got = simulate_sharded(tape, dist, rng=np.random.default_rng(seed), engine=NumpyEngine(n - g))
+    ref = o_sim.simulate(tape, rng=np.random.default_rng(seed))
+    same = all(np.array_equal(np.asarray(a[0]).reshape(-1), np.asarray(b[0]).reshape(-1))
+               and [int(x) for x in a[1:]] == [int(x) for x in b[1:]] for a, b in zip(got, ref))
+    return len(got), len(ref), bool(same), sorted({tuple(int(x) for x in a[1:]) for a in got})
+
+
 # ---------------------------------------------------------------------------------------------
 # tests
 # ---------------------------------------------------------------------------------------------
@@ -289,3 +323,10 @@ def test_planner_belady_and_exchange_volume():
     assert sorted(final) == list(range(n))
     runs = [s for s in steps if isinstance(s, RunStep)]
     assert sum(len(r.ops) for r in runs) == len(_hea(n, 4, 0))
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_sharded_mid_circuit_measurements_match_oracle(world):
+    for n_got, n_ref, same, outcomes in run_ranks(world, "w_mcm", 6, 13, 12):
+        assert n_got == n_ref == 12 and same
+        assert len(outcomes) > 1                       # several branches were actually visited
