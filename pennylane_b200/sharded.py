@@ -428,6 +428,9 @@ class CudaEngine:
     def probs_device(self, local_wires):
         return self.sv.probs_device(local_wires)
 
+    def reduced_dm(self, local_wires):
+        return self.sv.reduced_dm(local_wires)
+
     def probs_inplace_device(self, chunk_bits: int = 26):
         """|psi|^2 over all local wires written over the state itself (the state is consumed):
         at 33 local qubits the complex128 shard is 128 GiB and a separate 64 GiB probability
@@ -917,6 +920,21 @@ class ShardedStateVector:
         out = self._ordered_sum(full.reshape(B, -1))
         return out if B > 1 else out[0]
 
+    def reduced_dm(self, wires):
+        """Reduced density matrix over ``wires`` (``reduce_statevector``, math/quantum.py:386-487)
+        of the sharded state: the kept wires are made local (one exchange at most), every rank
+        forms the Gram blocks of its shard (``b200q_gram_block`` — a rank's bits are part of the
+        traced index) and the 4^m partial matrices are added in rank order."""
+        wires = list(wires)
+        if len(wires) > self.nl:
+            raise ValueError(f"reduced_dm over {len(wires)} wires needs them local; shards hold "
+                             f"{self.nl} qubits")
+        self.remap([self.bit_of(w) for w in wires])
+        lw = [self.nl - 1 - self.phys[self.bit_of(w)] for w in wires]
+        part = np.asarray(self.engine.reduced_dm(lw), dtype=np.complex128)
+        tot = self._ordered_sum(np.stack([part.real, part.imag]))
+        return tot[0] + 1j * tot[1]
+
     def norm2(self):
         xs, zs, ys, cs = [0], [0], [0], [1.0]
         r = self._ordered_sum(self.engine.expval_terms(xs, zs, ys, cs))
@@ -1074,6 +1092,10 @@ def simulate_sharded(circuit, dist, rng=None, dtype=np.complex128, engine=None, 
                 results.append(np.float64(r) if np.ndim(r) == 0 else r)
             elif mp.kind == "probs" and mp.obs is None:
                 results.append(sv.probs(list(mp.wires) if len(mp.wires) else None))
+            elif mp.kind in ("density_matrix", "purity", "vn_entropy", "mutual_info"):
+                from .simulate import _measure_density
+
+                results.append(_measure_density(mp, sv, False))
             elif mp.kind == "state":
                 results.append(sv.to_numpy())
             else:

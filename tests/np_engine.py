@@ -80,6 +80,12 @@ class NumpyEngine:
         p = probs_process_state(flat if self.batch > 1 else flat[0], [] if full else list(local_wires), self.n)
         return p.reshape(self.batch, -1)
 
+    def reduced_dm(self, local_wires):
+        from oracle.measure import reduce_statevector
+
+        flat = self.data.numpy()
+        return reduce_statevector(flat if self.batch > 1 else flat[0], list(local_wires))
+
     def probs_device(self, local_wires):
         return torch.from_numpy(np.ascontiguousarray(self.probs(local_wires)).copy())
 

@@ -90,6 +90,15 @@ def _check_all(dist, n, seed, fusion, world_note=""):
         np.array_equal(np.asarray(a[0]).reshape(-1), np.asarray(b[0]).reshape(-1))
         and [int(x) for x in a[1:]] == [int(x) for x in b[1:]] for a, b in zip(got, ref))
     out["mcm_one_shot"] = 0.0 if same else 1.0
+    # reduced density matrices: per-rank Gram blocks added in rank order
+    ops_ = _hea(n, 2, seed)
+    mps = [qb.density_matrix([0, n - 1]), qb.purity([1, 0, 3]), qb.vn_entropy([n - 2], log_base=2),
+           qb.mutual_info([0], [2, 1])]
+    tape = qb.QuantumScript(ops_, mps)
+    got = simulate_sharded(tape, dist, fusion=fusion)
+    ref = o_sim.simulate(tape)
+    for i, (a, b) in enumerate(zip(got, ref)):
+        out[f"density_{i}"] = float(np.max(np.abs(np.asarray(a) - np.asarray(b))))
     return out
 
 

@@ -236,6 +236,23 @@ def w_simulate(rank, world, n, seed):
     return abs(got[0] - ref[0]), float(np.max(np.abs(got[1] - ref[1])))
 
 
+def w_density(rank, world, n, seed):
+    """Reduced density matrices and the measurements on them, global and local wires mixed."""
+    import pennylane_b200 as qb
+    from np_engine import NumpyEngine
+    from oracle import simulate as o_sim
+    from pennylane_b200.sharded import simulate_sharded
+
+    g = world.bit_length() - 1
+    ops_ = _hea(n, 2, seed)
+    mps = [qb.density_matrix([0, n - 1]), qb.purity([1, 0, 3]), qb.vn_entropy([n - 2], log_base=2),
+           qb.mutual_info([0], [2, 1]), qb.density_matrix([2])]
+    tape = qb.QuantumScript(ops_, mps)
+    got = simulate_sharded(tape, dist, engine=NumpyEngine(n - g))
+    ref = o_sim.simulate(tape)
+    return [float(np.max(np.abs(np.asarray(a) - np.asarray(b)))) for a, b in zip(got, ref)]
+
+
 def _mcm_tape(n, seed, shots):
     import pennylane_b200 as qb
     from pennylane_b200 import ops as q
@@ -330,3 +347,9 @@ def test_sharded_mid_circuit_measurements_match_oracle(world):
     for n_got, n_ref, same, outcomes in run_ranks(world, "w_mcm", 6, 13, 12):
         assert n_got == n_ref == 12 and same
         assert len(outcomes) > 1                       # several branches were actually visited
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_sharded_density_measurements_match_oracle(world):
+    for errs in run_ranks(world, "w_density", 7, 3):
+        assert len(errs) == 5 and max(errs) < 1e-12
