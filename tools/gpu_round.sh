@@ -21,3 +21,13 @@ for k,v in d.items():
         print('   ', v['per_segment'][:8])
     else: print(k, round(v))
 PY
+# mid-circuit measurement / reduced-density-matrix kernels and the one-shot loop (profiles/r1g_mcm.json)
+timeout 400 python tools/bench_mcm.py ${MCM_ARGS:-30 26 400} > gpurun_out/mcm.json 2> gpurun_out/mcm.err; echo "mcm rc=$?"
+python - <<'PY'
+import json
+d = json.load(open('gpurun_out/mcm.json'))
+for k, v in d['kernels'].items():
+    if isinstance(v, dict):
+        print(k, round(v['ms'], 3), round(v['frac'], 3))
+print(d['one_shot'])
+PY
