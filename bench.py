@@ -268,9 +268,8 @@ def run_ours(args):
 
     fused_segments = None
     if args.fusion == "on":
-        from pennylane_b200.compiler import compile_ops
-        dT, dL = sv.default_tile()
-        fused_segments = compile_ops(ops_, n, level=args.fusion_level, T=dT, L=dL)
+        fused_segments = sv.compile_fused(ops_, level=args.fusion_level)
+        sv.prepare_segments(fused_segments)
 
     def forward(record):
         nonlocal launches

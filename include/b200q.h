@@ -217,6 +217,33 @@ int b200q_apply_rtile_bcast(void* vec0, void* vec1, int n, int dtype, int64_t ba
                             uint64_t base_hi, double scale, double* out_dev, void* work,
                             size_t work_bytes, void* stream);
 
+/* Structure-specialised fused segment kernel (pennylane_b200/csrc/segk.cuh): the same tile
+ * pipeline as b200q_apply_rtile, but the segment's STRUCTURE (round layouts, record kinds,
+ * register bits, control locations) is compiled into the kernel and only the VALUES are launch
+ * arguments.  The host (pennylane_b200/segjit.py) emits two small headers per structure
+ * ("sk_config.inc", "sk_body.inc"); b200q_jit_compile turns segk.cuh + headers into an sm_100a
+ * cubin through NVRTC (dlopen'ed libnvrtc.so.12; needs no GPU), b200q_seg_load makes it
+ * launchable, b200q_seg_launch runs one segment:
+ *   tile_bits[T] as for b200q_apply_rtile; RB / minb: register bits and CTAs per SM the kernel
+ *   was compiled for; ext_pos[n_ext]: global positions of the bits outside the tile that the
+ *   kernel's predicates read (base_hi is OR-ed into the tile base first: rank bits of a sharded
+ *   state); coef_host[n_coef] doubles (x batch tables when coef_batched): matrix coefficients
+ *   in the order the body consumes them; vec1 / nslots / write0 / scale / out_dev: adjoint mode,
+ *   as for b200q_apply_rtile.
+ * Replaces simulate.py:214-235 (gate loop) and adjoint_jacobian.py:121-137 (reverse sweep). */
+int b200q_jit_available(void);
+int b200q_jit_compile(const char* source, const char* const* header_names,
+                      const char* const* header_sources, int n_headers, int lineinfo,
+                      void** cubin_out, size_t* size_out);
+void b200q_jit_free(void* cubin);
+int b200q_seg_load(const void* cubin, size_t size, void** handle_out);
+int b200q_seg_unload(void* handle);
+int b200q_seg_launch(void* handle, void* vec0, void* vec1, int n, int dtype, int64_t batch,
+                     const int* tile_bits, int T, int L, int RB, int minb, const int* ext_pos,
+                     int n_ext, const double* coef_host, int n_coef, int coef_batched, int nslots,
+                     int write0, uint64_t base_hi, double scale, double* out_dev, void* work,
+                     size_t work_bytes, void* stream);
+
 /* One reverse-sweep step of adjoint differentiation on vecs = [1 + n_bras][2^n] (row 0 = ket):
  *   z_b = <bra_b| G |ket>,  ket <- A ket,  bra_b <- A bra_b      (A = U^dagger, k <= 3)
  * out_dev[b] = -Im z_b  (= Re <bra_b| i G |ket>, the Jacobian entry when bras carry the factor

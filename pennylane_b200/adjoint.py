@@ -218,6 +218,23 @@ def _fused_reverse_program(tape, n, RB, level):
     return prims, filled, trainable
 
 
+#: records per fused reverse segment (a module attribute so that tests can force a parameter's
+#: generator terms into different segments)
+MAX_SEGMENT_OPS = 64
+
+
+def _accumulate_slot_sums(raw, gather, n_rows, n_bras):
+    """``vals[param, bra]`` from the per-(segment, slot) sums of the fused reverse sweep.  The
+    generator terms of ONE parameter may land in different segments (merge_blocks hoists / defers
+    Z terms and emits identity terms at once; pack_segments cuts on the record budget and on the
+    tile-bit budget) and each segment gives the parameter its own local slot, so the partial sums
+    are ADDED, in segment order."""
+    vals = np.zeros((max(1, n_rows), n_bras))
+    for off, b, param in gather:
+        vals[param, b] += raw[off]
+    return vals
+
+
 def _reverse_sweep_fused(tape, sweep: "_Sweep", level: int = 1):
     """Reverse sweep through ``b200q_apply_rtile`` in adjoint mode: one read + one write of the
     ket and of each bra per SEGMENT of gates (instead of per gate), generator inner products
@@ -229,24 +246,39 @@ def _reverse_sweep_fused(tape, sweep: "_Sweep", level: int = 1):
     torch = _torch()
     ket = sweep.ket
     n = sweep.n
-    T, RB, _ = ket.rt_geometry(2)
+    jit = ket.jit_enabled(2)
+    if jit:
+        from . import segjit
+        geom = segjit.default_geometry(ket.dtype_code, 2)
+        T, RB = geom.T, geom.RB
+    else:
+        T, RB, _ = ket.rt_geometry(2)
     if n < T:
         return None
     prog = _fused_reverse_program(tape, n, RB, level)
     if prog is None:
         return None
     prims, filled, trainable = prog
-    prims = merge_blocks(prims, level)
+    prims = merge_blocks(prims, level, fold_cx=not jit)
     _, L = ket.default_tile(2)
-    segs = pack_segments(prims, n, T=T, L=L, max_ops=64)
+    L = min(L, T)
+    segs = pack_segments(prims, n, T=T, L=L, max_ops=MAX_SEGMENT_OPS)
     n_bras = sweep.n_bras
-    total_slots = sum(len({p.param for p in s.prims if p.kind == GEN}) for s in segs)
+    plans = {}
+    if jit:
+        for i, seg in enumerate(segs):
+            if seg.tile_bits is not None:
+                plans[i] = segjit.plan_segment(seg, geom, _low_run(seg.tile_bits))
+        segjit.ensure_compiled(plans.values())
+        total_slots = sum(p.nslots for p in plans.values())
+    else:
+        total_slots = sum(len({p.param for p in s.prims if p.kind == GEN}) for s in segs)
     acc = torch.zeros(max(1, total_slots * n_bras), dtype=torch.float64, device=ket.device)
     gather = []                                   # (offset in acc, bra, param index)
     offset = 0
     w, wb = ket.workspace()
     sww = 3 if ket.dtype_code else 4
-    for seg in segs:
+    for i, seg in enumerate(segs):
         if seg.tile_bits is None:
             p = seg.prims[0]
             if p.op is not None:
@@ -255,6 +287,18 @@ def _reverse_sweep_fused(tape, sweep: "_Sweep", level: int = 1):
                 sweep.all.apply_diag(np.asarray(p.mat), [n - 1 - b for b in p.other])
             else:  # pragma: no cover
                 raise RuntimeError("unexpected generic primitive in the reverse sweep")
+            continue
+        if jit:
+            plan = plans[i]
+            coefs = segjit.coefficients(plan, seg.prims)
+            nslots = plan.nslots
+            for b in range(n_bras):
+                segjit.launch(plan, coefs, ket.ptr, sweep.bra(b).ptr, n, 1, w, wb, ket.stream,
+                              write0=1 if b == n_bras - 1 else 0, scale=-1.0,
+                              out_ptr=C.c_void_p(acc.data_ptr() + 8 * offset) if nslots else None)
+                for slot, param in enumerate(plan.slot_params):
+                    gather.append((offset + slot, b, param))
+                offset += nslots
             continue
         local = {}
         for p in seg.prims:
@@ -272,10 +316,7 @@ def _reverse_sweep_fused(tape, sweep: "_Sweep", level: int = 1):
             for param, slot in local.items():
                 gather.append((offset + slot, b, param))
             offset += nslots
-    raw = acc.cpu().numpy()
-    vals = np.zeros((max(1, len(trainable)), n_bras))
-    for off, b, param in gather:
-        vals[param, b] = raw[off]
+    vals = _accumulate_slot_sums(acc.cpu().numpy(), gather, len(trainable), n_bras)
     return vals, filled, trainable
 
 

@@ -12,10 +12,10 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(CSRC, "libb200q.so")
-SOURCES = ["api.cu", "dm.cu", "rtile.cu"] + [f"rtile_k_{p}_{k}.cu" for p in "df"
+SOURCES = ["api.cu", "dm.cu", "rtile.cu", "segk_host.cu"] + [f"rtile_k_{p}_{k}.cu" for p in "df"
                                     for k in ("fwd", "ws", "adj", "adj2")]          # compiled in parallel, one object each
 HEADERS = ["common.cuh", "gates.cuh", "measure.cuh", "sample.cuh", "adjoint.cuh", "tile.cuh",
-           "rtile.cuh", "rtile_host.h", "rtile_launch.cuh", os.path.join("..", "..", "include", "b200q.h")]
+           "rtile.cuh", "rtile_host.h", "rtile_launch.cuh", "segk_args.h", os.path.join("..", "..", "include", "b200q.h")]
 OBJDIR = os.path.join(CSRC, "build")
 
 NVCC_FLAGS = [
@@ -73,7 +73,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         for _, log in results:
             print(log)
     cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "--shared", "-Xcompiler", "-fPIC",
-           *[o for o, _ in results], "-o", OUT]
+           *[o for o, _ in results], "-ldl", "-o", OUT]
     res = subprocess.run(cmd, capture_output=True, text=True, cwd=CSRC)
     if res.returncode != 0:
         raise RuntimeError(f"link failed:\n{' '.join(cmd)}\n{res.stdout}\n{res.stderr}")

@@ -271,8 +271,12 @@ def _place_generator(g: Prim, pending: dict, out: list) -> bool:
     return True
 
 
-def merge_blocks(prims: list[Prim], level: int = 1) -> list[Prim]:
-    """level 0: nothing; 1: products of single-qubit runs, with singly-controlled X gates on
+def merge_blocks(prims: list[Prim], level: int = 1, fold_cx: bool = True) -> list[Prim]:
+    """``fold_cx=False`` (the specialised kernels of segjit.py): CNOTs stay separate records — a
+    register renaming or a per-thread select there — and single-qubit runs stay uncontrolled, so
+    that they can be applied in their normalised form.
+
+    level 0: nothing; 1: products of single-qubit runs, with singly-controlled X gates on
     the same target folded in as *controlled-select* blocks (``mat`` where the control holds,
     ``mat0`` where it does not: CNOT next to a single-qubit block costs no extra pass and no
     data movement); 2: also absorb single-qubit blocks into adjacent dense two-qubit gates and
@@ -329,7 +333,7 @@ def merge_blocks(prims: list[Prim], level: int = 1) -> list[Prim]:
             else:
                 pending[b] = Prim(DENSE1, targets=[b], mat=m.copy(), ngates=p.ngates, seq=seq)
             continue
-        if p.kind == CX and len(p.ctrl) == 1:
+        if fold_cx and p.kind == CX and len(p.ctrl) == 1:
             t = p.targets[0]
             (c, v), = p.ctrl.items()
             flush_controlled_by(t)               # they read t before it is flipped
@@ -470,14 +474,14 @@ def pack_segments(prims: list[Prim], n: int, T: int = 12, L: int = 5, max_ops: i
 
 
 def compile_ops(ops_, n: int, bit_of=None, level: int = 1, T: int = 12, L: int = 5,
-                batched_ok: bool = False):
+                batched_ok: bool = False, fold_cx: bool = True):
     """Operators -> list of :class:`Segment`."""
     if bit_of is None:
         bit_of = lambda w: n - 1 - int(w)          # noqa: E731
     prims: list[Prim] = []
     for op in ops_:
         prims.extend(lower(op, bit_of, batched_ok))
-    prims = merge_blocks(prims, level)
+    prims = merge_blocks(prims, level, fold_cx)
     return pack_segments(prims, n, T=T, L=L)
 
 

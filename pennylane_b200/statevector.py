@@ -393,23 +393,90 @@ class StateVector:
         L = int(os.environ.get("B200Q_TILE_L", 4 if (self.dtype_code and T <= 11) else 5))
         return T, min(L, T)
 
-    def apply_operations_fused(self, ops_, level: int = 1, T: int | None = None,
-                               L: int | None = None, bit_of=None):
-        """Apply a list of operators through the fusion pass (compiler.py): returns the number of
-        state sweeps (kernel launches over the full state) that were issued."""
+    def jit_enabled(self, nvec: int = 1) -> bool:
+        """Whether fused segments go through the structure-specialised kernels (segjit.py /
+        csrc/segk.cuh) instead of the record interpreter.  ``B200Q_JIT``: 1 = always, 0 = never,
+        unset = for states of at least ``B200Q_JIT_MIN_QUBITS`` (default 22) qubits, where the
+        one-off NVRTC compilation of a structure (about a second) is small against the sweeps."""
+        import os
+
+        from . import segjit
+
+        mode = os.environ.get("B200Q_JIT", "auto")
+        geom = segjit.default_geometry(self.dtype_code, nvec)
+        if mode == "0" or self.n < geom.T:
+            return False
+        if mode == "auto" and self.n < int(os.environ.get("B200Q_JIT_MIN_QUBITS", 22)):
+            return False
+        return bool(self.lib.b200q_jit_available())
+
+    def compile_fused(self, ops_, level: int = 1, T: int | None = None, L: int | None = None,
+                      bit_of=None):
+        """Operators -> segments for this state (host fusion pass, compiler.py)."""
         from .compiler import compile_ops
 
         dT, dL = self.default_tile()
         rtT, _, _ = self.rt_geometry(1)
-        segs = compile_ops(ops_, self.n, bit_of=bit_of, level=level, T=T or dT, L=L if L is not None else dL,
-                           batched_ok=(T or dT) == rtT and self.n >= rtT)
+        jit = self.jit_enabled(1) and (T or dT) == rtT
+        return compile_ops(ops_, self.n, bit_of=bit_of, level=level, T=T or dT, L=L if L is not None else dL,
+                           batched_ok=(T or dT) == rtT and self.n >= rtT, fold_cx=not jit)
+
+    def apply_operations_fused(self, ops_, level: int = 1, T: int | None = None,
+                               L: int | None = None, bit_of=None):
+        """Apply a list of operators through the fusion pass (compiler.py): returns the number of
+        state sweeps (kernel launches over the full state) that were issued."""
+        segs = self.compile_fused(ops_, level, T, L, bit_of)
+        self.prepare_segments(segs)
         for seg in segs:
             self.run_segment(seg)
         return len(segs)
 
+    def prepare_segments(self, segs):
+        """Plan every tile segment for the specialised kernels and compile the structures that
+        are in no cache yet, in parallel (no-op on the interpreter path)."""
+        from . import segjit
+
+        if not self.jit_enabled(1):
+            return
+        rtT = self.rt_geometry(1)[0]
+        geom = segjit.default_geometry(self.dtype_code, 1)
+        plans = []
+        for seg in segs:
+            if seg.tile_bits is None or len(seg.tile_bits) != rtT:
+                continue
+            if getattr(seg, "_sk_plan", None) is None:
+                seg._sk_plan = segjit.plan_segment(seg, geom, _low_run(seg.tile_bits))
+                seg._sk_coefs = segjit.coefficients(seg._sk_plan, seg.prims)
+            plans.append(seg._sk_plan)
+        segjit.ensure_compiled(plans)
+
+    def _run_segment_jit(self, seg, base_hi: int = 0):
+        """One fused segment through its structure-specialised kernel.  The plan (structure) and
+        the coefficient table (values) are kept on the segment object."""
+        from . import segjit
+
+        plan = getattr(seg, "_sk_plan", None)
+        if plan is None:
+            geom = segjit.default_geometry(self.dtype_code, 1)
+            plan = segjit.plan_segment(seg, geom, _low_run(seg.tile_bits))
+            seg._sk_plan = plan
+            seg._sk_coefs = segjit.coefficients(plan, seg.prims)
+        coefs = seg._sk_coefs
+        if coefs.ndim == 2 and coefs.shape[0] != self.batch:   # broadcast parameters
+            if self.batch != 1:
+                raise ValueError(f"broadcast gates of batch {coefs.shape[0]} on a state of "
+                                 f"batch {self.batch}")
+            self._resize_batch(coefs.shape[0])
+        w, wb = self.workspace()
+        segjit.launch(plan, coefs, self.ptr, None, self.n, self.batch, w, wb, self.stream,
+                      base_hi=base_hi)
+
     def run_segment(self, seg, base_hi: int = 0):
         from .compiler import DIAG, encode_rt_segment, encode_segment
 
+        if seg.tile_bits is not None and self.jit_enabled(1) \
+                and len(seg.tile_bits) == self.rt_geometry(1)[0]:
+            return self._run_segment_jit(seg, base_hi)
         if seg.tile_bits is None:
             p = seg.prims[0]
             if p.op is not None:
