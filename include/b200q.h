@@ -227,8 +227,10 @@ int b200q_apply_rtile_bcast(void* vec0, void* vec1, int n, int dtype, int64_t ba
  *   tile_bits[T] as for b200q_apply_rtile; RB / minb: register bits and CTAs per SM the kernel
  *   was compiled for; ext_pos[n_ext]: global positions of the bits outside the tile that the
  *   kernel's predicates read (base_hi is OR-ed into the tile base first: rank bits of a sharded
- *   state); coef_host[n_coef] doubles (x batch tables when coef_batched): matrix coefficients
- *   in the order the body consumes them; vec1 / nslots / write0 / scale / out_dev: adjoint mode,
+ *   state); coef_host[n_coef] doubles: matrix coefficients in the order the body consumes them;
+ *   coef_mode 0: one table, staged in shared memory; 1: `batch` tables, batch element b reads
+ *   table b (broadcast parameters); 2: the table is passed as a kernel parameter (kernels
+ *   compiled with SK_COEF_PARAM: coefficients become constant-bank operands); vec1 / nslots / write0 / scale / out_dev: adjoint mode,
  *   as for b200q_apply_rtile.
  * Replaces simulate.py:214-235 (gate loop) and adjoint_jacobian.py:121-137 (reverse sweep). */
 int b200q_jit_available(void);
@@ -240,7 +242,7 @@ int b200q_seg_load(const void* cubin, size_t size, void** handle_out);
 int b200q_seg_unload(void* handle);
 int b200q_seg_launch(void* handle, void* vec0, void* vec1, int n, int dtype, int64_t batch,
                      const int* tile_bits, int T, int L, int RB, int minb, const int* ext_pos,
-                     int n_ext, const double* coef_host, int n_coef, int coef_batched, int nslots,
+                     int n_ext, const double* coef_host, int n_coef, int coef_mode, int nslots,
                      int write0, uint64_t base_hi, double scale, double* out_dev, void* work,
                      size_t work_bytes, void* stream);
 

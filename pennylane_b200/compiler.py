@@ -410,10 +410,16 @@ class Segment:
     tile_bits: list | None                    # None -> generic op
     prims: list
     ngates: int = 0
+    rounds: list | None = None                # round schedule fixed by the packer (round budget)
 
 
 def pack_segments(prims: list[Prim], n: int, T: int = 12, L: int = 5, max_ops: int = 96,
-                  max_mat: int = 1024) -> list[Segment]:
+                  max_mat: int = 1024, round_budget: int | None = None, RB: int = 4,
+                  sww: int = 3) -> list[Segment]:
+    """``round_budget``: the primitives of a segment that do not fit that many rounds of the
+    register kernel (``RB`` register bits per round) are handed back and packed later — an extra
+    shared-memory transposition per tile costs about a quarter of a sweep, so single-qubit blocks
+    that a later segment can take for free should not force one."""
     T = min(T, n)
     L = min(L, T)
     free = T - L
@@ -468,13 +474,27 @@ def pack_segments(prims: list[Prim], n: int, T: int = 12, L: int = 5, max_ops: i
         if seg:
             fill = [b for b in range(L, n) if b not in hi]
             bits = list(range(L)) + sorted(list(hi) + fill[: free - len(hi)])
+            if round_budget is not None and len(bits) == T and len(bits) > RB \
+                    and not any(p.kind == SWAP for p in seg):
+                rounds, left = schedule_rounds_budget(seg, bits, RB, sww, round_budget)
+                if left and len(left) < len(seg):
+                    drop = {id(p) for p in left}
+                    seg = [p for p in seg if id(p) not in drop]
+                    order = {id(p): i for i, p in enumerate(remaining)}
+                    keep = sorted(keep + left, key=lambda p: order[id(p)])
+                    left = []
+                if not left:
+                    segments.append(Segment(bits, seg, sum(p.ngates for p in seg), rounds))
+                    remaining = keep
+                    continue
             segments.append(Segment(bits, seg, sum(p.ngates for p in seg)))
         remaining = keep
     return segments
 
 
 def compile_ops(ops_, n: int, bit_of=None, level: int = 1, T: int = 12, L: int = 5,
-                batched_ok: bool = False, fold_cx: bool = True):
+                batched_ok: bool = False, fold_cx: bool = True, round_budget: int | None = None,
+                RB: int = 4, sww: int = 3):
     """Operators -> list of :class:`Segment`."""
     if bit_of is None:
         bit_of = lambda w: n - 1 - int(w)          # noqa: E731
@@ -482,7 +502,7 @@ def compile_ops(ops_, n: int, bit_of=None, level: int = 1, T: int = 12, L: int =
     for op in ops_:
         prims.extend(lower(op, bit_of, batched_ok))
     prims = merge_blocks(prims, level, fold_cx)
-    return pack_segments(prims, n, T=T, L=L)
+    return pack_segments(prims, n, T=T, L=L, round_budget=round_budget, RB=RB, sww=sww)
 
 
 def _expand_select(prims):
@@ -637,11 +657,160 @@ def schedule_rounds(prims, tile_bits, RB: int, sww: int = 3):
 
     A primitive can run in a round when all its targets are register bits of that round and no
     earlier unscheduled primitive shares a bit with it.  The first and last rounds are "IO
-    rounds": their register bits avoid tile positions 0..4, which stay on the lanes."""
+    rounds": their register bits avoid tile positions 0..4, which stay on the lanes.
+
+    Two list schedulers are tried and the one with fewer rounds wins: program order (the first
+    fit) and critical path first (the ready primitive with the longest chain of dependants picks
+    the next register bit) — on a CNOT ring the former spends register bits on single-qubit
+    blocks whose chain comes much later and revisits them (4 rounds for 12 targets), the latter
+    follows the chain (3)."""
+    a = _schedule_rounds_order(prims, tile_bits, RB, sww)
+    if len(a) <= 2:
+        return a
+    b = _schedule_rounds_critical(prims, tile_bits, RB, sww)
+    return b if len(b) < len(a) else a
+
+
+def _round_helpers(tile_bits, RB, sww):
     T = len(tile_bits)
-    pos = {b: i for i, b in enumerate(tile_bits)}
     lanes = min(_IO_LANES, T - RB)
     io_allowed = set(range(lanes, T))
+
+    def finish(R, io):
+        pool = [p for p in (sorted(io_allowed, reverse=True) if io else range(T - 1, -1, -1))
+                if p not in R]
+        R = list(R) + pool[: RB - len(R)]
+        free = [p for p in range(T) if p not in R]
+        return R, _thread_positions(free, sww, io)
+
+    return T, lanes, io_allowed, finish
+
+
+def _close_rounds(rounds, lanes, io_allowed, finish):
+    last = rounds[-1]
+    if any(r not in io_allowed for r in last.rpos) or last.tpos[:lanes] != list(range(lanes)):
+        R, tpos = finish([], True)
+        rounds.append(Round(R, tpos, []))
+    return rounds
+
+
+def schedule_rounds_budget(prims, tile_bits, RB: int, sww: int, max_rounds: int):
+    """At most ``max_rounds`` rounds (the last one IO-compatible): returns (rounds, leftover) where
+    ``leftover`` are the primitives, in their original order, that did not fit — a set closed
+    under "depends on", so the packer can hand them to a later segment."""
+    return _schedule_rounds_critical(prims, tile_bits, RB, sww, max_rounds)
+
+
+def _schedule_rounds_critical(prims, tile_bits, RB: int, sww: int = 3, max_rounds: int | None = None):
+    T, lanes, io_allowed, finish = _round_helpers(tile_bits, RB, sww)
+    pos = {b: i for i, b in enumerate(tile_bits)}
+    ps = _expand_swaps(prims)
+    n = len(ps)
+    bits = [p.bits for p in ps]
+    tpos_of = [[pos[b] for b in p.targets] for p in ps]
+    # immediate predecessors / successors through shared bits (global phases order with everything)
+    preds = [set() for _ in range(n)]
+    succs = [set() for _ in range(n)]
+    last_on: dict = {}
+    last_global = -1
+    for i in range(n):
+        if not bits[i]:
+            for j in range(i):
+                preds[i].add(j)
+            last_global = i
+        else:
+            for b in bits[i]:
+                if b in last_on:
+                    preds[i].add(last_on[b])
+                last_on[b] = i
+            if last_global >= 0:
+                preds[i].add(last_global)
+    for i in range(n):
+        for j in preds[i]:
+            succs[j].add(i)
+    height = [1] * n
+    for i in range(n - 1, -1, -1):
+        for j in succs[i]:
+            height[i] = max(height[i], 1 + height[j])
+    done = [False] * n
+    npred = [len(preds[i]) for i in range(n)]
+    left = n
+    rounds: list[Round] = []
+    first = True
+
+    def run_round(allowed, commit):
+        nonlocal left
+        d = list(done)
+        c = list(npred)
+        R, run = [], []
+        ready = sorted((i for i in range(n) if not d[i] and c[i] == 0), key=lambda i: (-height[i], i))
+        while True:
+            progressed = False
+            # everything that fits the current register set, in program order
+            for i in sorted(ready):
+                if all(t in R for t in tpos_of[i]):
+                    run.append(i)
+                    d[i] = True
+                    ready.remove(i)
+                    for j in succs[i]:
+                        c[j] -= 1
+                        if c[j] == 0:
+                            ready.append(j)
+                    progressed = True
+                    break
+            if progressed:
+                continue
+            # the ready primitive with the longest chain behind it picks the next register bits
+            for i in sorted(ready, key=lambda i: (-height[i], i)):
+                need = [t for t in tpos_of[i] if t not in R]
+                if all(t in allowed for t in tpos_of[i]) and len(R) + len(set(need)) <= RB:
+                    for t in need:
+                        if t not in R:
+                            R.append(t)
+                    progressed = True
+                    break
+            if not progressed:
+                break
+        if commit:
+            for i in run:
+                done[i] = True
+            for i in range(n):
+                npred[i] = c[i]
+            left -= len(run)
+        return R, run, sum(1 for x in d if not x)
+
+    while left or first:
+        closing = max_rounds is not None and len(rounds) == max_rounds - 1
+        if first:
+            allowed = set(range(min(sww, T - RB), T))
+            if closing:
+                allowed &= io_allowed
+            R, run, _ = run_round(allowed, True)
+            io = True
+        else:
+            R, run, rest = run_round(io_allowed, False)
+            if rest == 0 or closing:
+                R, run, _ = run_round(io_allowed, True)
+                io = True
+            else:
+                R, run, _ = run_round(set(range(T)), True)
+                io = all(r in io_allowed for r in R)
+        if not run and not first and not closing:
+            raise RuntimeError("round scheduling made no progress")   # pragma: no cover
+        Rf, tp = finish(R, io)
+        rounds.append(Round(Rf, tp, [ps[i] for i in run]))
+        first = False
+        if closing:
+            break
+    rounds = _close_rounds(rounds, lanes, io_allowed, finish)
+    if max_rounds is None:
+        return rounds
+    return rounds, [ps[i] for i in range(n) if not done[i]]
+
+
+def _schedule_rounds_order(prims, tile_bits, RB: int, sww: int = 3):
+    T, lanes, io_allowed, finish = _round_helpers(tile_bits, RB, sww)
+    pos = {b: i for i, b in enumerate(tile_bits)}
     remaining = _expand_swaps(prims)
     rounds: list[Round] = []
 
@@ -662,13 +831,6 @@ def schedule_rounds(prims, tile_bits, RB: int, sww: int = 3):
                 blocked |= pb
                 keep.append(p)
         return R, run, keep
-
-    def finish(R, io):
-        pool = [p for p in (sorted(io_allowed, reverse=True) if io else range(T - 1, -1, -1))
-                if p not in R]
-        R = list(R) + pool[: RB - len(R)]
-        free = [p for p in range(T) if p not in R]
-        return R, _thread_positions(free, sww, io)
 
     first = True
     while remaining or first:
@@ -691,11 +853,7 @@ def schedule_rounds(prims, tile_bits, RB: int, sww: int = 3):
         rounds.append(Round(R, tpos, run))
         remaining = keep
         first = False
-    last = rounds[-1]
-    if any(r not in io_allowed for r in last.rpos) or last.tpos[:lanes] != list(range(lanes)):
-        R, tpos = finish([], True)
-        rounds.append(Round(R, tpos, []))
-    return rounds
+    return _close_rounds(rounds, lanes, io_allowed, finish)
 
 
 def _swap_2q(m):

@@ -38,7 +38,14 @@
 //
 // This file is compiled by NVRTC only (no system headers).  "sk_config.inc" defines
 //   SK_REAL (float|double) SK_RB SK_TB SK_NV SK_L SK_MINB SK_NROUNDS SK_NCOEF SK_NSLOTS SK_NEXT
-//   SK_SWW SK_RPOS {{...},...} SK_TPOS {{...},...}
+//   SK_SWW SK_COEF_PARAM SK_RPOS {{...},...} SK_TPOS {{...},...}
+//
+// Coefficients.  SK_COEF_PARAM = 1: the table is a KERNEL PARAMETER (constant bank): every
+// coefficient is an immediate-like operand of the FP64 instruction that uses it — no load, no
+// register, no latency, and the pivot flags are uniform branches.  0 (tables larger than a few KB,
+// or one table per batch element): the table is copied to shared memory once per CTA and read
+// with volatile loads (the table is invariant over the tile loop and ptxas would otherwise hoist
+// the coefficients of every record into registers).
 #include "segk_args.h"
 #include "sk_config.inc"
 
@@ -133,18 +140,37 @@ __device__ __forceinline__ void sk_tma_load(void* dst_smem, const SkTensorMap* t
       break;
   }
 }
-// complex coefficient pair from the shared-memory table by 32-bit address.  volatile: the table
-// is invariant over the tile loop and ptxas would otherwise hoist the coefficients of every
-// record into registers (tools/micro/fp64_forms.cu: 128 registers + spills).
-__device__ __forceinline__ C sk_ldc(const unsigned addr) {
-  C r;
+struct SkCoef { real v[SK_NCOEF]; };
+
+// coefficient source (see the header): pair(i) = (table[i], table[i + 1])
+#if SK_COEF_PARAM
+struct Coefs {
+  const SkCoef& cf;
+  __device__ __forceinline__ C pair(const unsigned i) const { C r; r.x = cf.v[i]; r.y = cf.v[i + 1]; return r; }
+  __device__ __forceinline__ bool flag(const unsigned i) const {
 #if SK_IS_DOUBLE
-  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "r"(addr));
+    return __double2hiint(cf.v[i]) != 0;
 #else
-  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "r"(addr));
+    return __float_as_int(cf.v[i]) != 0;
 #endif
-  return r;
-}
+  }
+};
+#else
+struct Coefs {
+  unsigned base;          // shared-memory address of the table
+  __device__ __forceinline__ C pair(const unsigned i) const {
+    C r;
+    const unsigned addr = base + i * RSZ;
+#if SK_IS_DOUBLE
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "r"(addr));
+#else
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "r"(addr));
+#endif
+    return r;
+  }
+  __device__ __forceinline__ bool flag(const unsigned i) const { return pair(i - 1).y != (real)0; }
+};
+#endif
 
 __device__ __forceinline__ C sk_cmul(const C a, const C b) {
   C r;
@@ -196,12 +222,17 @@ __device__ __forceinline__ void sk_dk_body(C (&A)[NV][NA], const real t, const C
   }
 }
 template <int Q, int KERN, bool DL, bool DR>
-__device__ __forceinline__ void sk_dk(C (&A)[NV][NA], const unsigned ca) {
-  const C tf = sk_ldc(ca);
+__device__ __forceinline__ void sk_dk(C (&A)[NV][NA], const Coefs& cs, const unsigned off) {
+  const C tf = cs.pair(off);
   C r = {1, 0}, l = {1, 0};
-  if (DR) r = sk_ldc(ca + 2 * RSZ);
-  if (DL) l = sk_ldc(ca + (DR ? 4 : 2) * RSZ);
-  if (tf.y == (real)0) sk_dk_body<Q, KERN, DL, DR, false>(A, tf.x, r, l);
+  if (DR) r = cs.pair(off + 2);
+  if (DL) l = cs.pair(off + (DR ? 4 : 2));
+#if SK_COEF_PARAM
+  const bool sinp = cs.flag(off + 1);
+#else
+  const bool sinp = tf.y != (real)0;
+#endif
+  if (!sinp) sk_dk_body<Q, KERN, DL, DR, false>(A, tf.x, r, l);
   else sk_dk_body<Q, KERN, DL, DR, true>(A, tf.x, r, l);
 }
 
@@ -236,11 +267,11 @@ __device__ __forceinline__ void sk_matvec(C (&A)[NA], const int (&ix)[D], const 
 // compile time; `pred`: the thread / external part of the controls.  HAS0: a second matrix (at
 // ca + 8 reals) acts where the controls fail (controlled-select), else those pairs are skipped.
 template <int Q, unsigned CR, unsigned CV, bool HAS0>
-__device__ __forceinline__ void sk_f16(C (&A)[NV][NA], const unsigned ca, const bool pred) {
+__device__ __forceinline__ void sk_f16(C (&A)[NV][NA], const Coefs& cs, const unsigned off, const bool pred) {
   if (HAS0 || pred) {
     {
-      const unsigned a1 = (HAS0 && !pred) ? ca + 8 * RSZ : ca;
-      const C m[4] = {sk_ldc(a1), sk_ldc(a1 + 2 * RSZ), sk_ldc(a1 + 4 * RSZ), sk_ldc(a1 + 6 * RSZ)};
+      const unsigned a1 = (HAS0 && !pred) ? off + 8 : off;
+      const C m[4] = {cs.pair(a1), cs.pair(a1 + 2), cs.pair(a1 + 4), cs.pair(a1 + 6)};
 #pragma unroll
       for (int k = 0; k < NA; ++k) {
         if (((k >> Q) & 1) || ((unsigned)k & CR) != CV) continue;
@@ -250,8 +281,8 @@ __device__ __forceinline__ void sk_f16(C (&A)[NV][NA], const unsigned ca, const 
       }
     }
     if (HAS0 && CR != 0u) {
-      const unsigned a0 = ca + 8 * RSZ;
-      const C m[4] = {sk_ldc(a0), sk_ldc(a0 + 2 * RSZ), sk_ldc(a0 + 4 * RSZ), sk_ldc(a0 + 6 * RSZ)};
+      const unsigned a0 = off + 8;
+      const C m[4] = {cs.pair(a0), cs.pair(a0 + 2), cs.pair(a0 + 4), cs.pair(a0 + 6)};
 #pragma unroll
       for (int k = 0; k < NA; ++k) {
         if (((k >> Q) & 1) || ((unsigned)k & CR) == CV) continue;
@@ -266,7 +297,7 @@ __device__ __forceinline__ void sk_f16(C (&A)[NV][NA], const unsigned ca, const 
 // General 4x4 block on register bits Q0 (matrix MSB) > Q1, controls as sk_f16.  The 16 entries
 // are re-read per quad (64 registers of amplitudes leave no room to pin them).
 template <int Q0, int Q1, unsigned CR, unsigned CV>
-__device__ __forceinline__ void sk_d2(C (&A)[NV][NA], const unsigned ca, const bool pred) {
+__device__ __forceinline__ void sk_d2(C (&A)[NV][NA], const Coefs& cs, const unsigned off, const bool pred) {
   if (pred) {
 #pragma unroll
     for (int k = 0; k < NA; ++k) {
@@ -276,7 +307,7 @@ __device__ __forceinline__ void sk_d2(C (&A)[NV][NA], const unsigned ca, const b
       for (int v = 0; v < NV; ++v) {
         C m[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) m[i] = sk_ldc(ca + 2 * i * RSZ);
+        for (int i = 0; i < 16; ++i) m[i] = cs.pair(off + 2 * i);
         sk_matvec<4>(A[v], ix, m);
       }
     }
@@ -310,11 +341,12 @@ __device__ __forceinline__ void sk_cx(C (&A)[NV][NA], const bool pred) {
 // on the host (uncontrolled phases; the quotient is part of the segment scalar) and only m1 is
 // in the table.
 template <unsigned CR, unsigned CV, unsigned PR, bool RTPAR, bool NORM>
-__device__ __forceinline__ void sk_par(C (&A)[NV][NA], const unsigned ca, const bool cpred, const unsigned par_rt) {
+__device__ __forceinline__ void sk_par(C (&A)[NV][NA], const Coefs& cs, const unsigned off, const bool cpred,
+                                       const unsigned par_rt) {
   if (cpred) {
     C me = {1, 0}, mo;
-    if (NORM) mo = sk_ldc(ca);
-    else { me = sk_ldc(ca); mo = sk_ldc(ca + 2 * RSZ); }
+    if (NORM) mo = cs.pair(off);
+    else { me = cs.pair(off); mo = cs.pair(off + 2); }
     if (RTPAR) {
       const C a = me, b = mo;
       me.x = par_rt ? b.x : a.x; me.y = par_rt ? b.y : a.y;
@@ -334,16 +366,16 @@ __device__ __forceinline__ void sk_par(C (&A)[NV][NA], const unsigned ca, const 
 // Diagonal table: amp *= tab[i0 | KI(k)], KI(k) = OR of the contributions RCb of the register
 // bits set in k (compile time), i0 = the thread / external part.
 template <unsigned RC0, unsigned RC1, unsigned RC2, unsigned RC3, unsigned RC4>
-__device__ __forceinline__ void sk_diag(C (&A)[NV][NA], const unsigned ca, const unsigned i0) {
+__device__ __forceinline__ void sk_diag(C (&A)[NV][NA], const Coefs& cs, const unsigned off, const unsigned i0) {
   constexpr unsigned rc[5] = {RC0, RC1, RC2, RC3, RC4};
-  const unsigned base = ca + i0 * 2u * RSZ;
+  const unsigned base = off + i0 * 2u;
 #pragma unroll
   for (int k = 0; k < NA; ++k) {
     unsigned ki = 0;
 #pragma unroll
     for (int b = 0; b < RB; ++b)
       if ((k >> b) & 1) ki |= rc[b];
-    const C d = sk_ldc(base + ki * 2u * RSZ);
+    const C d = cs.pair(base + ki * 2u);
 #pragma unroll
     for (int v = 0; v < NV; ++v) A[v][k] = sk_cmul(d, A[v][k]);
   }
@@ -351,8 +383,8 @@ __device__ __forceinline__ void sk_diag(C (&A)[NV][NA], const unsigned ca, const
 
 // every amplitude times the scalar at `ca` (the product of the scalars the normalised records of
 // this segment left out)
-__device__ __forceinline__ void sk_scale(C (&A)[NV][NA], const unsigned ca) {
-  const C s = sk_ldc(ca);
+__device__ __forceinline__ void sk_scale(C (&A)[NV][NA], const Coefs& cs, const unsigned off) {
+  const C s = cs.pair(off);
 #pragma unroll
   for (int v = 0; v < NV; ++v)
 #pragma unroll
@@ -364,8 +396,8 @@ __device__ __forceinline__ void sk_scale(C (&A)[NV][NA], const unsigned ca) {
 // register bits; `tpar`: parity of the thread / external Z part (+ the i^2 of two Y factors);
 // ODD: an odd number of Y factors (the term is i * real Pauli: take Re instead of Im).
 template <unsigned XR, unsigned ZR, bool ODD, int SLOT>
-__device__ __forceinline__ void sk_gen(const C (&A)[NV][NA], const unsigned ca, const unsigned tpar,
-                                       double* accs, const unsigned tid) {
+__device__ __forceinline__ void sk_gen(const C (&A)[NV][NA], const Coefs& cs, const unsigned off,
+                                       const unsigned tpar, double* accs, const unsigned tid) {
   double acc = 0.0;
 #pragma unroll
   for (int k = 0; k < NA; ++k) {
@@ -376,7 +408,7 @@ __device__ __forceinline__ void sk_gen(const C (&A)[NV][NA], const unsigned ca, 
     if (__popc((unsigned)(k ^ XR) & ZR) & 1) acc -= val;
     else acc += val;
   }
-  const C cf = sk_ldc(ca);
+  const C cf = cs.pair(off);
   acc *= tpar ? -(double)cf.x : (double)cf.x;
   acc = sk_warp_sum(acc);
   if ((tid & 31u) == 0) accs[SLOT * NW + (tid >> 5)] += acc;
@@ -413,7 +445,7 @@ __device__ __forceinline__ void sk_fetch(const SkArgs& a, C* const (&vec)[2], C*
         if (a.tma_len[r]) c[r] = (int)((base >> a.tma_lo[r]) & ((1ull << a.tma_len[r]) - 1ull));
       sk_mbar_expect_tx(bar, bytes);
 #pragma unroll
-      for (int v = 0; v < NV; ++v) sk_tma_load(tile + ((size_t)v << T), tm + v, a.tma_rank, c, bar);
+      for (int v = 0; v < NV; ++v) sk_tma_load(tile + ((unsigned long long)v << T), tm + v, a.tma_rank, c, bar);
     }
   } else {
     if (tid == 0) sk_mbar_expect_tx(bar, bytes);
@@ -421,7 +453,7 @@ __device__ __forceinline__ void sk_fetch(const SkArgs& a, C* const (&vec)[2], C*
     const unsigned long long base = sk_tile_base(a, t);
     for (unsigned j = tid; j < (unsigned)NV << (T - L); j += THREADS) {
       const unsigned v = j >> (T - L), r = j & ((1u << (T - L)) - 1u);
-      sk_bulk_g2s(tile + ((size_t)v << T) + ((size_t)r << L), vec[v] + base + sk_gscatter(r << L, a),
+      sk_bulk_g2s(tile + ((unsigned long long)v << T) + ((unsigned long long)r << L), vec[v] + base + sk_gscatter(r << L, a),
                   (unsigned)sizeof(C) << L, bar);
     }
   }
@@ -465,34 +497,49 @@ __device__ __forceinline__ void sk_xpose(C (&A)[NV][NA], C* tile, const unsigned
 #define SK_LOAD(R) sk_load<R>(A, tile, sk_tj<R>(tid));
 #define SK_XPOSE(R0, R1) sk_xpose<R0, R1>(A, tile, tid);
 #define SK_FETCH_NEXT() if (more) sk_fetch(a, vec, tile, t + gridDim.x, bar, tm, tid);
-#define SK_COEF(off) (coef_s + (unsigned)(off) * RSZ)
+#define SK_COEF(off) cs, (unsigned)(off)
 #define SK_TBIT(b) ((tid >> (b)) & 1u)
 #define SK_EBIT(e) ((ext >> (e)) & 1u)
 
 extern "C" __global__ void __launch_bounds__(1 << SK_TB, SK_MINB)
 sk_kernel(const __grid_constant__ SkArgs a, C* __restrict__ v0, C* __restrict__ v1,
           const double* __restrict__ coef_g, const long long coef_bstride,
-          const SkTensorMap* __restrict__ tm, double* __restrict__ partials) {
+          const SkTensorMap* __restrict__ tm, double* __restrict__ partials
+#if SK_COEF_PARAM
+          , const __grid_constant__ SkCoef cf
+#endif
+          ) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   C* tile = reinterpret_cast<C*>(smem_raw);                                            // NV << T
-  real* coef = reinterpret_cast<real*>(tile + ((size_t)NV << T));                     // SK_NCOEF
+#if SK_COEF_PARAM
+  unsigned long long* koff = reinterpret_cast<unsigned long long*>(tile + ((unsigned long long)NV << T));   // NA
+#else
+  real* coef = reinterpret_cast<real*>(tile + ((unsigned long long)NV << T));           // SK_NCOEF
   unsigned long long* koff = reinterpret_cast<unsigned long long*>(coef + SK_NCOEF);   // NA
+#endif
   unsigned long long* bar = koff + NA;                                                 // 1
   double* accs = reinterpret_cast<double*>(bar + 1);                                   // NSLOTS * NW
   const unsigned tid = threadIdx.x;
 
   {
+#if !SK_COEF_PARAM
     const double* cg = coef_g + (long long)blockIdx.y * coef_bstride;
     for (int i = tid; i < SK_NCOEF; i += THREADS) coef[i] = (real)cg[i];
+#endif
     for (int i = tid; i < SK_NSLOTS * NW; i += THREADS) accs[i] = 0.0;
     if (tid < NA) koff[tid] = sk_gscatter(sk_kj(SK_NROUNDS - 1, (int)tid), a);
     if (tid == 0) sk_mbar_init(bar, 1);
   }
   __syncthreads();
-  const unsigned coef_s = sk_smem_u32(coef);
+#if SK_COEF_PARAM
+  const Coefs cs = {cf};
+#else
+  const Coefs cs = {sk_smem_u32(coef)};
+#endif
   C* const vec[2] = {v0 + ((unsigned long long)blockIdx.y << a.n),
                      NV > 1 ? v1 + ((unsigned long long)blockIdx.y << a.n) : nullptr};
   const unsigned long long toff_st = sk_gscatter(sk_tj<SK_NROUNDS - 1>(tid), a);
+  const unsigned koff_s = sk_smem_u32(koff);
 
   if (blockIdx.x < a.ntiles) sk_fetch(a, vec, tile, blockIdx.x, bar, tm, tid);
   unsigned phase = 0;
@@ -518,7 +565,11 @@ sk_kernel(const __grid_constant__ SkArgs a, C* __restrict__ v0, C* __restrict__ 
       if (v == 0 && NV > 1 && !a.write0) continue;
       C* dst = vec[v] + base + toff_st;
 #pragma unroll
-      for (int k = 0; k < NA; ++k) dst[koff[k]] = A[v][k];
+      for (int k = 0; k < NA; ++k) {
+        unsigned long long ko;     // volatile: 2^RB 64-bit offsets must not be hoisted out of the tile loop
+        asm volatile("ld.shared.u64 %0, [%1];" : "=l"(ko) : "r"(koff_s + 8u * k));
+        dst[ko] = A[v][k];
+      }
     }
   }
 
@@ -527,7 +578,7 @@ sk_kernel(const __grid_constant__ SkArgs a, C* __restrict__ v0, C* __restrict__ 
     for (int s = tid; s < SK_NSLOTS; s += THREADS) {
       double acc = 0.0;
       for (int w = 0; w < NW; ++w) acc += accs[s * NW + w];
-      partials[((size_t)blockIdx.y * SK_NSLOTS + s) * gridDim.x + blockIdx.x] = acc;
+      partials[((unsigned long long)blockIdx.y * SK_NSLOTS + s) * gridDim.x + blockIdx.x] = acc;
     }
   }
 }

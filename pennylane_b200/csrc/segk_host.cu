@@ -206,7 +206,7 @@ int b200q_seg_unload(void* handle) {
 
 int b200q_seg_launch(void* handle, void* vec0, void* vec1, int n, int dtype, int64_t batch,
                      const int* tile_bits, int T, int L, int RB, int minb, const int* ext_pos, int n_ext,
-                     const double* coef_host, int n_coef, int coef_batched, int nslots, int write0,
+                     const double* coef_host, int n_coef, int coef_mode, int nslots, int write0,
                      uint64_t base_hi, double scale, double* out_dev, void* work, size_t work_bytes,
                      void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
@@ -254,18 +254,23 @@ int b200q_seg_launch(void* handle, void* vec0, void* vec1, int n, int dtype, int
   static const int tma_knob = getenv("B200Q_RT_TMA") ? atoi(getenv("B200Q_RT_TMA")) : 1;     // tuning knob
   if (tma_knob && batch == 1) sk_build_tile_maps(a, n, dtype, inmask, L, vec0, vec1, tm);
   // workspace: [coefficients | ... | tensor maps (last 512 bytes of the table region) | partial sums]
-  const size_t coef_bytes = (size_t)n_coef * sizeof(double) * (coef_batched ? (size_t)batch : 1);
+  // coef_mode 0: one table, copied to shared memory by the kernel; 1: one table per batch
+  // element; 2: the table is a kernel parameter (the kernel was compiled with SK_COEF_PARAM)
+  const bool coef_batched = coef_mode == 1, coef_param = coef_mode == 2;
+  B200Q_REQUIRE(coef_mode >= 0 && coef_mode <= 2, "seg_launch: bad coef_mode %d", coef_mode);
+  const size_t coef_bytes = coef_param ? 0 : (size_t)n_coef * sizeof(double) * (coef_batched ? (size_t)batch : 1);
   B200Q_REQUIRE(work && coef_bytes + 1024 <= kTermRegion && work_bytes >= kWorkBytes,
                 "seg_launch: coefficient table too large for the workspace");
+  B200Q_REQUIRE(!coef_param || (size_t)n_coef * (elem / 2) <= 4000, "seg_launch: parameter table too large");
   char* w = (char*)work;
-  B200Q_CHECK(cudaMemcpyAsync(w, coef_host, coef_bytes, cudaMemcpyHostToDevice, s));
+  if (!coef_param) B200Q_CHECK(cudaMemcpyAsync(w, coef_host, coef_bytes, cudaMemcpyHostToDevice, s));
   const size_t tm_off = kTermRegion - 512;
   if (a.tma_rank > 0) B200Q_CHECK(cudaMemcpyAsync(w + tm_off, tm, sizeof(tm), cudaMemcpyHostToDevice, s));
   double* partials = (double*)(w + kTermRegion);
   const size_t pcap = (work_bytes - kTermRegion) / sizeof(double);
   const int threads = 1 << (T - RB);
   const size_t real_b = elem / 2;
-  const size_t smem = ((size_t)NV * elem << T) + (size_t)n_coef * real_b + ((size_t)(1 << RB) + 1) * 8 +
+  const size_t smem = ((size_t)NV * elem << T) + (coef_param ? 0 : (size_t)n_coef * real_b) + ((size_t)(1 << RB) + 1) * 8 +
                       (size_t)nslots * (threads / 32) * sizeof(double) + 64;
   B200Q_REQUIRE(smem <= 227 * 1024, "seg_launch: %zu bytes of shared memory needed", smem);
   uint64_t per_sm = std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)std::max(minb, 1), (227 * 1024) / smem));
@@ -279,7 +284,15 @@ int b200q_seg_launch(void* handle, void* vec0, void* vec1, int n, int dtype, int
   const double* coef_dev = (const double*)w;
   long long bstride = coef_batched ? n_coef : 0;
   const void* tm_dev = w + tm_off;
-  void* args[] = {&a, &vec0, &vec1, &coef_dev, &bstride, &tm_dev, &partials};
+  // parameter table in the kernel's precision (ignored by kernels compiled without SK_COEF_PARAM)
+  std::vector<double> cf64;
+  std::vector<float> cf32;
+  void* cf_arg = (void*)coef_host;
+  if (coef_param && dtype == B200Q_C64) {
+    cf32.assign(coef_host, coef_host + n_coef);
+    cf_arg = cf32.data();
+  }
+  void* args[] = {&a, &vec0, &vec1, &coef_dev, &bstride, &tm_dev, &partials, cf_arg};
   B200Q_CHECK(cudaLaunchKernel((const void*)k->kern, grid, dim3(threads), args, smem, s));
   if (nslots > 0) {
     k_sk_final_reduce<<<(unsigned)(batch * nslots), 256, 0, s>>>(partials, out_dev, (int)grid.x, scale);

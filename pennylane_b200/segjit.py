@@ -40,6 +40,8 @@ _CSRC = os.path.join(_HERE, "csrc")
 #: |phase - 1| below this is treated as exactly 1 (the record then skips the multiplication);
 #: the relative error this leaves is far below the 1e-12 parity bar
 PHASE_TOL = 1e-15
+#: coefficient tables up to this size travel as a kernel parameter (constant bank operands)
+COEF_PARAM_MAX_BYTES = 3072
 #: a 2x2 block is normalised only when it is unitary to this tolerance (else the plain product)
 UNITARY_TOL = 1e-12
 
@@ -153,6 +155,10 @@ class Geometry:
 def default_geometry(dtype_code: int, nv: int = 1) -> Geometry:
     """Forward: T = 12 (c128) / 13 (c64), 256 threads, 2 CTAs per SM.  Adjoint (two vectors per
     thread): one register bit fewer, 512 threads, 1 CTA per SM (B200Q_SK_ADJ=1: 256 x 2)."""
+    env = os.environ.get("B200Q_SK_FWD" if nv == 1 else "B200Q_SK_ADJGEOM")     # tuning knob: "RB,TB,MINB"
+    if env:
+        rb, tb, minb = (int(x) for x in env.split(","))
+        return Geometry(dtype_code, rb + (0 if dtype_code else 1), tb, nv, minb)
     if nv == 1:
         return Geometry(dtype_code, 4 if dtype_code else 5, 8, 1, 2)
     if int(os.environ.get("B200Q_SK_ADJ", "0")):
@@ -176,6 +182,7 @@ class SegPlan:
     body: str = ""
     key: str = ""
     slot_params: list = field(default_factory=list)   # slot -> trainable parameter index
+    coef_param: bool = False          # the coefficient table is a kernel parameter (constant bank)
 
 
 class FormMismatch(Exception):
@@ -242,7 +249,7 @@ def plan_segment(seg, geom: Geometry, L: int, forms_hint=None, final_scale: bool
     tile_bits = list(seg.tile_bits)
     assert len(tile_bits) == geom.T
     RB, TB = geom.RB, geom.TB
-    rounds = cc.schedule_rounds(seg.prims, tile_bits, RB, geom.sww)
+    rounds = getattr(seg, "rounds", None) or cc.schedule_rounds(seg.prims, tile_bits, RB, geom.sww)
     bld = _Builder(geom, tile_bits, L)
     index_of = {id(p): i for i, p in enumerate(seg.prims)}
     nrounds = len(rounds)
@@ -345,6 +352,8 @@ def plan_segment(seg, geom: Geometry, L: int, forms_hint=None, final_scale: bool
     plan = SegPlan(geom, L, tile_bits, [(list(r.rpos), list(r.tpos)) for r in rounds], bld.ir,
                    list(bld.ext), max(2, bld.ncoef), len(slot_params), bld.fill, bld.forms,
                    slot_params=slot_params)
+    real_bytes = 8 if geom.dtype_code else 4
+    plan.coef_param = (not batched) and plan.ncoef * real_bytes <= COEF_PARAM_MAX_BYTES
     plan.config = emit_config(plan)
     plan.body = emit_body(plan)
     plan.key = hashlib.sha256((plan.config + "\n//--\n" + plan.body).encode()).hexdigest()
@@ -482,6 +491,7 @@ def emit_config(plan: SegPlan) -> str:
         f"#define SK_NROUNDS {len(plan.rounds)}", f"#define SK_NCOEF {plan.ncoef}",
         f"#define SK_NSLOTS {plan.nslots}", f"#define SK_NEXT {len(plan.ext_pos)}",
         f"#define SK_SWW {g.sww}",
+        f"#define SK_COEF_PARAM {1 if plan.coef_param else 0}",
         f"#define SK_RPOS {_arr2([r for r, _ in plan.rounds])}",
         f"#define SK_TPOS {_arr2([t for _, t in plan.rounds])}",
     ]
@@ -695,5 +705,6 @@ def launch(plan: SegPlan, coefs: np.ndarray, vec0_ptr, vec1_ptr, n: int, batch: 
     check(lib.b200q_seg_launch(
         h, vec0_ptr, vec1_ptr, n, g.dtype_code, batch, int_array(plan.tile_bits), g.T, plan.L, g.RB,
         g.MINB, int_array(plan.ext_pos) if plan.ext_pos else None, len(plan.ext_pos),
-        coefs.ctypes.data_as(C.POINTER(C.c_double)), int(coefs.shape[-1]), 1 if batched else 0,
+        coefs.ctypes.data_as(C.POINTER(C.c_double)), int(coefs.shape[-1]),
+        (2 if plan.coef_param else 1 if batched else 0),
         plan.nslots, write0, int(base_hi), float(scale), out_ptr, work, work_bytes, stream))

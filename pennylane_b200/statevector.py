@@ -372,6 +372,11 @@ class StateVector:
     # ---- fused execution (host fusion pass + tile kernels) ------------------------------------
     def rt_geometry(self, nvec: int = 1):
         """(T, RB, threads) of the register-tiled kernel for this dtype (b200q_rtile_geometry)."""
+        if self.jit_enabled(nvec):
+            from . import segjit
+
+            g = segjit.default_geometry(self.dtype_code, nvec)
+            return g.T, g.RB, 1 << g.TB
         key = (self.dtype_code, nvec)
         if key not in _RT_GEOM:
             T, RB, th = C.c_int(), C.c_int(), C.c_int()
@@ -413,13 +418,19 @@ class StateVector:
     def compile_fused(self, ops_, level: int = 1, T: int | None = None, L: int | None = None,
                       bit_of=None):
         """Operators -> segments for this state (host fusion pass, compiler.py)."""
+        import os
+
         from .compiler import compile_ops
 
         dT, dL = self.default_tile()
         rtT, _, _ = self.rt_geometry(1)
         jit = self.jit_enabled(1) and (T or dT) == rtT
+        budget = None
+        if jit:
+            budget = int(os.environ.get("B200Q_ROUND_BUDGET", 0)) or None      # tuning knob
         return compile_ops(ops_, self.n, bit_of=bit_of, level=level, T=T or dT, L=L if L is not None else dL,
-                           batched_ok=(T or dT) == rtT and self.n >= rtT, fold_cx=not jit)
+                           batched_ok=(T or dT) == rtT and self.n >= rtT, fold_cx=not jit,
+                           round_budget=budget, RB=self.rt_geometry(1)[1], sww=3 if self.dtype_code else 4)
 
     def apply_operations_fused(self, ops_, level: int = 1, T: int | None = None,
                                L: int | None = None, bit_of=None):

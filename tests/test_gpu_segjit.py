@@ -116,3 +116,54 @@ def test_external_predicates_with_rank_bits():
             assert seg.tile_bits is not None
             sv.run_segment(seg, base_hi=rank << n_loc)
         assert np.max(np.abs(sv.to_numpy().reshape(-1) - ref[rank])) < 1e-12
+
+
+@pytest.mark.parametrize("dtype,tol", [(np.complex128, 1e-12), (np.complex64, 2e-5)])
+@pytest.mark.parametrize("n,seed,level", [(13, 1, 1), (14, 2, 1), (13, 3, 0)])
+def test_adjoint_jacobian_matches_oracle(dtype, tol, n, seed, level):
+    """Fused reverse sweep through the specialised kernels (two vectors per thread, generator
+    inner products in the same pass) against the oracle's adjoint_jacobian."""
+    from oracle import adjoint_jacobian as o_adj
+    from oracle import simulate as o_sim
+    from pennylane_b200 import adjoint
+    from test_compiler import _trainable_circuit
+
+    ops_ = _trainable_circuit(n, 90, seed=seed)
+    obs = [q.PauliZ(wires=0) @ q.PauliX(wires=2), q.PauliY(wires=n - 1)]
+    tape = qb.QuantumScript(ops_, [qb.expval(o) for o in obs])
+    st, _ = o_sim.get_final_state(tape)
+    ref = np.array(o_adj.adjoint_jacobian(tape, st), dtype=float)
+    jac = np.array(adjoint.adjoint_jacobian(tape, dtype=dtype, fusion=max(level, 1) if level else 1), dtype=float)
+    assert jac.shape == ref.shape
+    assert np.max(np.abs(jac - ref)) < tol          # 1e-12 (c128) / 2e-5 (c64)
+
+
+def test_adjoint_of_the_ansatz_and_split_parameters(monkeypatch):
+    """The benchmark tape at 16 qubits, and a small record budget so that the generator terms of
+    some parameters straddle segments (the slot sums must be added)."""
+    import bench
+    from oracle import adjoint_jacobian as o_adj
+    from oracle import simulate as o_sim
+    from pennylane_b200 import adjoint
+
+    tape = bench.hea_tape(16, 3)
+    st, _ = o_sim.get_final_state(tape)
+    ref = np.array(o_adj.adjoint_jacobian(tape, st), dtype=float)
+    jac = np.array(adjoint.adjoint_jacobian(tape, fusion=1), dtype=float)
+    assert np.max(np.abs(jac - ref)) < 1e-12
+    n = 13
+    rng = np.random.default_rng(5)
+    ops_ = []
+    for _ in range(20):
+        a, b = (int(x) for x in rng.permutation(n)[:2])
+        ops_ += [q.RY(rng.uniform(0, 6), wires=a), q.IsingXY(rng.uniform(0, 6), wires=[a, b]),
+                 q.PhaseShift(rng.uniform(0, 6), wires=b)]
+    tape = qb.QuantumScript(ops_, [qb.expval(q.PauliZ(wires=0) @ q.PauliY(wires=3))])
+    st, _ = o_sim.get_final_state(tape)
+    ref = np.array(o_adj.adjoint_jacobian(tape, st), dtype=float)
+    monkeypatch.setattr(adjoint, "MAX_SEGMENT_OPS", 3)
+    jac = np.array(adjoint.adjoint_jacobian(tape, fusion=1), dtype=float)
+    assert np.max(np.abs(jac - ref)) < 1e-12
+    monkeypatch.setenv("B200Q_JIT", "0")             # same split through the record interpreter
+    jac = np.array(adjoint.adjoint_jacobian(tape, fusion=1), dtype=float)
+    assert np.max(np.abs(jac - ref)) < 1e-12
