@@ -173,7 +173,7 @@ def cpu_baseline_sample(n_full, n_twin=26, gates_per_kind=8, repeat=1):
     desc = (f"oracle (numpy restatement of default.qubit apply_operation) on a {n_twin}-qubit twin: "
             f"{len(ops_)} gates (RY, RZ, ring CNOT on {gates_per_kind} spread wires) in {best:.2f} s "
             f"= {gps_twin:.3f} gates/s; extrapolated x2 per qubit (/{scale:.0f}) to {n_full} qubits")
-    return gps_twin / scale, desc, cores, best
+    return gps_twin / scale, desc, cores, best, n_twin
 
 
 # --------------------------------------------------------------------------------------------
@@ -186,10 +186,10 @@ def run_reference(args):
     n_full = args.qubits + int(np.log2(args.gpus))
     vals, last = [], None
     for i in range(args.warmup + args.steps):
-        v, desc, cores, dt = cpu_baseline_sample(n_full, gates_per_kind=4 if args.quick else 8)
+        v, desc, cores, dt, n_twin = cpu_baseline_sample(n_full, gates_per_kind=4 if args.quick else 8)
         if i >= args.warmup:
             vals.append((v, dt))
-        last = (desc, cores)
+        last = (desc, cores, n_twin)
     value = float(np.mean([v for v, _ in vals]))
     ms = float(np.mean([dt for _, dt in vals]) * 1e3)
     line = {
@@ -197,7 +197,11 @@ def run_reference(args):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "c128",
         "data": "synthetic",
-        "config": workload_config(args, n_full),
+        "config": dict(workload_config(args, n_full),
+                       measured_on=f"{last[2]}-qubit twin of the circuit (RY, RZ, ring CNOT on spread wires), "
+                                   "gates/s divided by 2 per missing qubit (BASELINE.md section 3); "
+                                   "ms_per_step is the twin's time",
+                       reference_twin_qubits=last[2], extrapolation_factor=float(2.0 ** (n_full - last[2]))),
         "cpu_baseline": {"value": value, "unit": "gates/s", "cores": last[1], "kind": "port",
                          "sample": last[0]},
         "e2e": {"value": value, "unit": "gates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -267,9 +271,14 @@ def run_ours(args):
     launches = 0
 
     fused_segments = None
+    use_program = False
     if args.fusion == "on":
-        fused_segments = sv.compile_fused(ops_, level=args.fusion_level)
-        sv.prepare_segments(fused_segments)
+        from pennylane_b200 import program as _program
+        prog, _ = _program.get_program(sv, ops_, args.fusion_level)
+        if prog is not None:
+            fused_segments, use_program = prog.segs, True      # specialised kernels (segk.cuh)
+        else:
+            fused_segments = sv.compile_fused(ops_, level=args.fusion_level)
 
     def forward(record):
         nonlocal launches
@@ -277,11 +286,21 @@ def run_ours(args):
         launches += 2
         if fused_segments is not None:
             S2 = 2.0 * 16 * (1 << n)
-            for seg in fused_segments:
+            if use_program:
+                # what execute() does on a structure it has seen: rebind the parameter values
+                # (host, ~4 ms, overlapped with the device) and launch the cached kernels
+                pg, _hit = _program.get_program(sv, ops_, args.fusion_level)
+                items = list(zip(pg.segs, pg.plans, pg.tables))
+            else:
+                items = [(seg, None, None) for seg in fused_segments]
+            for seg, plan, tab in items:
                 if record:
                     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
                     e0.record()
-                sv.run_segment(seg)
+                if plan is not None:
+                    sv._launch_plan(plan, tab)
+                else:
+                    sv.run_segment(seg)
                 launches += 1
                 if record:
                     e1.record()
@@ -345,7 +364,9 @@ def run_ours(args):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
-    kernel_of = {"tile_segment": "k_rtile<double,4,1,256,2> (fused segment: 2*S per launch)",
+    kernel_of = {"tile_segment": ("sk_kernel (csrc/segk.cuh: structure-specialised fused segment, NVRTC; "
+                                  "2*S per launch)" if use_program else
+                                  "k_rtile<double,4,1,256,2> (fused segment: 2*S per launch)"),
                  "RY": "k_dense<double,1,byval>", "RZ": "k_parity_phase<double>",
                  "CNOT": "k_dense<double,1,byval> (1 control)"}
     all_gate_bytes = sum(v["bytes"] for k, v in fam_stats.items() if k != "expval")
@@ -412,6 +433,25 @@ def run_ours(args):
             meas[name] = {"kernel": kern, "launches": len(calls), "gbps": gb, "frac": gb / peak}
         roofline["measurement_kernels"] = meas
 
+    # Closed-form check at FULL size through the same fused path (nothing else pins correctness
+    # above the ~24 qubits the oracle can hold): RY(theta_w) on every wire, then a CNOT chain
+    # 0 -> 1 -> ... -> n-1: <Z_k> = prod_{j <= k} cos(theta_j).
+    closed = None
+    if args.fusion == "on" and not args.quick:
+        th = np.random.default_rng(11).uniform(0.2, 1.2, n)
+        cops = [q.RY(float(th[w]), wires=w) for w in range(n)] + \
+               [q.CNOT(wires=[w, w + 1]) for w in range(n - 1)]
+        sv.reset()
+        sv.apply_operations_fused(cops, level=args.fusion_level)
+        errs = {}
+        for k in sorted({0, 1, n // 2, n - 2, n - 1}):
+            got = float(measure(qb.expval(q.PauliZ(wires=k)), sv))
+            errs[k] = abs(got - float(np.prod(np.cos(th[: k + 1]))))
+        closed = {"circuit": f"RY(theta_w) on {n} wires + CNOT chain, <Z_k> = prod_(j<=k) cos(theta_j)",
+                  "wires_checked": sorted(errs), "max_abs_err": max(errs.values()),
+                  "norm2_minus_1": float(sv.norm2()) - 1.0}
+        assert closed["max_abs_err"] < 1e-12, closed
+
     # e2e: public API, host parameters in / host scalar out, wall clock
     dev = qb.B200Qubit(wires=n, seed=0, fusion=args.fusion_level if args.fusion == "on" else 0)
     par = np.random.default_rng(3).uniform(0, 2 * np.pi, (args.layers, n, 2))
@@ -431,15 +471,19 @@ def run_ours(args):
 
     e2e_step()
     torch.cuda.synchronize()
-    e2e_steps = max(1, min(args.steps, 3))
+    e2e_steps = max(1, min(args.steps, 10))
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         r = e2e_step()
     torch.cuda.synchronize()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
     assert abs(float(r) - float(val)) < 1e-9, (r, val)
-    # per step: every gate's matrix / phases go host->device in the launch parameters
-    h2d = sum(64 if o.name == "RY" else 32 if o.name == "RZ" else 64 for o in ops_)
+    # per step: the coefficient tables (kernel parameters) and two tensor maps per launch go
+    # host->device; without the specialised path every gate's matrix / phases do
+    if use_program:
+        h2d = sum(8 * int(p.ncoef) + 256 for p in prog.plans if p is not None)
+    else:
+        h2d = sum(64 if o.name == "RY" else 32 if o.name == "RZ" else 64 for o in ops_)
     e2e = {"value": ngates / e2e_s, "unit": "gates/s", "h2d_bytes_per_step": int(h2d),
            "d2h_bytes_per_step": 8, "seconds_per_step": e2e_s}
 
@@ -469,22 +513,31 @@ def run_ours(args):
             from pennylane_b200.compiler import merge_blocks, pack_segments
             T2, RB2, _ = sv.rt_geometry(2)
             _, L2 = sv.default_tile(2)
-            prog = _fused_reverse_program(tape, n, RB2, args.fusion_level)
-            if prog is not None:
-                rev_segments = len(pack_segments(merge_blocks(prog[0], args.fusion_level), n, T=T2, L=L2,
-                                                 max_ops=64))
+            rprog = _fused_reverse_program(tape, n, RB2, args.fusion_level)
+            if rprog is not None:
+                rev_segments = len(pack_segments(merge_blocks(rprog[0], args.fusion_level, fold_cx=not use_program),
+                                                 n, T=T2, L=min(L2, T2), max_ops=64))
                 fused_bytes = (len(fused_segments) * 2 + rev_segments * 4 + 3) * S
         adjoint = {"seconds_per_step": adj_s, "first_call_seconds": adj_first, "params": len(jac), "n_obs": 1,
                    "reverse_segments": rev_segments,
                    "fused_gbps": fused_bytes / adj_s / 1e9 if fused_bytes else None,
                    "frac_of_hbm_peak": fused_bytes / adj_s / 1e9 / peak if fused_bytes else None,
                    "per_gate_algorithmic_gbps": adj_bytes / adj_s / 1e9,
-                   "grad_norm": float(np.linalg.norm(np.array(jac, dtype=float)))}
+                   "grad_norm": float(np.linalg.norm(np.array(jac, dtype=float))),
+                   # the step as one kernel family: 2*S per forward segment + 4*S (ket and bra,
+                   # read + write) per reverse segment + 3*S to form the bra, over the WHOLE call
+                   # (host work included), against the measured copy peak
+                   "roofline": {"bound": "hbm", "kernel": "sk_kernel (NV = 2: ket + bra, generator inner "
+                                "products fused)" if use_program else "k_rtile<double,3,2,512,1>",
+                                "achieved": fused_bytes / adj_s / 1e9 if fused_bytes else None,
+                                "peak": peak, "unit": "GB/s",
+                                "frac": fused_bytes / adj_s / 1e9 / peak if fused_bytes else None,
+                                "traffic": None}}
     clk = clocks.stop()
 
     cpu = None
     if not args.no_cpu_baseline:
-        v, desc, cores, _ = cpu_baseline_sample(n, gates_per_kind=4 if args.quick else 8)
+        v, desc, cores, _, _ = cpu_baseline_sample(n, gates_per_kind=4 if args.quick else 8)
         cpu = {"value": v, "unit": "gates/s", "cores": cores, "kind": "port", "sample": desc}
 
     line = {
@@ -495,6 +548,8 @@ def run_ours(args):
         "hbm_gbps": roofline["all_gates_gbps"], "expval": float(val),
         "state_sweeps_per_step": (len(fused_segments) if fused_segments is not None else ngates),
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "adjoint": adjoint,
+        "closed_form_check": closed,
+        "program_cache": dict(_program.STATS) if use_program else None,
         "gpu_launches": int(timed_launches), "clocks": clk,
     }
     print(json.dumps(line))

@@ -192,9 +192,11 @@ def _fused_reverse_program(tape, n, RB, level):
     while t_number >= 0 and trainable[t_number] > param_number:
         t_number -= 1
     prims, filled = [], []
+    idx = -1                      # position in the sweep order (provenance for rebinding)
     for op in reversed(tape.operations[tape.num_preps:]):
         if op.name == "Snapshot":
             continue
+        idx += 1
         npar = len(op.data)
         is_trainable = npar == 1 and param_number in trainable
         if npar > 1 and any((param_number - j) in trainable for j in range(npar)):
@@ -202,6 +204,10 @@ def _fused_reverse_program(tape, n, RB, level):
                 f"adjoint differentiation: operation {op.name} has {npar} parameters; it must "
                 "be decomposed into one-parameter gates first (default_qubit.py:286-292)")
         adj_prims = lower(_op_adjoint(op), bit_of)
+        exact = len(adj_prims) == 1 and len(op.wires) == 1 and adj_prims[0].kind != GENERIC \
+            and getattr(op, "batch_size", None) is None
+        for j, p in enumerate(adj_prims):
+            p.src, p.src_j, p.src_exact = [idx], j, exact
         if is_trainable:
             if getattr(op, "batch_size", None) is not None:
                 return None
@@ -247,6 +253,15 @@ def _reverse_sweep_fused(tape, sweep: "_Sweep", level: int = 1):
     ket = sweep.ket
     n = sweep.n
     jit = ket.jit_enabled(2)
+    if not jit and ket.jit_possible(2):
+        # below the size threshold a tape STRUCTURE is compiled the second time it is swept
+        from . import program
+        ops_seen = [op for op in tape.operations[tape.num_preps:] if op.name != "Snapshot"]
+        if not any(getattr(op, "batch_size", None) is not None for op in ops_seen) and \
+                program.seen_before(program.structure_key(ops_seen, (
+                    "adjoint-seen", tuple(tape.trainable_params), n, ket.dtype_code, int(level)))):
+            with ket.hot():
+                return _reverse_sweep_fused(tape, sweep, level)
     if jit:
         from . import segjit
         geom = segjit.default_geometry(ket.dtype_code, 2)
@@ -255,6 +270,30 @@ def _reverse_sweep_fused(tape, sweep: "_Sweep", level: int = 1):
         T, RB, _ = ket.rt_geometry(2)
     if n < T:
         return None
+    cache_key = None
+    n_sweep_ops = 0
+    if jit:
+        # structure-keyed cache of the whole reverse program; only the values are rebound
+        import os
+
+        from . import program
+        sweep_ops = [op for op in reversed(tape.operations[tape.num_preps:]) if op.name != "Snapshot"]
+        n_sweep_ops = len(sweep_ops)
+        if not any(getattr(op, "batch_size", None) is not None for op in sweep_ops):
+            cache_key = program.structure_key(sweep_ops, (
+                "adjoint", tuple(tape.trainable_params), n, ket.dtype_code, int(level), T, RB,
+                MAX_SEGMENT_OPS, os.environ.get("B200Q_TILE_L"), os.environ.get("B200Q_IO_LANES")))
+            cached = program.lookup(cache_key)
+            if cached is not None:
+                try:
+                    tabs = cached.bind(sweep_ops, lambda w: n - 1 - int(w), False, adjoint=True)
+                    filled, trainable = cached.meta
+                    plans = {i: p for i, p in enumerate(cached.plans) if p is not None}
+                    return _run_reverse_segments(
+                        sweep, cached.segs, plans, {i: tabs[i] for i in plans},
+                        sum(p.nslots for p in plans.values()), True, T, RB, filled, trainable)
+                except program.RebindError:
+                    program.drop(cache_key)
     prog = _fused_reverse_program(tape, n, RB, level)
     if prog is None:
         return None
@@ -271,8 +310,30 @@ def _reverse_sweep_fused(tape, sweep: "_Sweep", level: int = 1):
                 plans[i] = segjit.plan_segment(seg, geom, _low_run(seg.tile_bits))
         segjit.ensure_compiled(plans.values())
         total_slots = sum(p.nslots for p in plans.values())
+        tables = {i: segjit.coefficients(p, segs[i].prims) for i, p in plans.items()}
+        if cache_key is not None:
+            from . import program
+            try:
+                prog = program.FusedProgram(segs, [plans.get(i) for i in range(len(segs))], n_sweep_ops)
+                prog.meta = (filled, trainable)
+                program.store(cache_key, prog)
+            except program.RebindError:
+                pass
     else:
         total_slots = sum(len({p.param for p in s.prims if p.kind == GEN}) for s in segs)
+    return _run_reverse_segments(sweep, segs, plans, tables if jit else None, total_slots, jit, T, RB,
+                                 filled, trainable)
+
+
+def _run_reverse_segments(sweep, segs, plans, tables, total_slots, jit, T, RB, filled, trainable):
+    from .compiler import DIAG, GEN, encode_rt_segment
+    from .statevector import _low_run
+    from . import segjit
+
+    torch = _torch()
+    ket = sweep.ket
+    n = sweep.n
+    n_bras = sweep.n_bras
     acc = torch.zeros(max(1, total_slots * n_bras), dtype=torch.float64, device=ket.device)
     gather = []                                   # (offset in acc, bra, param index)
     offset = 0
@@ -290,7 +351,7 @@ def _reverse_sweep_fused(tape, sweep: "_Sweep", level: int = 1):
             continue
         if jit:
             plan = plans[i]
-            coefs = segjit.coefficients(plan, seg.prims)
+            coefs = tables[i]
             nslots = plan.nslots
             for b in range(n_bras):
                 segjit.launch(plan, coefs, ket.ptr, sweep.bra(b).ptr, n, 1, w, wb, ket.stream,

@@ -64,6 +64,11 @@ class Prim:
     pure_cx: bool = False                            # merge_blocks: block is exactly one CX so far
     deferred: list = field(default_factory=list)     # merge_blocks: (GEN, 2x2 Pauli) evaluated
                                                      # right after this block
+    src: list | None = None                          # provenance for parameter rebinding: indices
+                                                     # of the source operators, in order of
+                                                     # application (None: unknown)
+    src_j: int = 0                                   # position among the primitives of src[0]
+    src_exact: bool = False                          # mat == product of the operators' matrices
 
     @property
     def bits(self):
@@ -330,8 +335,11 @@ def merge_blocks(prims: list[Prim], level: int = 1, fold_cx: bool = True) -> lis
                     q.mat0 = m @ q.mat0
                 q.ngates += p.ngates
                 q.pure_cx = False
+                q.src = (q.src + p.src) if (q.src is not None and p.src is not None) else None
+                q.src_exact = q.src_exact and p.src_exact
             else:
-                pending[b] = Prim(DENSE1, targets=[b], mat=m.copy(), ngates=p.ngates, seq=seq)
+                pending[b] = Prim(DENSE1, targets=[b], mat=m.copy(), ngates=p.ngates, seq=seq,
+                                  src=None if p.src is None else list(p.src), src_exact=p.src_exact)
             continue
         if fold_cx and p.kind == CX and len(p.ctrl) == 1:
             t = p.targets[0]
@@ -354,6 +362,7 @@ def merge_blocks(prims: list[Prim], level: int = 1, fold_cx: bool = True) -> lis
                 q.mat = _X @ q.mat
                 q.ngates += p.ngates
                 q.pure_cx = False
+                q.src, q.src_exact = None, False
             continue
         if level >= 2 and p.kind == DENSE2 and not p.ctrl:
             # absorb pending (uncontrolled) single-qubit blocks that precede this gate
@@ -391,6 +400,7 @@ def merge_blocks(prims: list[Prim], level: int = 1, fold_cx: bool = True) -> lis
             q.ngates = p.ngates
             if q.kind == DIAG and np.allclose(q.mat, 1.0):
                 q = Prim(PARITY, mat=np.array([1.0 + 0j, 1.0 + 0j]), ngates=p.ngates)
+            q.src, q.src_exact = p.src, p.src_exact and q.kind == DENSE1
             norm.append(q)
         elif p.kind == DENSE1 and p.mat0 is not None and np.array_equal(p.mat0, np.eye(2)):
             p.mat0 = None                        # plain controlled gate: skip where control fails
@@ -492,15 +502,26 @@ def pack_segments(prims: list[Prim], n: int, T: int = 12, L: int = 5, max_ops: i
     return segments
 
 
+def lower_all(ops_, bit_of, batched_ok: bool = False) -> list[Prim]:
+    """:func:`lower` over a list of operators, with provenance (``Prim.src``) for rebinding."""
+    prims: list[Prim] = []
+    for i, op in enumerate(ops_):
+        low = lower(op, bit_of, batched_ok)
+        exact = len(low) == 1 and len(op.wires) == 1 and getattr(op, "batch_size", None) is None \
+            and low[0].kind != GENERIC
+        for j, p in enumerate(low):
+            p.src, p.src_j, p.src_exact = [i], j, exact
+        prims.extend(low)
+    return prims
+
+
 def compile_ops(ops_, n: int, bit_of=None, level: int = 1, T: int = 12, L: int = 5,
                 batched_ok: bool = False, fold_cx: bool = True, round_budget: int | None = None,
                 RB: int = 4, sww: int = 3):
     """Operators -> list of :class:`Segment`."""
     if bit_of is None:
         bit_of = lambda w: n - 1 - int(w)          # noqa: E731
-    prims: list[Prim] = []
-    for op in ops_:
-        prims.extend(lower(op, bit_of, batched_ok))
+    prims = lower_all(ops_, bit_of, batched_ok)
     prims = merge_blocks(prims, level, fold_cx)
     return pack_segments(prims, n, T=T, L=L, round_budget=round_budget, RB=RB, sww=sww)
 

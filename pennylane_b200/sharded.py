@@ -393,10 +393,9 @@ class CudaEngine:
     def compile(self, local_ops):
         if not self.fusion:
             return ("ops", list(local_ops))
-        from .compiler import compile_ops
-
-        T, L = self.sv.default_tile()
-        return ("segs", compile_ops(local_ops, self.sv.n, level=self.fusion, T=T, L=L))
+        segs = self.sv.compile_fused(local_ops, level=self.fusion)
+        self.sv.prepare_segments(segs)
+        return ("segs", segs)
 
     def run(self, handle):
         kind, items = handle
@@ -572,6 +571,12 @@ class ShardedStateVector:
             raise ValueError("fewer than one local qubit per rank")
         self.engine = engine if engine is not None else CudaEngine(self.nl, dtype, batch, device,
                                                                    fusion)
+        # real dtype of the shards (the engine's buffer when it has one)
+        data = getattr(self.engine, "data", None)
+        if data is None:
+            data = getattr(getattr(self.engine, "sv", None), "data", None)
+        self.np_dtype = (np.dtype(np.complex64) if data is not None and "complex64" in str(data.dtype)
+                         else np.dtype(dtype) if data is None else np.dtype(np.complex128))
         self.phys = list(range(self.n))
         self.stage_bytes = int(stage_bytes)
         self._stage = None
@@ -674,7 +679,9 @@ class ShardedStateVector:
             raise AssertionError("mid_measurements dictionary is required for MidMeasure")
         wire = op.wires[0]
         p = self.probs([wire])
-        sample, scale = StateVector.mid_measure_draw(p, np.dtype(np.complex128), rng)
+        # the state's own precision decides the renormalisation tolerance (finfo(state.dtype) in
+        # apply_operation.py:451-457): a complex64 state drifts in norm by ~1e-7
+        sample, scale = StateVector.mid_measure_draw(p, self.np_dtype, rng)
         mid_measurements[op] = sample
         if sample == 1 and getattr(op, "reset", False):
             mat = np.zeros((2, 2), dtype=complex)

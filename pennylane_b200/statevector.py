@@ -411,9 +411,39 @@ class StateVector:
         geom = segjit.default_geometry(self.dtype_code, nvec)
         if mode == "0" or self.n < geom.T:
             return False
-        if mode == "auto" and self.n < int(os.environ.get("B200Q_JIT_MIN_QUBITS", 22)):
+        if mode == "auto" and not getattr(self, "_jit_hot", False) \
+                and self.n < int(os.environ.get("B200Q_JIT_MIN_QUBITS", 22)):
             return False
         return bool(self.lib.b200q_jit_available())
+
+    def jit_possible(self, nvec: int = 1) -> bool:
+        """The specialised kernels could run on this state (ignoring the size threshold): used by
+        the program cache to promote a circuit STRUCTURE that is executed a second time — a
+        training loop on a small register — to the compiled path."""
+        import os
+
+        from . import segjit
+
+        if os.environ.get("B200Q_JIT", "auto") == "0":
+            return False
+        return self.n >= segjit.default_geometry(self.dtype_code, nvec).T \
+            and bool(self.lib.b200q_jit_available())
+
+    class _Hot:
+        """``with sv.hot():`` — run the specialised path regardless of the size threshold."""
+
+        def __init__(self, sv):
+            self.sv = sv
+
+        def __enter__(self):
+            self.prev = getattr(self.sv, "_jit_hot", False)
+            self.sv._jit_hot = True
+
+        def __exit__(self, *a):
+            self.sv._jit_hot = self.prev
+
+    def hot(self):
+        return StateVector._Hot(self)
 
     def compile_fused(self, ops_, level: int = 1, T: int | None = None, L: int | None = None,
                       bit_of=None):
@@ -436,11 +466,34 @@ class StateVector:
                                L: int | None = None, bit_of=None):
         """Apply a list of operators through the fusion pass (compiler.py): returns the number of
         state sweeps (kernel launches over the full state) that were issued."""
+        from . import program
+
+        prog, _ = program.get_program(self, ops_, level, T, L, bit_of)
+        if prog is not None:
+            # cached structure, tables bound to the current parameter values
+            for seg, plan, tab in zip(prog.segs, prog.plans, prog.tables):
+                if plan is None:
+                    self.run_segment(seg)
+                else:
+                    self._launch_plan(plan, tab)
+            return len(prog.segs)
         segs = self.compile_fused(ops_, level, T, L, bit_of)
         self.prepare_segments(segs)
         for seg in segs:
             self.run_segment(seg)
         return len(segs)
+
+    def _launch_plan(self, plan, coefs, base_hi: int = 0):
+        from . import segjit
+
+        if coefs.ndim == 2 and coefs.shape[0] != self.batch:   # broadcast parameters
+            if self.batch != 1:
+                raise ValueError(f"broadcast gates of batch {coefs.shape[0]} on a state of "
+                                 f"batch {self.batch}")
+            self._resize_batch(coefs.shape[0])
+        w, wb = self.workspace()
+        segjit.launch(plan, coefs, self.ptr, None, self.n, self.batch, w, wb, self.stream,
+                      base_hi=base_hi)
 
     def prepare_segments(self, segs):
         """Plan every tile segment for the specialised kernels and compile the structures that
@@ -472,15 +525,7 @@ class StateVector:
             plan = segjit.plan_segment(seg, geom, _low_run(seg.tile_bits))
             seg._sk_plan = plan
             seg._sk_coefs = segjit.coefficients(plan, seg.prims)
-        coefs = seg._sk_coefs
-        if coefs.ndim == 2 and coefs.shape[0] != self.batch:   # broadcast parameters
-            if self.batch != 1:
-                raise ValueError(f"broadcast gates of batch {coefs.shape[0]} on a state of "
-                                 f"batch {self.batch}")
-            self._resize_batch(coefs.shape[0])
-        w, wb = self.workspace()
-        segjit.launch(plan, coefs, self.ptr, None, self.n, self.batch, w, wb, self.stream,
-                      base_hi=base_hi)
+        self._launch_plan(plan, seg._sk_coefs, base_hi)
 
     def run_segment(self, seg, base_hi: int = 0):
         from .compiler import DIAG, encode_rt_segment, encode_segment

@@ -258,3 +258,222 @@ def test_reverse_sweep_of_the_ansatz_uses_one_block_per_wire_and_layer():
         plan = sj.plan_segment(seg, geom, 5)
         # RY^dagger RZ^dagger: the real kernel with one (right) phase
         assert all(r[2:5] == (0, 0, 1) for r in plan.ir if r[0] == "dk")
+
+
+# ---- structure-keyed program cache with parameter rebinding (CPU) ------------------------------
+class _FakeState:
+    """The slice of StateVector the program cache reads (no CUDA)."""
+
+    def __init__(self, n, geom, L, above_threshold=True):
+        self.n, self.dtype_code, self._geom, self._L = n, geom.dtype_code, geom, L
+        self.above_threshold, self._hot = above_threshold, False
+
+    def jit_enabled(self, nvec=1):
+        return self.above_threshold or self._hot
+
+    def jit_possible(self, nvec=1):
+        return True
+
+    def hot(self):
+        import contextlib
+
+        @contextlib.contextmanager
+        def ctx():
+            prev, self._hot = self._hot, True
+            try:
+                yield
+            finally:
+                self._hot = prev
+        return ctx()
+
+    def rt_geometry(self, nvec=1):
+        return self._geom.T, self._geom.RB, 1 << self._geom.TB
+
+    def default_tile(self, nvec=1):
+        return self._geom.T, self._L
+
+    def compile_fused(self, ops_, level=1, T=None, L=None, bit_of=None):
+        return cc.compile_ops(ops_, self.n, bit_of=bit_of, level=level, T=T or self._geom.T,
+                              L=self._L if L is None else L, batched_ok=True, fold_cx=False)
+
+    def prepare_segments(self, segs):
+        for seg in segs:
+            if seg.tile_bits is not None:
+                seg._sk_plan = sj.plan_segment(seg, self._geom, self._L)
+                seg._sk_coefs = sj.coefficients(seg._sk_plan, seg.prims)
+
+
+def _run_program(prog, n):
+    from oracle.apply_operation import apply_operation as o_apply
+
+    state = np.zeros(1 << n, dtype=complex)
+    state[0] = 1.0
+    for seg, plan, tab in zip(prog.segs, prog.plans, prog.tables):
+        if plan is None:
+            state = o_apply(seg.prims[0].op, state.reshape((2,) * n)).reshape(-1)
+        else:
+            state = run_plan(plan, tab, state, n)
+    return state
+
+
+def _param_circuit(n, rng, special=False):
+    """Fixed structure, parameters drawn from ``rng`` (``special``: angles 0 / pi / pi/2)."""
+    def ang():
+        return float(rng.choice([0.0, np.pi, np.pi / 2, 2 * np.pi])) if special else float(rng.uniform(0, 6))
+    ops_ = []
+    for l in range(3):
+        for w in range(n):
+            ops_ += [q.RY(ang(), wires=w), q.RZ(ang(), wires=w)]
+        ops_ += [q.CNOT(wires=[w, (w + 1) % n]) for w in range(n)]
+        ops_ += [q.RX(ang(), wires=0), q.Hadamard(wires=1), q.PhaseShift(ang(), wires=2),
+                 q.Rot(ang(), ang(), ang(), wires=3), q.CRY(ang(), wires=[4, 5]),
+                 q.IsingZZ(ang(), wires=[5, 6]), q.IsingXY(ang(), wires=[6, 7]), q.RZ(ang(), wires=7),
+                 q.T(wires=0), q.MultiRZ(ang(), wires=[0, 3, 5]), q.GlobalPhase(ang()),
+                 q.QubitUnitary(_random_unitary(rng), wires=1)]
+    return ops_
+
+
+def test_program_cache_rebinds_parameters_without_recompiling(monkeypatch):
+    from oracle import simulate as o_sim
+    from pennylane_b200 import program
+
+    program.clear()
+    n, geom, L = 9, sj.Geometry(1, 3, 5, 1, 2), 4
+    sv = _FakeState(n, geom, L)
+    calls = {"n": 0}
+    real = cc.compile_ops
+
+    def counting(*a, **k):
+        calls["n"] += 1
+        return real(*a, **k)
+
+    monkeypatch.setattr(cc, "compile_ops", counting)
+    rng = np.random.default_rng(0)
+    keys = None
+    for it in range(4):
+        ops_ = _param_circuit(n, rng, special=(it == 3))
+        prog, hit = program.get_program(sv, ops_, 1)
+        assert prog is not None
+        ref, _ = o_sim.get_final_state(qb.QuantumScript(ops_, [qb.state()]))
+        got = _run_program(prog, n)
+        assert np.max(np.abs(got - ref.reshape(-1))) < 1e-12
+        if it == 0:
+            assert not hit and calls["n"] == 1
+            keys = [p.key for p in prog.plans if p is not None]
+        elif it < 3:
+            # new generic angles: zero compile_ops calls, same kernels
+            assert hit and calls["n"] == 1
+            assert [p.key for p in prog.plans if p is not None] == keys
+    assert program.STATS["hits"] >= 2
+
+
+def test_program_cache_first_call_with_special_values_then_generic():
+    """Compiled at angles 0 / pi (blocks happen to be diagonal / permutations), then generic
+    angles: the entry is dropped and rebuilt instead of producing a wrong state."""
+    from oracle import simulate as o_sim
+    from pennylane_b200 import program
+
+    program.clear()
+    n, geom, L = 9, sj.Geometry(1, 3, 5, 1, 2), 4
+    sv = _FakeState(n, geom, L)
+    rng = np.random.default_rng(1)
+    for special in (True, False, False, True):
+        ops_ = _param_circuit(n, rng, special=special)
+        prog, _ = program.get_program(sv, ops_, 1)
+        ref, _ = o_sim.get_final_state(qb.QuantumScript(ops_, [qb.state()]))
+        assert np.max(np.abs(_run_program(prog, n) - ref.reshape(-1))) < 1e-12
+
+
+def test_canon_batch_matches_scalar_forms():
+    from pennylane_b200.program import canon_batch
+
+    rng = np.random.default_rng(3)
+    us, forms = [], []
+    for _ in range(300):
+        kind = rng.integers(5)
+        th, ph = rng.uniform(0, 6.3, size=2)
+        if rng.random() < 0.15:
+            th = float(rng.choice([0.0, np.pi, 2 * np.pi]))
+        ry, rx, rz = (np.asarray(g(a, wires=0).matrix()) for g, a in ((q.RY, th), (q.RX, th), (q.RZ, ph)))
+        u = [ry, rx, rz @ ry, ry @ rz, _random_unitary(rng)][kind]
+        c = sj.canon_1q(u)
+        us.append(u)
+        forms.append((c.kern, c.dl, c.dr))
+    U = np.array(us)
+    kern = np.array([f[0] for f in forms]); dl = np.array([f[1] for f in forms]); dr = np.array([f[2] for f in forms])
+    t, sinp, r, l, s, ok = canon_batch(U, kern, dl, dr)
+    assert np.all(ok)
+    for k in range(len(us)):
+        c = sj.Canon(int(kern[k]), bool(sinp[k]), float(t[k]), complex(r[k]), complex(l[k]), complex(s[k]))
+        assert np.max(np.abs(c.matrix() - us[k])) < 1e-13
+        assert (not c.dl or dl[k]) and (not c.dr or dr[k])
+    # a general block does not fit the bare kernel
+    _, _, _, _, _, ok = canon_batch(np.array([_random_unitary(rng)]), np.array([0]), np.array([False]), np.array([False]))
+    assert not ok[0]
+
+
+def test_small_registers_are_promoted_on_the_second_execution():
+    """Below the size threshold a structure runs through the interpreter the first time it is
+    seen and is compiled when it comes back (a training loop)."""
+    from pennylane_b200 import program
+
+    program.clear()
+    n, geom, L = 9, sj.Geometry(1, 3, 5, 1, 2), 4
+    sv = _FakeState(n, geom, L, above_threshold=False)
+    rng = np.random.default_rng(2)
+    prog, hit = program.get_program(sv, _param_circuit(n, rng), 1)
+    assert prog is None and not hit
+    prog, hit = program.get_program(sv, _param_circuit(n, rng), 1)
+    assert prog is not None and not hit
+    prog, hit = program.get_program(sv, _param_circuit(n, rng), 1)
+    assert prog is not None and hit
+
+
+def test_adjoint_program_rebinds_parameters():
+    """The cached reverse program of one tape, rebound to the parameter values of another tape of
+    the same structure, gives that tape's Jacobian (emulated; conj-transposed operator matrices
+    multiplied along the merged blocks, generator coefficients corrected by the block scalars)."""
+    from oracle import adjoint_jacobian as o_adj
+    from oracle import simulate as o_sim
+    from oracle.apply_operation import apply_operation as o_apply
+    from pennylane_b200 import program
+    from pennylane_b200.adjoint import _accumulate_slot_sums, _fused_reverse_program
+
+    n, RB, TB, L = 9, 3, 5, 4
+    geom = sj.Geometry(1, RB, TB, 2, 1)
+
+    def tape_for(seed):
+        rng = np.random.default_rng(seed)
+        ops_ = []
+        for l in range(3):
+            for w in range(n):
+                ops_ += [q.RY(rng.uniform(0, 6), wires=w), q.RZ(rng.uniform(0, 6), wires=w)]
+            ops_ += [q.CNOT(wires=[w, (w + 1) % n]) for w in range(n)]
+            ops_ += [q.RX(rng.uniform(0, 6), wires=1), q.IsingXY(rng.uniform(0, 6), wires=[2, 5]),
+                     q.PhaseShift(rng.uniform(0, 6), wires=4), q.CZ(wires=[0, 3]),
+                     q.Hadamard(wires=6)]
+        obs = q.PauliZ(wires=0) @ q.PauliY(wires=3)
+        return qb.QuantumScript(ops_, [qb.expval(obs)]), obs
+
+    tape_a, _ = tape_for(1)
+    prims, filled, trainable = _fused_reverse_program(tape_a, n, RB, 1)
+    segs = cc.pack_segments(cc.merge_blocks(prims, 1, fold_cx=False), n, T=geom.T, L=L, max_ops=64)
+    plans = [sj.plan_segment(s, geom, L) for s in segs]
+    prog = program.FusedProgram(segs, plans, len(tape_a.operations))
+    assert len(prog.blocks) > 0
+    for seed in (2, 3):
+        tape_b, obs = tape_for(seed)
+        sweep_ops = list(reversed(tape_b.operations))
+        tabs = prog.bind(sweep_ops, lambda w: n - 1 - int(w), False, adjoint=True)
+        state, _ = o_sim.get_final_state(tape_b)
+        ref = np.array(o_adj.adjoint_jacobian(tape_b, state), dtype=float)
+        ket = state.reshape(-1).copy()
+        bra = 2.0 * o_apply(obs, state).reshape(-1)
+        raw, gather = [], []
+        for plan, tab in zip(plans, tabs):
+            ket, bra, sums = run_plan(plan, tab, ket, n, bra=bra)
+            for slot, param in enumerate(plan.slot_params):
+                gather.append((len(raw) + slot, 0, param))
+            raw += list(-sums)
+        jac = _accumulate_slot_sums(np.array(raw), gather, len(trainable), 1)[:, 0]
+        assert np.max(np.abs(jac - ref)) < 1e-12
