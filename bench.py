@@ -183,7 +183,8 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n_full = args.qubits + int(np.log2(args.gpus))
+    per_gpu = args.qubits if (args.gpus == 1 or args.weak16g or args.qubits != 30) else 33
+    n_full = per_gpu + int(np.log2(args.gpus))
     vals, last = [], None
     for i in range(args.warmup + args.steps):
         v, desc, cores, dt, n_twin = cpu_baseline_sample(n_full, gates_per_kind=4 if args.quick else 8)
@@ -568,6 +569,8 @@ def main():
     ap.add_argument("--no-adjoint", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--weak16g", action="store_true",
+                    help="multi-GPU: 30 + log2 N qubits (16 GiB per GPU) instead of 33 + log2 N (128 GiB)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

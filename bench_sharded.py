@@ -17,6 +17,15 @@ import time
 import numpy as np
 
 
+def _log(rank, msg, t0=[None]):
+    """Progress on stderr (rank 0) — a 128 GiB-per-GPU run is long enough to want a pulse."""
+    import sys
+    if t0[0] is None:
+        t0[0] = time.perf_counter()
+    if rank == 0:
+        print(f"[bench_sharded +{time.perf_counter() - t0[0]:7.1f}s] {msg}", file=sys.stderr, flush=True)
+
+
 def run_sharded(args, dist, rank, world, local_rank):
     import torch
 
@@ -26,13 +35,22 @@ def run_sharded(args, dist, rank, world, local_rank):
     from pennylane_b200.sharded import ShardedStateVector, simulate_sharded
 
     g = world.bit_length() - 1
-    n = args.qubits + g
+    # BASELINE.json's multi-GPU point is 36 qubits on 8 GPUs: 128 GiB of state per GPU.  N = 2 and
+    # 4 use the same shard size (34 / 35 qubits) so that the N > 1 points are mutually comparable;
+    # `--weak16g` keeps the 1-GPU shard (30 + log2 N qubits, 16 GiB per GPU) of round 1.
+    per_gpu_qubits = args.qubits if (args.weak16g or args.qubits != 30) else 33
+    n = per_gpu_qubits + g
+    _log(rank, f"start: {n} qubits over {world} GPUs")
+    parity = parity_twin(dist, rank, world, args)
+    _log(rank, f"parity twin done: {parity}")
     ops_ = hea_ops(n, args.layers)
     ngates = len(ops_)
     obs = q.PauliZ(wires=0)
     fusion = args.fusion_level if args.fusion == "on" else 0
     sv = ShardedStateVector(n, dist, dtype=np.complex128, fusion=fusion)
+    _log(rank, "state allocated")
     program = sv.compile(ops_)
+    _log(rank, f"compiled: {program['n_exchanges']} exchanges")
     S_loc = 16.0 * (1 << sv.nl)
 
     records = []
@@ -50,8 +68,10 @@ def run_sharded(args, dist, rank, world, local_rank):
         sv.run(program)
         return sv.expval_pauli_sentence(obs.pauli_rep)
 
-    for _ in range(args.warmup):
+    for i in range(args.warmup):
         step()
+        torch.cuda.synchronize()
+        _log(rank, f"warm-up step {i} done")
     torch.cuda.synchronize()
     dist.barrier()
     clocks = ClockSampler(local_rank)
@@ -69,6 +89,7 @@ def run_sharded(args, dist, rank, world, local_rank):
     torch.cuda.synchronize()
     dist.barrier()
     sv.timer = None
+    _log(rank, "timed steps done")
     ms = torch.tensor([start.elapsed_time(end)], dtype=torch.float64, device="cuda")
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     total_ms = float(ms.item())
@@ -105,6 +126,7 @@ def run_sharded(args, dist, rank, world, local_rank):
     torch.cuda.empty_cache()
     e2e_step()
     torch.cuda.synchronize(); dist.barrier()
+    _log(rank, "first e2e step done")
     k2 = max(1, min(args.steps, 2))
     t0 = time.perf_counter()
     for _ in range(k2):
@@ -118,13 +140,20 @@ def run_sharded(args, dist, rank, world, local_rank):
     if rank == 0:
         cfg = workload_config(args, n)
         cfg["shard_bytes"] = int(S_loc)
+        cfg["workload"] += (f"; sharded over {world} GPUs by the top {g} qubits, {per_gpu_qubits} local qubits "
+                            f"({int(S_loc) >> 30} GiB) per GPU" +
+                            ("" if per_gpu_qubits == 33 else " [--weak16g / --qubits: not BASELINE's 36q@8 shard size]"))
         line = {
             "metric": "gates_per_s", "value": ngates / (ms_per_step * 1e-3), "unit": "gates/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "c128",
             "data": "synthetic", "config": cfg, "expval": float(val),
+            # gates/s falls by 2 per added qubit at fixed hardware speed; the size-independent
+            # figure is amplitude updates per second and per GPU
+            "amplitude_updates_per_s_per_gpu": ngates * float(2 ** n) / world / (ms_per_step * 1e-3),
+            "parity": parity,
             "state_sweeps_per_step": sweeps // args.steps,
-            "roofline": {"bound": "hbm", "kernel": "k_rtile<double,4,1,256,2> (fused segment on each shard: 2*S_loc per launch)",
+            "roofline": {"bound": "hbm", "kernel": "sk_kernel (csrc/segk.cuh, structure-specialised fused segment on each shard: 2*S_loc per launch)",
                          "achieved": hbm, "peak": peak, "unit": "GB/s",
                          "frac": (hbm / peak) if hbm else None, "traffic": None,
                          "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
@@ -144,6 +173,54 @@ def run_sharded(args, dist, rank, world, local_rank):
         print(json.dumps(line))
     dist.barrier()
     dist.destroy_process_group()
+
+
+def parity_twin(dist, rank, world, args, n=20, shots=2000):
+    """A 20-qubit twin of the workload through the SAME sharded path (planner, exchanges over
+    NCCL, specialised segment kernels forced on) against the oracle, which rank 0 runs on the
+    host: final state, expectation value and seeded samples.  Reported in the bench line."""
+    import torch
+
+    import pennylane_b200 as qb
+    from bench import hea_ops
+    from pennylane_b200 import ops as q
+    from pennylane_b200.sharded import ShardedStateVector
+
+    prev = os.environ.get("B200Q_JIT")
+    os.environ["B200Q_JIT"] = "1"
+    try:
+        ops_ = hea_ops(n, 3, seed=5)
+        fusion = args.fusion_level if args.fusion == "on" else 0
+        sv = ShardedStateVector(n, dist, dtype=np.complex128, fusion=fusion)
+        sv.run(sv.compile(ops_))
+        ev = float(sv.expval_pauli_sentence((q.PauliZ(wires=0) @ q.PauliX(wires=n - 1)).pauli_rep))
+        n_ex = sv.stats["exchanges"]
+        state = sv.to_numpy()
+        samples = sv.sample(shots, np.random.default_rng(17), exact=True)
+        out = None
+        if rank == 0:
+            from oracle import simulate as o_sim
+            tape = qb.QuantumScript(ops_, [qb.state()])
+            ref, _ = o_sim.get_final_state(tape)
+            ref = np.asarray(ref).reshape(-1)
+            tape_e = qb.QuantumScript(ops_, [qb.expval(q.PauliZ(wires=0) @ q.PauliX(wires=n - 1))])
+            ref_e = float(o_sim.measure_final_state(tape_e, o_sim.get_final_state(tape_e)[0], False))
+            tape_s = qb.QuantumScript(ops_, [qb.sample(wires=range(n))], shots=shots)
+            ref_s = o_sim.simulate(tape_s, rng=np.random.default_rng(17))
+            out = {"circuit": f"hea{n} (3 layers, seed 5) sharded over {world} GPUs, {n_ex} exchanges",
+                   "max_abs_err_state": float(np.max(np.abs(np.asarray(state).reshape(-1) - ref))),
+                   "abs_err_expval": abs(ev - ref_e),
+                   "samples_identical": bool(np.array_equal(np.asarray(samples), np.asarray(ref_s))),
+                   "shots": shots, "oracle": "oracle/ (numpy restatement of default.qubit) on rank 0"}
+            assert out["max_abs_err_state"] < 1e-12 and out["abs_err_expval"] < 1e-12, out
+        del sv
+        torch.cuda.empty_cache()
+        return out
+    finally:
+        if prev is None:
+            os.environ.pop("B200Q_JIT", None)
+        else:
+            os.environ["B200Q_JIT"] = prev
 
 
 def sv_stats_per_step(nbytes, steps):

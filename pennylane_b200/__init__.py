@@ -8,7 +8,7 @@ operator / tape / measurement mirror classes in this package drive it directly.
 """
 from . import mcm, measurements, one_shot, ops, pauli
 from ._lib import B200QError, LIB_PATH
-from .device import B200Qubit, DeviceError, ExecutionConfig, QuantumFunctionError, device
+from .device import B200Qubit, DeviceError, ExecutionConfig, MCMConfig, QuantumFunctionError, device
 from .mcm import cond, measure
 from .measurements import (classical_shadow, counts, density_matrix, expval, mutual_info, probs, purity, sample,
                            shadow_expval, state, var, vn_entropy)
@@ -18,7 +18,7 @@ from .tape import QuantumScript, QuantumTape, Shots
 __version__ = "0.1.0"
 
 __all__ = [
-    "B200Qubit", "device", "ExecutionConfig", "DeviceError", "QuantumFunctionError", "StateVector",
+    "B200Qubit", "device", "ExecutionConfig", "MCMConfig", "DeviceError", "QuantumFunctionError", "StateVector",
     "QuantumScript", "QuantumTape", "Shots", "ops", "measurements", "pauli", "mcm", "one_shot",
     "measure", "cond",
     "expval", "var", "probs", "sample", "counts", "state", "density_matrix", "purity",

@@ -453,7 +453,7 @@ def _adjoint_jacobian_state(tape, dtype=np.complex128, device=None):
 
 
 def adjoint_jacobian(tape, dtype=np.complex128, device=None, return_state: bool = False,
-                     fusion: int = 0):
+                     fusion: int = 0, return_torch: bool = False):
     """adjoint_jacobian.py:77-149.  Runs the forward pass itself (directly into row 0 of the
     sweep buffer).  Returns the Jacobian in the reference's nested-tuple layout; with
     ``return_state`` also a ``StateVector`` copy of the final state taken before the sweep."""
@@ -477,6 +477,11 @@ def adjoint_jacobian(tape, dtype=np.complex128, device=None, return_state: bool 
     jac = np.zeros((n_obs, len(trainable)))
     for t in filled:
         jac[:, t] = vals[t]
+    if return_torch:
+        # device option `return_torch`: the (n_obs, n_trainable) Jacobian as ONE CUDA tensor
+        # (the reference's nested tuples are a host layout; stack them to compare)
+        res = _torch().from_numpy(jac).to(sweep.ket.device)
+        return (res, final) if return_state else res
     jac = np.squeeze(jac)
     if jac.ndim == 0:
         res = np.array(jac)

@@ -49,6 +49,18 @@ class ExecutionConfig:
     interface: str | None = None
     derivative_order: int = 1
     convert_to_numpy: bool = True
+    mcm_config: "MCMConfig" = None
+
+    def __post_init__(self):
+        if self.mcm_config is None:
+            object.__setattr__(self, "mcm_config", MCMConfig())
+
+
+@dataclass(frozen=True)
+class MCMConfig:
+    """pennylane/devices/execution_config.py:31-71."""
+    mcm_method: str | None = None
+    postselect_mode: str | None = None
 
 
 class Tracker:
@@ -218,10 +230,11 @@ class B200Qubit:
     pennylane_requires = ">=0.44"
     version = "0.1.0"
     author = "b200-qubit"
-    _device_options = ("rng", "c_dtype", "exact_sampling", "fusion")
+    _device_options = ("rng", "c_dtype", "exact_sampling", "fusion", "return_torch")
 
     def __init__(self, wires=None, shots=None, seed="global", c_dtype=np.complex128,
-                 exact_sampling: bool = True, device=None, max_workers=None, fusion: int = 1):
+                 exact_sampling: bool = True, device=None, max_workers=None, fusion: int = 1,
+                 return_torch: bool = False):
         if max_workers is not None:
             raise DeviceError("b200.qubit owns a CUDA context and does not support max_workers "
                               "(process pools); run one device per GPU instead.")
@@ -238,6 +251,7 @@ class B200Qubit:
         self._c_dtype = np.dtype(c_dtype)
         self._exact_sampling = bool(exact_sampling)
         self._fusion = int(fusion)
+        self._return_torch = bool(return_torch)     # state / probs / Jacobians stay on the device
         self._torch_device = device
         self._debugger = None
         self._state_cache = None
@@ -285,8 +299,28 @@ class B200Qubit:
         opts.setdefault("c_dtype", self._c_dtype)
         opts.setdefault("exact_sampling", self._exact_sampling)
         opts.setdefault("fusion", self._fusion)
+        opts.setdefault("return_torch", self._return_torch)
         updated["device_options"] = opts
+        updated["mcm_config"] = self._setup_mcm_config(config.mcm_config, circuit)
         return replace(config, **updated)
+
+    def _setup_mcm_config(self, mcm_config, tape):
+        """default_qubit.py:739-760.  "deferred" is a transform above this boundary
+        (``defer_measurements``): tapes that still hold a ``MidMeasure`` when they reach
+        ``preprocess`` without shots and without tree-traversal are rejected there."""
+        final = mcm_config.mcm_method
+        if final is None:
+            final = "one-shot" if getattr(tape, "shots", None) else "deferred"
+        elif final == "device":
+            final = "tree-traversal"
+        supported = {"one-shot", "deferred", "tree-traversal"}
+        if final not in supported:
+            raise DeviceError(f"mcm_method {final} not supported on {self.name}. "
+                              f"Supported methods are {supported}")
+        if mcm_config.postselect_mode == "fill-shots" and final != "deferred":
+            raise DeviceError(
+                "Using postselect_mode='fill-shots' is only supported with mcm_method='deferred'.")
+        return replace(mcm_config, mcm_method=final)
 
     # ---- preprocessing ----------------------------------------------------------------------
     def _validate(self, tape: QuantumScript):
@@ -339,7 +373,13 @@ class B200Qubit:
             self._validate(t)
             t = _decompose(t, lambda op, _tr: stopping_condition(op), self.name)
             post = None
-            if any(op.name == "MidMeasureMP" for op in t.operations):
+            tree = (execution_config is not None and execution_config.mcm_config is not None
+                    and execution_config.mcm_config.mcm_method in ("tree-traversal", "device"))
+            if tree and any(op.name == "MidMeasureMP" for op in t.operations):
+                # default_qubit.py:660-661: the tape goes to simulate_tree_mcm as it is
+                if config.gradient_method == "adjoint":
+                    raise DeviceError("Mid-circuit measurements are not supported with adjoint + b200.qubit")
+            elif any(op.name == "MidMeasureMP" for op in t.operations):
                 # default_qubit.py:632-664 with mcm_method "one-shot" (the default with shots,
                 # :744); the analytic default is "deferred", a transform above this boundary
                 if not t.shots:
@@ -386,7 +426,8 @@ class B200Qubit:
             circuit, rng=opts.get("rng", self._rng), dtype=opts.get("c_dtype", self._c_dtype),
             device=self._torch_device, exact_sampling=opts.get("exact_sampling", self._exact_sampling),
             state_cache=self._state_cache, fusion=opts.get("fusion", self._fusion),
-            debugger=self._debugger)
+            debugger=self._debugger, return_torch=bool(opts.get("return_torch", self._return_torch)),
+            mcm_method=(config.mcm_config.mcm_method if config is not None and config.mcm_config else None))
 
     def execute(self, circuits, execution_config: ExecutionConfig | None = None):
         batch, single = self._as_batch(circuits)
@@ -400,11 +441,21 @@ class B200Qubit:
         opts = (config.device_options if config else {}) or {}
         return opts.get("c_dtype", self._c_dtype)
 
+    def _opt(self, config, name):
+        opts = (config.device_options if config else {}) or {}
+        return opts.get(name, getattr(self, f"_{name}"))
+
+    def _fusion_of(self, config):
+        """The ``fusion`` device option of the execution config, else the constructor's (the
+        derivative entry points honour it like ``execute`` does)."""
+        return int(self._opt(config, "fusion"))
+
     def compute_derivatives(self, circuits, execution_config: ExecutionConfig | None = None):
         batch, single = self._as_batch(circuits)
         self._track(batch, "derivative_batches")
         res = tuple(_adjoint.adjoint_jacobian(c, dtype=self._dtype(execution_config),
-                                              device=self._torch_device, fusion=self._fusion)
+                                              device=self._torch_device, fusion=self._fusion_of(execution_config),
+                                              return_torch=self._opt(execution_config, "return_torch"))
                     for c in batch)
         return res[0] if single else res
 
@@ -416,7 +467,8 @@ class B200Qubit:
             c = c.map_to_standard_wires()
             jac, final = _adjoint.adjoint_jacobian(c, dtype=self._dtype(execution_config),
                                                    device=self._torch_device, return_state=True,
-                                                   fusion=self._fusion)
+                                                   fusion=self._fusion_of(execution_config),
+                                                   return_torch=self._opt(execution_config, "return_torch"))
             results.append(_sim.measure_final_state(c, final, False))
             jacs.append(jac)
         if single:
@@ -428,7 +480,7 @@ class B200Qubit:
         tangents = (tangents,) if single else tuple(tangents)
         self._track(batch, "jvp_batches")
         res = tuple(_adjoint.adjoint_jvp(c, t, dtype=self._dtype(execution_config),
-                                         device=self._torch_device, fusion=self._fusion)
+                                         device=self._torch_device, fusion=self._fusion_of(execution_config))
                     for c, t in zip(batch, tangents))
         return res[0] if single else res
 
@@ -446,7 +498,7 @@ class B200Qubit:
             return self._state_cache.get(circuit.map_to_standard_wires().hash)
 
         res = tuple(_adjoint.adjoint_vjp(c, t, dtype=self._dtype(execution_config),
-                                         device=self._torch_device, fusion=self._fusion,
+                                         device=self._torch_device, fusion=self._fusion_of(execution_config),
                                          state=_state(c))
                     for c, t in zip(batch, cotangents))
         return res[0] if single else res

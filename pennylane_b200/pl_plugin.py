@@ -15,23 +15,37 @@ Entry point (``pyproject.toml`` of this package, group ``pennylane.plugins``,
     [project.entry-points."pennylane.plugins"]
     "b200.qubit" = "pennylane_b200.pl_plugin:B200QubitDevice"
 
-NOTE: PennyLane cannot be imported in the build container, so this file is
-exercised only where a real install exists; the engine underneath is what the test-suite covers.
+NOTE: PennyLane cannot be imported in the build container (autograd /
+autoray / rustworkx are absent), so this file cannot be executed here.  What IS checked here,
+statically against the reference sources (tests/test_plugin_conformance.py): every name this
+module imports from ``pennylane`` exists at that path, every overridden ``Device`` method has the
+reference's signature, and ``preprocess_transforms`` adds the transforms of
+``DefaultQubit.preprocess_transforms`` in the same order with the same keywords.
 """
 from __future__ import annotations
 
+from dataclasses import replace
+
 import numpy as np
 import pennylane as qml
-from pennylane.devices import DefaultQubit, Device, ExecutionConfig
+from pennylane import math
+from pennylane.core.transforms import CompilePipeline
+from pennylane.devices import Device, ExecutionConfig
+from pennylane.devices.default_qubit import (ALL_DQ_GATES, ALL_DQ_GATES_PLUS_MCM,
+                                             _add_adjoint_transforms, _conditional_broadcast_expand,
+                                             _supports_adjoint, accepted_analytic_measurement,
+                                             accepted_sample_measurement,
+                                             allow_mcms_stopping_condition, no_counts,
+                                             no_mcms_stopping_condition)
 from pennylane.devices.modifiers import simulator_tracking, single_tape_support
-from pennylane.devices.preprocess import (decompose, no_sampling, validate_adjoint_trainable_params,
-                                          validate_device_wires, validate_measurements,
-                                          validate_observables)
-from pennylane.transforms.core import TransformProgram
+from pennylane.devices.preprocess import (decompose, device_resolve_dynamic_wires, no_sampling,
+                                          validate_device_wires, validate_measurements)
+from pennylane.exceptions import DeviceError
+from pennylane.transforms import broadcast_expand, defer_measurements, dynamic_one_shot
 
 from . import adjoint as _adjoint
 from . import simulate as _sim
-from .device import adjoint_observables, adjoint_ops, stopping_condition
+from .device import stopping_condition as _engine_accepts
 
 _KIND = {"ExpectationMP": "expval", "VarianceMP": "var", "ProbabilityMP": "probs",
          "SampleMP": "sample", "CountsMP": "counts", "StateMP": "state",
@@ -48,7 +62,7 @@ class _MP:
         self._mp = mp
         self.kind = _KIND.get(type(mp).__name__)
         if self.kind is None:
-            raise qml.DeviceError(f"Measurement {mp} is not supported on b200.qubit")
+            raise DeviceError(f"Measurement {mp} is not supported on b200.qubit")
         self.obs = mp.obs
         self.mv = getattr(mp, "mv", None)     # sampled mid-circuit value of a one-shot tape
         self.log_base = getattr(mp, "log_base", None)
@@ -106,103 +120,152 @@ class B200QubitDevice(Device):
     def __init__(self, wires=None, shots=None, seed="global", c_dtype=np.complex128,
                  fusion: int = 1, exact_sampling: bool = True, max_workers=None):
         if max_workers is not None:
-            raise qml.DeviceError("b200.qubit does not support max_workers; run one device per GPU")
+            raise DeviceError("b200.qubit does not support max_workers; run one device per GPU")
         super().__init__(wires=wires, shots=shots)
         seed = np.random.randint(0, high=10000000) if isinstance(seed, str) and seed == "global" else seed
         self._rng = np.random.default_rng(seed)          # default_qubit.py:562-570
         self._c_dtype = np.dtype(c_dtype)
         self._fusion = int(fusion)
-        self._exact = bool(exact_sampling)
+        self._exact_sampling = bool(exact_sampling)
         self._debugger = None
+        self._state_cache = None
 
-    # ---- capability + configuration (default_qubit.py:574-608, 683-733) -----------------------
+    # ---- capability + configuration (default_qubit.py:572-608, 683-760) -----------------------
     def supports_derivatives(self, execution_config=None, circuit=None):
+        """default_qubit.py:572-608 without the backprop branch (amplitudes live in CUDA kernels:
+        nothing for an autodiff framework to trace)."""
         if execution_config is None:
             return True
-        if execution_config.gradient_method not in ("adjoint", "best"):
-            return False                                # no backprop: amplitudes live in CUDA kernels
-        if circuit is None:
-            return True
-        return DefaultQubit().supports_derivatives(
-            ExecutionConfig(gradient_method="adjoint"), circuit)
+        if execution_config.gradient_method in {"adjoint", "best"}:
+            return _supports_adjoint(circuit, device_wires=self.wires, device_name=self.name)
+        return False
 
     supports_jvp = supports_derivatives
     supports_vjp = supports_derivatives
 
     def setup_execution_config(self, config=None, circuit=None):
-        from dataclasses import replace
+        """default_qubit.py:683-737; "best" resolves to adjoint (there is no backprop)."""
         config = config or ExecutionConfig()
+        updated_values = {}
         for option in config.device_options:
             if option not in self._device_options:
-                raise qml.DeviceError(f"device option {option} not present on {self}")
-        updated = {}
-        method = "adjoint" if config.gradient_method == "best" else config.gradient_method
-        updated["gradient_method"] = method
+                raise DeviceError(f"device option {option} not present on {self}")
+        gradient_method = config.gradient_method
+        if config.gradient_method == "best":
+            gradient_method = "adjoint"
+            updated_values["gradient_method"] = gradient_method
         if config.use_device_gradient is None:
-            updated["use_device_gradient"] = method == "adjoint"
+            updated_values["use_device_gradient"] = gradient_method == "adjoint"
         if config.use_device_jacobian_product is None:
-            updated["use_device_jacobian_product"] = method == "adjoint"
+            updated_values["use_device_jacobian_product"] = gradient_method == "adjoint"
         if config.grad_on_execution is None:
-            updated["grad_on_execution"] = method == "adjoint"
-        opts = dict(config.device_options)
-        opts.setdefault("rng", self._rng)
-        opts.setdefault("c_dtype", self._c_dtype)
-        opts.setdefault("fusion", self._fusion)
-        opts.setdefault("exact_sampling", self._exact)
-        updated["device_options"] = opts
-        # _setup_mcm_config, default_qubit.py:740-760: one-shot with shots, deferred without;
-        # tree-traversal is not built on this device
-        mcm = config.mcm_config
-        method = mcm.mcm_method
-        if method is None:
-            method = "one-shot" if getattr(circuit, "shots", None) else "deferred"
-        if method not in ("deferred", "one-shot"):
-            raise qml.DeviceError(f"mcm_method {method} not supported on b200.qubit. "
-                                  "Supported methods are 'deferred' and 'one-shot'.")
-        if mcm.postselect_mode == "fill-shots" and method != "deferred":
-            raise qml.DeviceError(
+            updated_values["grad_on_execution"] = gradient_method == "adjoint"
+        updated_values["device_options"] = dict(config.device_options)  # copy
+        for option in self._device_options:
+            if option not in updated_values["device_options"]:
+                updated_values["device_options"][option] = getattr(self, f"_{option}")
+        updated_values["mcm_config"] = self._setup_mcm_config(config.mcm_config, circuit)
+        return replace(config, **updated_values)
+
+    def _setup_mcm_config(self, mcm_config, tape):
+        """default_qubit.py:739-760 (all three methods are native on this device)."""
+        final_mcm_method = mcm_config.mcm_method
+        if mcm_config.mcm_method is None:
+            final_mcm_method = "one-shot" if getattr(tape, "shots", None) else "deferred"
+        elif mcm_config.mcm_method == "device":
+            final_mcm_method = "tree-traversal"
+        supported_methods = {"one-shot", "deferred", "tree-traversal"}
+        if final_mcm_method not in supported_methods:
+            raise DeviceError(f"mcm_method {final_mcm_method} not supported on b200.qubit. "
+                              f"Supported methods are {supported_methods}")
+        if mcm_config.postselect_mode == "fill-shots" and final_mcm_method != "deferred":
+            raise DeviceError(
                 "Using postselect_mode='fill-shots' is only supported with mcm_method='deferred'.")
-        updated["mcm_config"] = replace(mcm, mcm_method=method)
-        return replace(config, **updated)
+        return replace(mcm_config, mcm_method=final_mcm_method)
 
     def preprocess_transforms(self, execution_config=None):
+        """default_qubit.py:611-679, transform for transform (tests/test_plugin_conformance.py
+        compares the two functions' ``add_transform`` sequences).  Left out: the
+        ``validate_multiprocessing_workers`` step (``max_workers`` is rejected in ``__init__``).
+        The stopping conditions are the reference's, narrowed by what the engine can apply
+        (dense matrices up to 10 wires)."""
         config = execution_config or ExecutionConfig()
-        prog = TransformProgram()
-        one_shot = config.mcm_config.mcm_method == "one-shot"      # default_qubit.py:632-664
-        if one_shot:
-            accept = stopping_condition                 # MidMeasure / Conditional applied natively
-        else:
-            prog.add_transform(qml.defer_measurements, allow_postselect=False)
 
-            def accept(op):
-                return op.name != "MidMeasureMP" and stopping_condition(op)
-        prog.add_transform(validate_device_wires, self.wires, name=self.name)
-        prog.add_transform(decompose, stopping_condition=accept, name=self.name)
-        prog.add_transform(validate_measurements, name=self.name)
-        prog.add_transform(validate_observables, lambda o: True, name=self.name)
-        if one_shot:
-            prog.add_transform(qml.transforms.dynamic_one_shot,
-                               postselect_mode=config.mcm_config.postselect_mode)
-        if config.gradient_method == "adjoint":         # _add_adjoint_transforms :315-349
-            name = "adjoint + b200.qubit"
-            prog.add_transform(no_sampling, name=name)
-            prog.add_transform(decompose, stopping_condition=adjoint_ops, name=name,
-                               skip_initial_state_prep=False)
-            prog.add_transform(validate_observables, adjoint_observables, name=name)
-            prog.add_transform(qml.transforms.broadcast_expand)
-            prog.add_transform(validate_adjoint_trainable_params)
-        return prog
+        compile_pipeline = CompilePipeline()
+        target_gate_set = ALL_DQ_GATES
+
+        if config.interface == math.Interface.JAX_JIT:
+            compile_pipeline.add_transform(no_counts)
+
+        if config.mcm_config.mcm_method == "deferred":
+            compile_pipeline.add_transform(defer_measurements, allow_postselect=True)
+            _reference_condition = no_mcms_stopping_condition
+        else:
+            _reference_condition = allow_mcms_stopping_condition
+            target_gate_set = ALL_DQ_GATES_PLUS_MCM
+
+        def _stopping_condition(op):
+            return _reference_condition(op) and _engine_accepts(op)
+
+        compile_pipeline.add_transform(
+            decompose,
+            stopping_condition=_stopping_condition,
+            device_wires=self.wires,
+            target_gates=target_gate_set,
+            name=self.name,
+        )
+        _allow_resets = config.mcm_config.mcm_method != "deferred"
+        compile_pipeline.add_transform(
+            device_resolve_dynamic_wires, wires=self.wires, allow_resets=_allow_resets
+        )
+        compile_pipeline.add_transform(validate_device_wires, self.wires, name=self.name)
+        compile_pipeline.add_transform(
+            validate_measurements,
+            analytic_measurements=accepted_analytic_measurement,
+            sample_measurements=accepted_sample_measurement,
+            name=self.name,
+        )
+        compile_pipeline.add_transform(_conditional_broadcast_expand)
+        if config.mcm_config.mcm_method == "tree-traversal":
+            compile_pipeline.add_transform(broadcast_expand)
+
+        if config.mcm_config.mcm_method == "one-shot":
+            compile_pipeline.add_transform(
+                dynamic_one_shot, postselect_mode=config.mcm_config.postselect_mode
+            )
+
+        if config.gradient_method == "backprop":
+            compile_pipeline.add_transform(no_sampling, name="backprop + b200.qubit")
+
+        if config.gradient_method == "adjoint":
+            # the reference's own helper: no_sampling, decompose(adjoint_ops), validate_observables,
+            # validate_measurements, adjoint_state_measurements, broadcast_expand,
+            # validate_adjoint_trainable_params (default_qubit.py:315-349)
+            _add_adjoint_transforms(
+                compile_pipeline,
+                device_vjp=config.use_device_jacobian_product,
+                device_wires=self.wires,
+                target_gates=target_gate_set,
+            )
+        return compile_pipeline
 
     # ---- execution (default_qubit.py:763-1071) --------------------------------------------------
     def _opts(self, config):
         o = (config.device_options if config else {}) or {}
         return (o.get("rng", self._rng), o.get("c_dtype", self._c_dtype),
-                o.get("fusion", self._fusion), o.get("exact_sampling", self._exact))
+                o.get("fusion", self._fusion), o.get("exact_sampling", self._exact_sampling))
 
     def execute(self, circuits, execution_config=None):
+        """default_qubit.py:763-846.  With ``use_device_jacobian_product`` the final state of every
+        circuit is kept (``_state_cache``, :772) for the ``compute_vjp`` that follows (:1021-1029)."""
+        if execution_config is None:
+            execution_config = ExecutionConfig()
         rng, dt, fusion, exact = self._opts(execution_config)
+        self._state_cache = {} if execution_config.use_device_jacobian_product else None
+        mcm_method = execution_config.mcm_config.mcm_method
         return tuple(_sim.simulate(_Tape(c), rng=rng, dtype=dt, exact_sampling=exact, fusion=fusion,
-                                   debugger=self._debugger)
+                                   debugger=self._debugger, state_cache=self._state_cache,
+                                   mcm_method=mcm_method)
                      for c in circuits)
 
     def compute_derivatives(self, circuits, execution_config=None):
@@ -228,8 +291,11 @@ class B200QubitDevice(Device):
         return self.execute(circuits, execution_config), self.compute_jvp(circuits, tangents, execution_config)
 
     def compute_vjp(self, circuits, cotangents, execution_config=None):
+        """default_qubit.py:1000-1034: the reverse sweep starts from the state the preceding
+        ``execute`` left in ``_state_cache`` (keyed by the circuit's hash) when there is one."""
         _, dt, fusion, _ = self._opts(execution_config)
-        return tuple(_adjoint.adjoint_vjp(_Tape(c), t, dtype=dt, fusion=fusion)
+        cache = getattr(self, "_state_cache", None) or {}
+        return tuple(_adjoint.adjoint_vjp(_Tape(c), t, dtype=dt, fusion=fusion, state=cache.get(c.map_to_standard_wires().hash))
                      for c, t in zip(circuits, cotangents))
 
     def execute_and_compute_vjp(self, circuits, cotangents, execution_config=None):

@@ -580,6 +580,7 @@ class ShardedStateVector:
         self.phys = list(range(self.n))
         self.stage_bytes = int(stage_bytes)
         self._stage = None
+        self._symm = None          # (buffer, handle, capacity) of the symmetric staging buffers
         self.stats = {"exchanges": 0, "exchange_bytes": 0, "run_steps": 0, "sweeps": 0}
         self.timer = None          # optional: callable(kind, fn) -> fn() (bench.py times steps)
         self.reset()
@@ -650,7 +651,14 @@ class ShardedStateVector:
     def run(self, program):
         if program["start"] != self.phys:
             raise ValueError("program compiled for another qubit map")
-        for kind, item in program["steps"]:
+        verbose = bool(os.environ.get("B200Q_SHARD_VERBOSE")) and self.rank == 0
+        for si, (kind, item) in enumerate(program["steps"]):
+            if verbose:
+                import sys
+                import time
+                import torch
+                torch.cuda.synchronize()
+                print(f"[sharded {time.time():.1f}] step {si}: {kind}", file=sys.stderr, flush=True)
             if kind == "run":
                 if item is not None:
                     if self.timer is not None:
@@ -720,6 +728,57 @@ class ShardedStateVector:
         self.run(self.compile(list(ops_)))
 
     # -- the exchange --------------------------------------------------------------------------
+    def _symm_stage(self, numel, dtype, device):
+        """Two staging buffers in SYMMETRIC memory (torch.distributed._symmetric_memory: every
+        rank can address every other rank's copy over NVLink), rendezvous'ed once and reused.
+        None when the backend is not NCCL on CUDA or the allocation is refused."""
+        if self._symm is False:
+            return None
+        if self._symm is not None and self._symm[2] >= numel and self._symm[0].dtype == dtype:
+            return self._symm
+        try:
+            import torch.distributed._symmetric_memory as symm
+
+            if device.type != "cuda" or os.environ.get("B200Q_EXCHANGE", "symm") != "symm":
+                raise RuntimeError("symmetric exchange disabled")
+            buf = symm.empty(2 * numel, dtype=dtype, device=device)
+            hdl = symm.rendezvous(buf, self.group if self.group is not None else self.dist.group.WORLD)
+            self._symm = (buf, hdl, numel)
+        except Exception as e:                       # noqa: BLE001 - any failure -> NCCL path
+            self._symm = False
+            self._symm_error = repr(e)
+            return None
+        return self._symm
+
+    def _exchange_symm(self, data, partners, q, chunk, piece):
+        """The exchange as PULLS over NVLink peer memory (K9 of SURVEY.md section 2c).  Per
+        piece: every rank copies what it gives away into its staging buffer (a local copy), one
+        device-side barrier, then every rank copies what it receives straight out of its partners'
+        staging buffers into place.  Two staging buffers alternate, so the barrier of piece i+1
+        (stream ordered behind the pulls of piece i on every rank) is also the "staging buffer i
+        may be overwritten" signal: one barrier per piece.  No NCCL send/recv, no copy back."""
+        buf, hdl, cap = self._symm
+        half = cap
+        B = data.shape[0]
+        it = 0
+        for b in range(B):
+            row = data[b]
+            for off in range(0, chunk, piece):
+                pp = it & 1
+                it += 1
+                for s, (j, r) in enumerate(partners):
+                    buf[pp * half + s * piece: pp * half + (s + 1) * piece].copy_(
+                        row[j * chunk + off: j * chunk + off + piece])
+                hdl.barrier(channel=pp)
+                for s, (j, r) in enumerate(partners):
+                    # partner r holds value j of the exchanged bits; in ITS partner list (all
+                    # values but j, ascending) my value q sits at index q - (q > j)
+                    s_there = q - (1 if q > j else 0)
+                    remote = hdl.get_buffer(r, (piece,), data.dtype, pp * half + s_there * piece)
+                    row[j * chunk + off: j * chunk + off + piece].copy_(remote)
+        hdl.barrier(channel=0)
+        hdl.barrier(channel=1)
+
     def exchange(self, ex: ExchangeStep):
         """Swap rank bits ``ex.rank_bits`` with local physical bits ``nl-k .. nl-1``."""
         import torch
@@ -742,6 +801,11 @@ class ShardedStateVector:
         itemsize = data.element_size()
         per_partner = max(1, self.stage_bytes // (itemsize * len(partners)))
         piece = min(chunk, 1 << (per_partner.bit_length() - 1))
+        if data.is_cuda and self._symm_stage(piece * len(partners), data.dtype, data.device) is not None:
+            self._exchange_symm(data, partners, q, chunk, piece)
+            self.stats["exchanges"] += 1
+            self.stats["exchange_bytes"] += B * chunk * len(partners) * itemsize
+            return
         if self._stage is None or self._stage.numel() < piece * len(partners) or \
                 self._stage.dtype != data.dtype:
             self._stage = torch.empty(piece * len(partners), dtype=data.dtype, device=data.device)

@@ -185,8 +185,10 @@ def _expval_pauli(sv, ps):
     return sv.expval_pauli_sentence(ps)
 
 
-def measure(mp, sv: StateVector, is_state_batched: bool = False):
-    """One analytic measurement (measure.py:224-239).
+def measure(mp, sv: StateVector, is_state_batched: bool = False, return_torch: bool = False):
+    """One analytic measurement (measure.py:224-239).  ``return_torch`` (device option, SURVEY
+    section 8 f2): ``state`` and ``probs`` — the results whose size grows with the register — stay
+    on the device and come back as torch CUDA tensors; no device-to-host copy is made.
 
     Strategy (the kernel-side replacement of ``get_measurement_function``, measure.py:165-221):
     observables with a Pauli representation go through the fused Pauli-sum reduction (no copy of
@@ -196,11 +198,17 @@ def measure(mp, sv: StateVector, is_state_batched: bool = False):
     kind = mp.kind
     obs = mp.obs
     if kind == "state":
+        if return_torch:
+            flat = sv.data.clone()
+            return flat if is_state_batched else flat[0]
         flat = sv.data.cpu().numpy()
         return flat if is_state_batched else flat[0]
     if kind == "probs":
         rot = _rotated(sv, mp.diagonalizing_gates()) if obs is not None else sv
         wires = list(mp.wires) if len(mp.wires) else list(range(sv.n))
+        if return_torch:
+            p = rot.probs_device(wires)
+            return p if sv.batch > 1 else p.reshape(-1)
         p = rot.probs(wires)
         return p
     if kind in ("density_matrix", "purity", "vn_entropy", "mutual_info"):
@@ -469,14 +477,14 @@ def measure_with_samples(mps, sv: StateVector, shots, rng, exact: bool = True,
 
 
 def measure_final_state(circuit, sv: StateVector, is_state_batched: bool, rng=None,
-                        exact_sampling: bool = True, mid_measurements=None):
+                        exact_sampling: bool = True, mid_measurements=None, return_torch: bool = False):
     """simulate.py:246-304."""
     if not circuit.shots:
         if mid_measurements is not None:
             raise TypeError("Native mid-circuit measurements are only supported with finite shots.")
         if len(circuit.measurements) == 1:
-            return measure(circuit.measurements[0], sv, is_state_batched)
-        return tuple(measure(mp, sv, is_state_batched) for mp in circuit.measurements)
+            return measure(circuit.measurements[0], sv, is_state_batched, return_torch)
+        return tuple(measure(mp, sv, is_state_batched, return_torch) for mp in circuit.measurements)
     rng = np.random.default_rng(rng)
     results = measure_with_samples(circuit.measurements, sv, circuit.shots, rng, exact_sampling,
                                    mid_measurements=mid_measurements)
@@ -623,11 +631,16 @@ def _prefix_state(ops_, n, dtype, device, fusion):
 
 
 def simulate(circuit, rng=None, dtype=np.complex128, device=None, exact_sampling: bool = True,
-             state_cache=None, fusion: int = 0, debugger=None):
-    """simulate.py:308-393.  Tapes with ``MidMeasure`` operations take the native one-shot
-    path (:356-381; tree-traversal is not built)."""
+             state_cache=None, fusion: int = 0, debugger=None, mcm_method=None,
+             return_torch: bool = False):
+    """simulate.py:308-393.  Tapes with ``MidMeasure`` operations take the tree-traversal path
+    when ``mcm_method == "tree-traversal"`` (:350-352, tree_mcm.py) and the native one-shot path
+    otherwise (:356-381)."""
     circuit = circuit.map_to_standard_wires()
     if any(is_mcm(op) for op in circuit.operations):
+        if mcm_method == "tree-traversal":
+            from .tree_mcm import simulate_tree_mcm
+            return simulate_tree_mcm(circuit, rng, dtype, device, exact_sampling, fusion, debugger)
         return _simulate_native_mcm(circuit, rng, dtype, device, exact_sampling, fusion, debugger)
     if debugger is not None and debugger.active and circuit.shots:
         rng = np.random.default_rng(rng)        # snapshots and final sampling share one stream
@@ -639,7 +652,8 @@ def simulate(circuit, rng=None, dtype=np.complex128, device=None, exact_sampling
         circuit = _OneShotView(circuit, sv.postselected_shots)     # circuit._shots = new_shots, :232
     if state_cache is not None:
         state_cache[circuit.hash] = sv
-    return measure_final_state(circuit, sv, batched, rng=rng, exact_sampling=exact_sampling)
+    return measure_final_state(circuit, sv, batched, rng=rng, exact_sampling=exact_sampling,
+                               return_torch=return_torch)
 
 
 __all__ = ["get_final_state", "apply_gates", "measure", "measure_with_samples",

@@ -214,3 +214,55 @@ def test_result_nesting_of_derivatives():
     res, jac = dev.execute_and_compute_derivatives((one, two_p))
     assert len(res) == 2 and len(jac) == 2
     assert abs(res[0] - np.cos(0.3)) < 1e-14 and abs(float(jac[0]) + np.sin(0.3)) < 1e-14
+
+
+def test_return_torch_keeps_state_probs_and_jacobian_on_the_device(monkeypatch):
+    """Device option ``return_torch``: ``state`` / ``probs`` results are
+    torch CUDA tensors and no device-to-host copy happens while producing them; the adjoint
+    Jacobian comes back as one CUDA tensor."""
+    import torch
+
+    import pennylane_b200 as qb
+    from oracle import simulate as o_sim
+    from pennylane_b200 import ops as q
+
+    n = 12
+    rng = np.random.default_rng(4)
+    ops_ = []
+    for w in range(n):
+        ops_ += [q.RY(rng.uniform(0, 6), wires=w), q.RZ(rng.uniform(0, 6), wires=w)]
+    ops_ += [q.CNOT(wires=[w, (w + 1) % n]) for w in range(n)]
+    tape = qb.QuantumScript(ops_, [qb.state(), qb.probs(wires=[0, 3, 5])])
+    dev = qb.B200Qubit(wires=n, return_torch=True)
+    batch, cfg = dev.preprocess(tape)
+    dev.execute(batch, cfg)                                   # warm-up: allocations, module loads
+    calls = {"n": 0}
+    real_cpu, real_item = torch.Tensor.cpu, torch.Tensor.item
+
+    def counting_cpu(self, *a, **k):
+        if self.is_cuda:
+            calls["n"] += 1
+        return real_cpu(self, *a, **k)
+
+    def counting_item(self, *a, **k):
+        if self.is_cuda:
+            calls["n"] += 1
+        return real_item(self, *a, **k)
+
+    monkeypatch.setattr(torch.Tensor, "cpu", counting_cpu)
+    monkeypatch.setattr(torch.Tensor, "item", counting_item)
+    state, probs = dev.execute(batch, cfg)[0]
+    monkeypatch.undo()
+    assert calls["n"] == 0, "a device-to-host copy happened with return_torch"
+    assert isinstance(state, torch.Tensor) and state.is_cuda and state.dtype == torch.complex128
+    assert isinstance(probs, torch.Tensor) and probs.is_cuda and probs.shape == (8,)
+    ref, _ = o_sim.get_final_state(tape)
+    assert np.max(np.abs(state.cpu().numpy() - np.asarray(ref).reshape(-1))) < 1e-12
+    ref_p = o_sim.measure_final_state(qb.QuantumScript(ops_, [qb.probs(wires=[0, 3, 5])]), ref, False)
+    assert np.max(np.abs(probs.cpu().numpy() - ref_p)) < 1e-12
+    # Jacobian
+    tape_g = qb.QuantumScript(ops_, [qb.expval(q.PauliZ(wires=0)), qb.expval(q.PauliX(wires=2))])
+    jac_t = dev.compute_derivatives(tape_g, cfg)
+    jac_n = qb.B200Qubit(wires=n).compute_derivatives(tape_g)
+    assert isinstance(jac_t, torch.Tensor) and jac_t.is_cuda and jac_t.shape == (2, 2 * n)
+    assert np.max(np.abs(jac_t.cpu().numpy() - np.array(jac_n, dtype=float))) < 1e-14
