@@ -404,6 +404,45 @@ def run_ours(args):
             byt = sum(credited_bytes(op, n) for op in plist)
             gb = byt / (e0.elapsed_time(e1) * 1e-3) / 1e9
             per_gate[name] = {"kernel": kernel_of[name], "launches": len(plist), "gbps": gb, "frac": gb / peak}
+            # per wire position (the bit-0 cases): a CNOT whose CONTROL is index bit 0
+            # touches every other 16-byte amplitude, DRAM still moves whole 32-byte sectors, so
+            # that position can reach at most half of its credited roofline
+            per_wire = {}
+            for op in plist:
+                e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+                e0.record()
+                sv.apply_operation(op); sv.apply_operation(op)
+                e1.record()
+                torch.cuda.synchronize()
+                per_wire[str(list(op.wires))] = round(
+                    2 * credited_bytes(op, n) / (e0.elapsed_time(e1) * 1e-3) / 1e9 / peak, 3)
+            per_gate[name]["frac_per_wires"] = per_wire
+        # Wide dense blocks (apply_operation.py:202-255, the tensordot path): compute-bound from
+        # K = 5 on — 4 * 2^K DFMA per amplitude against 32 bytes — so their roofline is the FP64
+        # pipe (34.1 TFLOP/s measured with tools/micro/fp64_forms.cu, profiles/r2_fp64_forms.txt).
+        fp64_peak = 34.1e12
+        rng_u = np.random.default_rng(5)
+        for K in (4, 6, 8):
+            m = np.linalg.qr(rng_u.normal(size=(1 << K, 1 << K)) + 1j * rng_u.normal(size=(1 << K, 1 << K)))[0]
+            wires_k = sorted({int(round(x)) for x in np.linspace(1, n - 2, K)})
+            while len(wires_k) < K:
+                wires_k = sorted(set(wires_k) | {len(wires_k)})
+            op = q.QubitUnitary(m, wires=wires_k[:K])
+            sv.apply_operation(op)
+            torch.cuda.synchronize()
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+            sv.apply_operation(op)
+            e1.record()
+            torch.cuda.synchronize()
+            secs = e0.elapsed_time(e1) * 1e-3
+            flops = 8.0 * (1 << K) * (1 << n)            # 4 FMA = 8 flop per complex multiply-add
+            per_gate[f"dense_k{K}"] = {"kernel": "k_dense_big<double,2048> (register-blocked)", "launches": 1,
+                                       "ms": secs * 1e3, "tflops": flops / secs / 1e12,
+                                       "frac_fp64": flops / secs / fp64_peak,
+                                       "gbps": 2 * 16.0 * (1 << n) / secs / 1e9,
+                                       "frac": 2 * 16.0 * (1 << n) / secs / 1e9 / peak,
+                                       "bound": "fp64" if K >= 5 else "hbm"}
         roofline["per_gate_kernels"] = per_gate
 
         # Measurement-side kernels outside the expval of the step: the two sweeps of a native

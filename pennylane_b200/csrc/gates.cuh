@@ -128,15 +128,40 @@ k_dense_big(cx<T>* __restrict__ state, const BigArgs a, const cx<T>* __restrict_
       }
     }
     __syncthreads();
+    // Register blocking: the PER outputs of a thread (e = tid + 256 p) share either their group
+    // (G <= 256: the column entry xs[c][gi] is loaded once per c and meets PER matrix rows) or
+    // their row (G > 256: one matrix entry meets PER groups).  The first version looped over c
+    // per output: two loads for every complex multiply-add (4 DFMA), i.e. bound by load issue;
+    // now PER complex multiply-adds share 1 + PER loads, and the contraction runs at the FP64
+    // pipe rate from K = 5 on (its roofline: 4 * 2^K DFMA per amplitude, see
+    // bench.py `per_gate_kernels.dense_k*`).
     cx<T> y[PER];
 #pragma unroll
-    for (int p = 0; p < PER; ++p) {
-      const int e = threadIdx.x + p * 256;
-      const int gi = e & (G - 1), r = e >> lgG;
-      cx<T> acc = make_cx<T>(0, 0);
-      const cx<T>* mrow = mat + (size_t)r * D;
-      for (int c = 0; c < D; ++c) cmac(acc, __ldg(mrow + c), xs[c * G + gi]);
-      y[p] = acc;
+    for (int p = 0; p < PER; ++p) y[p] = make_cx<T>(0, 0);
+    if (G <= 256) {
+      const int gi = threadIdx.x & (G - 1);
+      const int r0 = threadIdx.x >> lgG;                 // rows r0 + p * (256 / G)
+      const int rstep = 256 >> lgG;
+      const cx<T>* mrow = mat + (size_t)r0 * D;
+      const size_t mstep = (size_t)rstep * D;
+#pragma unroll 2
+      for (int c = 0; c < D; ++c) {
+        const cx<T> x = xs[c * G + gi];
+#pragma unroll
+        for (int p = 0; p < PER; ++p) cmac(y[p], __ldg(mrow + p * mstep + c), x);
+      }
+    } else {
+      // G is a multiple of 256: all PER outputs of a thread are in rows r = p * 256 / G ... with
+      // group gi = (tid + 256 p) & (G - 1)
+#pragma unroll
+      for (int p = 0; p < PER; ++p) {
+        const int e = threadIdx.x + p * 256;
+        const int gi = e & (G - 1), r = e >> lgG;
+        const cx<T>* mrow = mat + (size_t)r * D;
+        cx<T> acc = make_cx<T>(0, 0);
+        for (int c = 0; c < D; ++c) cmac(acc, __ldg(mrow + c), xs[c * G + gi]);
+        y[p] = acc;
+      }
     }
     __syncthreads();
 #pragma unroll

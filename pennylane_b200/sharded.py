@@ -553,6 +553,10 @@ class CudaEngine:
 
 # ---------------------------------------------------------------------------------------------
 # the sharded statevector
+#: process-wide symmetric staging buffers: (id(group), dtype) -> (buffer, handle, capacity) | False
+_SYMM_CACHE: dict = {}
+
+
 # ---------------------------------------------------------------------------------------------
 class ShardedStateVector:
     """``2**n`` amplitudes over ``dist.get_world_size()`` ranks (a power of two)."""
@@ -730,25 +734,54 @@ class ShardedStateVector:
     # -- the exchange --------------------------------------------------------------------------
     def _symm_stage(self, numel, dtype, device):
         """Two staging buffers in SYMMETRIC memory (torch.distributed._symmetric_memory: every
-        rank can address every other rank's copy over NVLink), rendezvous'ed once and reused.
-        None when the backend is not NCCL on CUDA or the allocation is refused."""
+        rank can address every other rank's copy over NVLink).  Allocated and rendezvous'ed ONCE
+        per process and (group, dtype) and shared by every ShardedStateVector; the decision to use
+        them is COLLECTIVE (a rank whose allocation failed would otherwise take the NCCL path
+        while its partners wait in the device-side barrier).  None -> NCCL send/recv."""
         if self._symm is False:
             return None
         if self._symm is not None and self._symm[2] >= numel and self._symm[0].dtype == dtype:
             return self._symm
+        key = (id(self.group), str(dtype))
+        cached = _SYMM_CACHE.get(key)
+        if cached is False:
+            self._symm = False
+            return None
+        if cached is not None and cached[2] >= numel:
+            self._symm = cached
+            return cached
+        import torch
+
+        entry, err = None, ""
         try:
             import torch.distributed._symmetric_memory as symm
 
             if device.type != "cuda" or os.environ.get("B200Q_EXCHANGE", "symm") != "symm":
                 raise RuntimeError("symmetric exchange disabled")
             buf = symm.empty(2 * numel, dtype=dtype, device=device)
-            hdl = symm.rendezvous(buf, self.group if self.group is not None else self.dist.group.WORLD)
-            self._symm = (buf, hdl, numel)
+            ok = torch.ones(1, dtype=torch.int32, device=device)
         except Exception as e:                       # noqa: BLE001 - any failure -> NCCL path
-            self._symm = False
-            self._symm_error = repr(e)
+            err = repr(e)
+            buf = None
+            ok = torch.zeros(1, dtype=torch.int32, device=device) if device.type == "cuda" else None
+        if ok is None:
+            _SYMM_CACHE[key] = self._symm = False
             return None
-        return self._symm
+        self.dist.all_reduce(ok, op=self.dist.ReduceOp.MIN, group=self.group)
+        if int(ok.item()) == 1:
+            try:
+                hdl = symm.rendezvous(buf, self.group if self.group is not None else self.dist.group.WORLD)
+                entry = (buf, hdl, numel)
+            except Exception as e:                   # noqa: BLE001
+                err = repr(e)
+        ok2 = torch.tensor([1 if entry is not None else 0], dtype=torch.int32, device=device)
+        self.dist.all_reduce(ok2, op=self.dist.ReduceOp.MIN, group=self.group)
+        if int(ok2.item()) != 1:
+            entry = None
+        _SYMM_CACHE[key] = entry if entry is not None else False
+        self._symm = _SYMM_CACHE[key]
+        self._symm_error = err
+        return entry
 
     def _exchange_symm(self, data, partners, q, chunk, piece):
         """The exchange as PULLS over NVLink peer memory (K9 of SURVEY.md section 2c).  Per
@@ -761,11 +794,19 @@ class ShardedStateVector:
         half = cap
         B = data.shape[0]
         it = 0
+        verbose = bool(os.environ.get("B200Q_SHARD_VERBOSE")) and self.rank == 0
         for b in range(B):
             row = data[b]
             for off in range(0, chunk, piece):
                 pp = it & 1
                 it += 1
+                if verbose and (it & 15) == 1:
+                    import sys
+                    import time
+                    import torch
+                    torch.cuda.synchronize()
+                    print(f"[sharded {time.time():.1f}]   exchange piece {it} (chunk {chunk}, piece {piece})",
+                          file=sys.stderr, flush=True)
                 for s, (j, r) in enumerate(partners):
                     buf[pp * half + s * piece: pp * half + (s + 1) * piece].copy_(
                         row[j * chunk + off: j * chunk + off + piece])
