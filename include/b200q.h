@@ -230,8 +230,12 @@ int b200q_apply_rtile_bcast(void* vec0, void* vec1, int n, int dtype, int64_t ba
  *   state); coef_host[n_coef] doubles: matrix coefficients in the order the body consumes them;
  *   coef_mode 0: one table, staged in shared memory; 1: `batch` tables, batch element b reads
  *   table b (broadcast parameters); 2: the table is passed as a kernel parameter (kernels
- *   compiled with SK_COEF_PARAM: coefficients become constant-bank operands); vec1 / nslots / write0 / scale / out_dev: adjoint mode,
- *   as for b200q_apply_rtile.
+ *   compiled with SK_COEF_PARAM: coefficients become constant-bank operands); vec1 / nslots /
+ *   write0 / scale / out_dev: adjoint mode, as for b200q_apply_rtile;
+ *   fix_mask / fix_val: PARTIAL launch — the non-tile index bits of fix_mask are held at
+ *   fix_val and only those 2^(n-T-popc(fix_mask)) tiles are processed (0, 0: the whole state).
+ *   The sharded engine runs the segments on either side of an exchange piece by piece so that
+ *   the NVLink transfer of piece p overlaps the sweeps of the other pieces.
  * Replaces simulate.py:214-235 (gate loop) and adjoint_jacobian.py:121-137 (reverse sweep). */
 int b200q_jit_available(void);
 int b200q_jit_compile(const char* source, const char* const* header_names,
@@ -243,8 +247,18 @@ int b200q_seg_unload(void* handle);
 int b200q_seg_launch(void* handle, void* vec0, void* vec1, int n, int dtype, int64_t batch,
                      const int* tile_bits, int T, int L, int RB, int minb, const int* ext_pos,
                      int n_ext, const double* coef_host, int n_coef, int coef_mode, int nslots,
-                     int write0, uint64_t base_hi, double scale, double* out_dev, void* work,
-                     size_t work_bytes, void* stream);
+                     int write0, uint64_t base_hi, uint64_t fix_mask, uint64_t fix_val, double scale,
+                     double* out_dev, void* work, size_t work_bytes, void* stream);
+
+/* Qubit-remapping exchange, data movement (K9 of SURVEY.md section 2c: the remap pack / unpack
+ * pair).  One PIECE of an exchanged slab is `count` runs of `run_bytes` bytes, `src_pitch` /
+ * `dst_pitch` bytes apart (pack: state -> dense staging buffer, dst_pitch == run_bytes; unpack:
+ * a partner's staging buffer, mapped over NVLink, -> state, src_pitch == run_bytes).  Issued on
+ * the copy engines (cudaMemcpy2DAsync; a loop of contiguous copies when the pitch exceeds the
+ * 2 GiB pitch limit), so it runs beside the segment kernels, which occupy every SM.
+ * The reference has no analogue (default.qubit is one array). */
+int b200q_remap_copy(void* dst, size_t dst_pitch, const void* src, size_t src_pitch,
+                     size_t run_bytes, size_t count, void* stream);
 
 /* One reverse-sweep step of adjoint differentiation on vecs = [1 + n_bras][2^n] (row 0 = ket):
  *   z_b = <bra_b| G |ket>,  ket <- A ket,  bra_b <- A bra_b      (A = U^dagger, k <= 3)

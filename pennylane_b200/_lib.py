@@ -67,7 +67,8 @@ SIGNATURES = {
     "b200q_seg_load": (_i, [_p, _sz, C.POINTER(_p)]),
     "b200q_seg_unload": (_i, [_p]),
     "b200q_seg_launch": (_i, [_p, _p, _p, _i, _i, _i64, _ip, _i, _i, _i, _i, _ip, _i, _dp, _i, _i,
-                              _i, _i, _u64, _d, _p, _p, _sz, _p]),
+                              _i, _i, _u64, _u64, _u64, _d, _p, _p, _sz, _p]),
+    "b200q_remap_copy": (_i, [_p, _sz, _p, _sz, _sz, _sz, _p]),
     "b200q_adjoint_step": (_i, [_p, _i, _i, _i, _ip, _i, _ip, _ip, _i, _p, _p, _p, _p, _sz, _p]),
 }
 

@@ -423,7 +423,7 @@ __device__ __forceinline__ unsigned long long sk_gscatter(unsigned j, const SkAr
   return off;
 }
 __device__ __forceinline__ unsigned long long sk_tile_base(const SkArgs& a, const unsigned long long t) {
-  unsigned long long base = 0;
+  unsigned long long base = a.base_fix;
   for (int r = 0; r < a.nruns; ++r)
     base |= ((t >> a.run_s[r]) & ((1ull << a.run_len[r]) - 1ull)) << a.run_g[r];
   return base;

@@ -15,4 +15,6 @@ struct SkArgs {
   signed char ext_pos[16];        // global positions of the external predicate bits
   unsigned long long ntiles;      // 2^(n-T)
   unsigned long long base_hi;     // OR-ed into the tile base for external predicates (rank bits)
+  unsigned long long base_fix;    // partial launch: non-tile bits held fixed (OR-ed into every tile base);
+                                  // ntiles / runs then enumerate the remaining non-tile bits only
 };

@@ -207,8 +207,8 @@ int b200q_seg_unload(void* handle) {
 int b200q_seg_launch(void* handle, void* vec0, void* vec1, int n, int dtype, int64_t batch,
                      const int* tile_bits, int T, int L, int RB, int minb, const int* ext_pos, int n_ext,
                      const double* coef_host, int n_coef, int coef_mode, int nslots, int write0,
-                     uint64_t base_hi, double scale, double* out_dev, void* work, size_t work_bytes,
-                     void* stream) {
+                     uint64_t base_hi, uint64_t fix_mask, uint64_t fix_val, double scale, double* out_dev,
+                     void* work, size_t work_bytes, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   B200Q_REQUIRE(handle && vec0 && tile_bits && coef_host, "seg_launch: null argument");
   B200Q_REQUIRE(dtype == B200Q_C64 || dtype == B200Q_C128, "seg_launch: unknown dtype %d", dtype);
@@ -221,7 +221,9 @@ int b200q_seg_launch(void* handle, void* vec0, void* vec1, int n, int dtype, int
                 "seg_launch: bulk copies need 16-byte aligned runs");
   SkArgs a;
   memset(&a, 0, sizeof(a));
-  a.n = n; a.write0 = write0; a.base_hi = base_hi;
+  a.n = n; a.write0 = write0; a.base_hi = base_hi; a.base_fix = fix_val;
+  B200Q_REQUIRE((fix_val & ~fix_mask) == 0 && (n >= 64 || (fix_mask >> n) == 0),
+                "seg_launch: fixed bits outside the mask / the state");
   uint64_t inmask = 0;
   for (int i = 0; i < T; ++i) {
     const int b = tile_bits[i];
@@ -231,9 +233,11 @@ int b200q_seg_launch(void* handle, void* vec0, void* vec1, int n, int dtype, int
     inmask |= 1ull << b;
     if (i >= L) a.hi_bits[i - L] = (signed char)b;
   }
-  int no = 0;
+  B200Q_REQUIRE((inmask & fix_mask) == 0, "seg_launch: a tile bit cannot be held fixed");
+  int no = 0, nfix = 0;
   for (int b = 0; b < n; ++b) {
     if ((inmask >> b) & 1) continue;
+    if ((fix_mask >> b) & 1) { ++nfix; continue; }
     if (a.nruns > 0 && a.run_g[a.nruns - 1] + a.run_len[a.nruns - 1] == b) {
       a.run_len[a.nruns - 1]++;
     } else {
@@ -247,7 +251,7 @@ int b200q_seg_launch(void* handle, void* vec0, void* vec1, int n, int dtype, int
     B200Q_REQUIRE(ext_pos[e] >= 0 && ext_pos[e] < 64, "seg_launch: bad external bit %d", ext_pos[e]);
     a.ext_pos[e] = (signed char)ext_pos[e];
   }
-  a.ntiles = 1ull << (n - T);
+  a.ntiles = 1ull << (n - T - nfix);
   const int NV = vec1 ? 2 : 1;
   CUtensorMap tm[2];
   memset(tm, 0, sizeof(tm));
@@ -298,6 +302,32 @@ int b200q_seg_launch(void* handle, void* vec0, void* vec1, int n, int dtype, int
     k_sk_final_reduce<<<(unsigned)(batch * nslots), 256, 0, s>>>(partials, out_dev, (int)grid.x, scale);
     B200Q_LAUNCH_CHECK();
   }
+  return 0;
+}
+
+int b200q_remap_copy(void* dst, size_t dst_pitch, const void* src, size_t src_pitch, size_t run_bytes,
+                     size_t count, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  B200Q_REQUIRE(dst && src && run_bytes > 0 && count > 0, "remap_copy: null / empty argument");
+  B200Q_REQUIRE(dst_pitch >= run_bytes && src_pitch >= run_bytes, "remap_copy: pitch smaller than a run");
+  if (count == 1 || (dst_pitch == run_bytes && src_pitch == run_bytes)) {
+    B200Q_CHECK(cudaMemcpyAsync(dst, src, run_bytes * count, cudaMemcpyDefault, s));
+    return 0;
+  }
+  static const size_t max_pitch = [] {
+    int dev = 0;
+    cudaDeviceProp p;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&p, dev) != cudaSuccess) return (size_t)0x7fffffff;
+    return (size_t)p.memPitch;
+  }();
+  if (dst_pitch <= max_pitch && src_pitch <= max_pitch) {
+    B200Q_CHECK(cudaMemcpy2DAsync(dst, dst_pitch, src, src_pitch, run_bytes, count, cudaMemcpyDefault, s));
+    return 0;
+  }
+  B200Q_REQUIRE(count <= 4096, "remap_copy: %zu runs with a pitch above the 2D-copy limit", count);
+  for (size_t i = 0; i < count; ++i)
+    B200Q_CHECK(cudaMemcpyAsync((char*)dst + i * dst_pitch, (const char*)src + i * src_pitch, run_bytes,
+                                cudaMemcpyDefault, s));
   return 0;
 }
 

@@ -693,8 +693,10 @@ def stats() -> dict:
 
 
 def launch(plan: SegPlan, coefs: np.ndarray, vec0_ptr, vec1_ptr, n: int, batch: int, work, work_bytes,
-           stream, base_hi: int = 0, write0: int = 1, scale: float = 1.0, out_ptr=None):
-    """One segment launch (``b200q_seg_launch``)."""
+           stream, base_hi: int = 0, write0: int = 1, scale: float = 1.0, out_ptr=None,
+           fix_mask: int = 0, fix_val: int = 0):
+    """One segment launch (``b200q_seg_launch``).  ``fix_mask`` / ``fix_val``: partial launch over
+    the tiles whose (non-tile) index bits ``fix_mask`` equal ``fix_val``."""
     lib = load()
     g = plan.geom
     h = kernel_for(plan)
@@ -707,4 +709,5 @@ def launch(plan: SegPlan, coefs: np.ndarray, vec0_ptr, vec1_ptr, n: int, batch: 
         g.MINB, int_array(plan.ext_pos) if plan.ext_pos else None, len(plan.ext_pos),
         coefs.ctypes.data_as(C.POINTER(C.c_double)), int(coefs.shape[-1]),
         (2 if plan.coef_param else 1 if batched else 0),
-        plan.nslots, write0, int(base_hi), float(scale), out_ptr, work, work_bytes, stream))
+        plan.nslots, write0, int(base_hi), int(fix_mask), int(fix_val), float(scale), out_ptr, work,
+        work_bytes, stream))

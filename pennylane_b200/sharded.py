@@ -324,6 +324,17 @@ def plan(ops_, n, g, phys=None, bit_of=None, defer=None):
     return steps, phys
 
 
+def _free_bit_window(busy, top, pb_max, min_bit):
+    """Highest run of ``pb`` consecutive index bits in [min_bit, top) that ``busy`` leaves free,
+    for the largest ``pb <= pb_max`` that has one: (lo, pb) or None."""
+    for pb in range(pb_max, 0, -1):
+        m = (1 << pb) - 1
+        for lo in range(top - pb, min_bit - 1, -1):
+            if not (busy >> lo) & m:
+                return lo, pb
+    return None
+
+
 def _defer_trailing_1q(run, keep, remaining, leaving, bit_of, deferred_once):
     """Move the trailing single-qubit gates of a run step into the next one when the first gate
     waiting on their wire is a CNOT targeting it.
@@ -406,6 +417,36 @@ class CudaEngine:
         for seg in items:
             self.sv.run_segment(seg)
         return len(items)
+
+    def units(self, handle):
+        """The separately launchable parts of a compiled run step: ``[(unit, busy)]`` with
+        ``busy`` = mask of the local index bits the unit acts on when it can also run on a
+        SUBSET of the state (partial launches of the specialised segment kernels: any index bit
+        outside ``busy`` may be held fixed), else ``None``.  ``None`` for the whole handle: not
+        divisible (per-gate mode, broadcast states)."""
+        kind, items = handle
+        if kind != "segs" or self.sv.batch != 1:
+            return None
+        out = []
+        for seg in items:
+            busy = None
+            if self.sv.segment_partial_ok(seg):
+                busy = 0
+                for b in seg.tile_bits:
+                    busy |= 1 << int(b)
+            out.append((seg, busy))
+        return out
+
+    def run_unit(self, seg, fix_mask: int = 0, fix_val: int = 0):
+        self.sv.run_segment(seg, 0, fix_mask, fix_val)
+        return 1
+
+    def remap_copy(self, dst_ptr, dst_pitch, src_ptr, src_pitch, run_bytes, count, stream):
+        """``b200q_remap_copy``: the pack / unpack copies of an exchange piece, on the copy engines."""
+        from ._lib import check
+
+        check(self.sv.lib.b200q_remap_copy(C.c_void_p(dst_ptr), dst_pitch, C.c_void_p(src_ptr), src_pitch,
+                                           run_bytes, count, C.c_void_p(stream)))
 
     # -- reductions ------------------------------------------------------------------------
     def expval_terms(self, xs, zs, ys, cs):
@@ -649,32 +690,131 @@ class ShardedStateVector:
                 prog.append(("run", self.engine.compile(lops) if lops else None))
             else:
                 prog.append(("exchange", st))
-        return {"steps": prog, "start": list(self.phys), "final": final,
+        return {"steps": prog, "schedule": self._schedule(prog), "start": list(self.phys), "final": final,
                 "n_exchanges": sum(1 for k, _ in prog if k == "exchange")}
+
+    # -- overlap of exchanges with the sweeps around them ----------------------------------------
+    def _schedule(self, steps):
+        """Program steps -> execution schedule.  An exchange moves whole slabs of the shard (the
+        values of the top ``k`` local bits); cut along ``pb`` further index bits it becomes
+        ``2**pb`` independent PIECES.  A fused segment whose tile does not contain those bits
+        can run piece by piece too (a partial launch), so the segments just before and just
+        after an exchange are pipelined against it: piece p is swept, its transfer starts on
+        the copy engines / NVLink while piece p+1 is swept, and the first segment after the
+        exchange starts on piece 0 as soon as that piece has arrived.  Entries:
+          ("run", handle) | ("units", [unit]) | ("exchange", ex)
+          ("window", [units before], ex, [units after], lo, pb)   # piece bits lo .. lo+pb-1
+        Knobs: B200Q_EXCHANGE_PIECE_BITS (default 3, 0 = no overlap), B200Q_EXCHANGE_WINDOW
+        (segments per side, default 2)."""
+        pb_max = int(os.environ.get("B200Q_EXCHANGE_PIECE_BITS", "3"))
+        wmax = int(os.environ.get("B200Q_EXCHANGE_WINDOW", "2"))
+        min_bit = int(os.environ.get("B200Q_EXCHANGE_MIN_BIT", "5"))
+        units_of = getattr(self.engine, "units", None)
+        items = []                                   # ["run", handle] | ["unit", unit, busy] | ["exchange", ex]
+        for kind, item in steps:
+            if kind == "run":
+                us = units_of(item) if (item is not None and units_of is not None and pb_max > 0 and wmax > 0) else None
+                if us is None:
+                    items.append(["run", item])
+                else:
+                    items.extend(["unit", u, busy] for u, busy in us)
+            else:
+                items.append(["exchange", item])
+        claimed: dict = {}                           # item index -> exchange index
+        windows: dict = {}
+        for i, it in enumerate(items):
+            if it[0] != "exchange":
+                continue
+            top = self.nl - it[1].k
+            before, j = [], i - 1
+            while j >= 0 and len(before) < wmax and items[j][0] == "unit" and items[j][2] is not None \
+                    and j not in claimed:
+                before.insert(0, j)
+                j -= 1
+            after, j = [], i + 1
+            while j < len(items) and len(after) < wmax and items[j][0] == "unit" and items[j][2] is not None:
+                after.append(j)
+                j += 1
+            best = None
+            for da in range(len(before), -1, -1):
+                for db in range(len(after), -1, -1):
+                    if da + db == 0:
+                        continue
+                    idx = before[len(before) - da:] + after[:db]
+                    busy = 0
+                    for x in idx:
+                        busy |= items[x][2]
+                    got = _free_bit_window(busy, top, pb_max, min_bit)
+                    if got is None:
+                        continue
+                    lo, pb = got
+                    score = (min(pb, 2), da + db, min(da, db), pb, lo)
+                    if best is None or score > best[0]:
+                        best = (score, before[len(before) - da:], after[:db], lo, pb)
+            if best is not None:
+                _, a_idx, b_idx, lo, pb = best
+                windows[i] = (a_idx, b_idx, lo, pb)
+                for x in a_idx + b_idx:
+                    claimed[x] = i
+        sched, pending = [], []
+
+        def flush():
+            if pending:
+                sched.append(("units", list(pending)))
+                pending.clear()
+
+        for i, it in enumerate(items):
+            if i in claimed:
+                continue
+            if it[0] == "unit":
+                pending.append(it[1])
+                continue
+            flush()
+            if it[0] == "run":
+                sched.append(("run", it[1]))
+            elif i in windows:
+                a_idx, b_idx, lo, pb = windows[i]
+                sched.append(("window", [items[x][1] for x in a_idx], it[1], [items[x][1] for x in b_idx], lo, pb))
+            else:
+                sched.append(("exchange", it[1]))
+        flush()
+        return sched
 
     def run(self, program):
         if program["start"] != self.phys:
             raise ValueError("program compiled for another qubit map")
-        verbose = bool(os.environ.get("B200Q_SHARD_VERBOSE")) and self.rank == 0
-        for si, (kind, item) in enumerate(program["steps"]):
-            if verbose:
-                import sys
-                import time
-                import torch
-                torch.cuda.synchronize()
-                print(f"[sharded {time.time():.1f}] step {si}: {kind}", file=sys.stderr, flush=True)
+        timed = self.timer if self.timer is not None else (lambda kind, fn: fn())
+        for entry in program["schedule"]:
+            kind = entry[0]
             if kind == "run":
-                if item is not None:
-                    if self.timer is not None:
-                        self.stats["sweeps"] += self.timer("run", lambda: self.engine.run(item))
-                    else:
-                        self.stats["sweeps"] += self.engine.run(item)
+                if entry[1] is not None:
+                    self.stats["sweeps"] += timed("run", lambda: self.engine.run(entry[1]))
                 self.stats["run_steps"] += 1
-            elif self.timer is not None:
-                self.timer("exchange", lambda: self.exchange(item))
+            elif kind == "units":
+                self.stats["sweeps"] += timed("run", lambda: sum(self.engine.run_unit(u) for u in entry[1]))
+            elif kind == "exchange":
+                timed("exchange", lambda: self.exchange(entry[1]))
             else:
-                self.exchange(item)
+                _, a_units, ex, b_units, lo, pb = entry
+                self.stats["sweeps"] += timed("window", lambda: self._run_window(a_units, ex, b_units, lo, pb))
+                self.stats["windows"] = self.stats.get("windows", 0) + 1
         self.phys = list(program["final"])
+
+    def _run_window(self, a_units, ex, b_units, lo, pb):
+        """[segments] -> exchange -> [segments], piece by piece (see :meth:`_schedule`)."""
+        P = 1 << pb
+        mask = (P - 1) << lo
+        ctx = self._exchange_begin(ex, lo, pb)
+        for p in range(P):
+            for u in a_units:
+                self.engine.run_unit(u, mask, p << lo)
+            self._exchange_piece(ctx, p)
+        for p in range(P):
+            self._exchange_wait(ctx, p)
+            for u in b_units:
+                self.engine.run_unit(u, mask, p << lo)
+        self._exchange_end(ctx)
+        return len(a_units) + len(b_units)
 
     def apply_mid_measure(self, op, mid_measurements: dict, rng=None):
         """``apply_mid_measure`` (apply_operation.py:415-497) on the sharded state.  The marginal
@@ -783,50 +923,21 @@ class ShardedStateVector:
         self._symm_error = err
         return entry
 
-    def _exchange_symm(self, data, partners, q, chunk, piece):
-        """The exchange as PULLS over NVLink peer memory (K9 of SURVEY.md section 2c).  Per
-        piece: every rank copies what it gives away into its staging buffer (a local copy), one
-        device-side barrier, then every rank copies what it receives straight out of its partners'
-        staging buffers into place.  Two staging buffers alternate, so the barrier of piece i+1
-        (stream ordered behind the pulls of piece i on every rank) is also the "staging buffer i
-        may be overwritten" signal: one barrier per piece.  No NCCL send/recv, no copy back."""
-        buf, hdl, cap = self._symm
-        half = cap
-        B = data.shape[0]
-        it = 0
-        verbose = bool(os.environ.get("B200Q_SHARD_VERBOSE")) and self.rank == 0
-        for b in range(B):
-            row = data[b]
-            for off in range(0, chunk, piece):
-                pp = it & 1
-                it += 1
-                if verbose and (it & 15) == 1:
-                    import sys
-                    import time
-                    import torch
-                    torch.cuda.synchronize()
-                    print(f"[sharded {time.time():.1f}]   exchange piece {it} (chunk {chunk}, piece {piece})",
-                          file=sys.stderr, flush=True)
-                for s, (j, r) in enumerate(partners):
-                    buf[pp * half + s * piece: pp * half + (s + 1) * piece].copy_(
-                        row[j * chunk + off: j * chunk + off + piece])
-                hdl.barrier(channel=pp)
-                for s, (j, r) in enumerate(partners):
-                    # partner r holds value j of the exchanged bits; in ITS partner list (all
-                    # values but j, ascending) my value q sits at index q - (q > j)
-                    s_there = q - (1 if q > j else 0)
-                    remote = hdl.get_buffer(r, (piece,), data.dtype, pp * half + s_there * piece)
-                    row[j * chunk + off: j * chunk + off + piece].copy_(remote)
-        hdl.barrier(channel=0)
-        hdl.barrier(channel=1)
-
     def exchange(self, ex: ExchangeStep):
-        """Swap rank bits ``ex.rank_bits`` with local physical bits ``nl-k .. nl-1``."""
-        import torch
+        """Swap rank bits ``ex.rank_bits`` with local physical bits ``nl-k .. nl-1`` (one piece:
+        the whole slabs)."""
+        ctx = self._exchange_begin(ex, self.nl - ex.k, 0)
+        self._exchange_piece(ctx, 0)
+        self._exchange_wait(ctx, 0)
+        self._exchange_end(ctx)
 
-        dist, k = self.dist, ex.k
+    def _exchange_begin(self, ex: ExchangeStep, lo: int, pb: int):
+        """Geometry of an exchange cut into ``2**pb`` pieces along index bits ``lo .. lo+pb-1``.
+        The data a rank gives to the partner that holds value ``j`` of the exchanged bits is slab
+        ``j`` of its shard (``chunk`` contiguous amplitudes) and what it receives lands in the same
+        slab; piece ``p`` of a slab is ``chunk >> (lo+pb)`` runs of ``2**lo`` amplitudes."""
+        k = ex.k
         data = self.engine.data                      # (B, 2**nl)
-        B = data.shape[0]
         chunk = 1 << (self.nl - k)
         q = 0
         for i, rb in enumerate(ex.rank_bits):
@@ -841,32 +952,126 @@ class ShardedStateVector:
             partners.append((j, r))
         itemsize = data.element_size()
         per_partner = max(1, self.stage_bytes // (itemsize * len(partners)))
-        piece = min(chunk, 1 << (per_partner.bit_length() - 1))
-        if data.is_cuda and self._symm_stage(piece * len(partners), data.dtype, data.device) is not None:
-            self._exchange_symm(data, partners, q, chunk, piece)
-            self.stats["exchanges"] += 1
-            self.stats["exchange_bytes"] += B * chunk * len(partners) * itemsize
+        cap = min(chunk >> pb, 1 << (per_partner.bit_length() - 1))      # amplitudes per partner and step
+        ctx = {"ex": ex, "data": data, "chunk": chunk, "q": q, "partners": partners, "lo": lo, "pb": pb,
+               "cap": cap, "itemsize": itemsize, "it": 0, "events": {}, "symm": None}
+        if data.is_cuda and self._symm_stage(cap * len(partners), data.dtype, data.device) is not None:
+            import torch
+
+            ctx["symm"] = self._symm
+            if getattr(self, "_comm_stream", None) is None:
+                self._comm_stream = torch.cuda.Stream(device=data.device)
+            ctx["compute"] = torch.cuda.current_stream(data.device)
+        elif self._stage is None or self._stage.numel() < cap * len(partners) or self._stage.dtype != data.dtype:
+            import torch
+
+            self._stage = torch.empty(cap * len(partners), dtype=data.dtype, device=data.device)
+        return ctx
+
+    @staticmethod
+    def _piece_steps(chunk, lo, pb, p, cap):
+        """Piece ``p`` of one slab in steps of at most ``cap`` amplitudes:
+        (offset in the slab, run, pitch, count) — ``count`` runs of ``run`` amplitudes ``pitch`` apart."""
+        run, pitch = 1 << lo, 1 << (lo + pb)
+        count = max(1, chunk // pitch)
+        first = p << lo
+        if run > cap:
+            for o in range(count):
+                for sub in range(0, run, cap):
+                    yield first + o * pitch + sub, cap, cap, 1
+        else:
+            rows = max(1, cap // run)
+            for o in range(0, count, rows):
+                yield first + o * pitch, run, pitch, min(rows, count - o)
+
+    def _exchange_piece(self, ctx, p):
+        """Start the transfer of piece ``p`` (every slab).  Symmetric-memory path: asynchronous,
+        on the communication stream, behind everything issued so far on the compute stream; per
+        step every rank PACKS what it gives away into its staging buffer (a copy-engine copy),
+        one device-side barrier, then every rank copies what it receives straight out of its
+        partners' staging buffers over NVLink into place.  Two staging buffers alternate, so the
+        barrier of step i+1 (stream-ordered behind the pulls of step i on every rank) is also
+        the "buffer i may be overwritten" signal.  Other backends: blocking send / recv."""
+        data, chunk, partners, q = ctx["data"], ctx["chunk"], ctx["partners"], ctx["q"]
+        lo, pb, cap, isz = ctx["lo"], ctx["pb"], ctx["cap"], ctx["itemsize"]
+        B = data.shape[0]
+        nelem = B * (chunk >> pb) * len(partners)
+        self.stats["exchange_bytes"] += nelem * isz
+        if ctx["symm"] is None:
+            self._exchange_piece_p2p(ctx, p)
             return
-        if self._stage is None or self._stage.numel() < piece * len(partners) or \
-                self._stage.dtype != data.dtype:
-            self._stage = torch.empty(piece * len(partners), dtype=data.dtype, device=data.device)
-        for b in range(B):
+        import torch
+
+        buf, hdl, half = ctx["symm"]
+        comm = self._comm_stream
+        ev = torch.cuda.Event()
+        ev.record(ctx["compute"])
+        comm.wait_event(ev)
+        cs = comm.cuda_stream
+        base, sbase = data.data_ptr(), buf.data_ptr()
+        row_stride = data.stride(0) * isz
+        with torch.cuda.stream(comm):
+            for b in range(B):
+                for off, run, pitch, count in self._piece_steps(chunk, lo, pb, p, cap):
+                    pp = ctx["it"] & 1
+                    ctx["it"] += 1
+                    for s_, (j, r) in enumerate(partners):
+                        self.engine.remap_copy(sbase + (pp * half + s_ * cap) * isz, run * isz,
+                                               base + b * row_stride + (j * chunk + off) * isz, pitch * isz,
+                                               run * isz, count, cs)
+                    hdl.barrier(channel=pp)
+                    for s_, (j, r) in enumerate(partners):
+                        # partner r holds value j of the exchanged bits; in ITS partner list (all
+                        # values but j, ascending) my value q sits at index q - (q > j)
+                        s_there = q - (1 if q > j else 0)
+                        remote = hdl.get_buffer(r, (cap,), data.dtype, pp * half + s_there * cap)
+                        self.engine.remap_copy(base + b * row_stride + (j * chunk + off) * isz, pitch * isz,
+                                               remote.data_ptr(), run * isz, run * isz, count, cs)
+            done = torch.cuda.Event()
+            done.record(comm)
+        ctx["events"][p] = done
+
+    def _exchange_piece_p2p(self, ctx, p):
+        import torch
+
+        dist = self.dist
+        data, chunk, partners = ctx["data"], ctx["chunk"], ctx["partners"]
+        lo, pb, cap = ctx["lo"], ctx["pb"], ctx["cap"]
+        for b in range(data.shape[0]):
             row = data[b]
-            for off in range(0, chunk, piece):
-                p2p = []
-                for s, (j, r) in enumerate(partners):
-                    mine = row[j * chunk + off: j * chunk + off + piece]
-                    stage = self._stage[s * piece:(s + 1) * piece]
+            for off, run, pitch, count in self._piece_steps(chunk, lo, pb, p, cap):
+                views, sends, p2p = [], [], []
+                for s_, (j, r) in enumerate(partners):
+                    v = torch.as_strided(row, (count, run), (pitch, 1), row.storage_offset() + j * chunk + off)
+                    snd = v.contiguous()
+                    stage = self._stage[s_ * cap: s_ * cap + count * run]
                     gr = r if self.group is None else dist.get_global_rank(self.group, r)
-                    p2p.append(dist.P2POp(dist.isend, mine, gr, self.group))
+                    p2p.append(dist.P2POp(dist.isend, snd, gr, self.group))
                     p2p.append(dist.P2POp(dist.irecv, stage, gr, self.group))
+                    views.append((v, stage))
+                    sends.append(snd)
                 for req in dist.batch_isend_irecv(p2p):
                     req.wait()
-                for s, (j, r) in enumerate(partners):
-                    row[j * chunk + off: j * chunk + off + piece].copy_(
-                        self._stage[s * piece:(s + 1) * piece])
+                for v, stage in views:
+                    v.copy_(stage.view(count, run))
+
+    def _exchange_wait(self, ctx, p):
+        """The compute stream waits for piece ``p`` to be in place."""
+        ev = ctx["events"].pop(p, None)
+        if ev is not None:
+            ctx["compute"].wait_event(ev)
+
+    def _exchange_end(self, ctx):
+        for p in list(ctx["events"]):
+            self._exchange_wait(ctx, p)
+        if ctx["symm"] is not None:
+            import torch
+
+            _, hdl, _ = ctx["symm"]
+            with torch.cuda.stream(self._comm_stream):
+                hdl.barrier(channel=0)
+                hdl.barrier(channel=1)
         self.stats["exchanges"] += 1
-        self.stats["exchange_bytes"] += B * chunk * len(partners) * itemsize
 
     def remap(self, want_local_bits, nxt=None):
         """Make the given logical bits local (one exchange at most)."""

@@ -483,7 +483,7 @@ class StateVector:
             self.run_segment(seg)
         return len(segs)
 
-    def _launch_plan(self, plan, coefs, base_hi: int = 0):
+    def _launch_plan(self, plan, coefs, base_hi: int = 0, fix_mask: int = 0, fix_val: int = 0):
         from . import segjit
 
         if coefs.ndim == 2 and coefs.shape[0] != self.batch:   # broadcast parameters
@@ -493,7 +493,7 @@ class StateVector:
             self._resize_batch(coefs.shape[0])
         w, wb = self.workspace()
         segjit.launch(plan, coefs, self.ptr, None, self.n, self.batch, w, wb, self.stream,
-                      base_hi=base_hi)
+                      base_hi=base_hi, fix_mask=fix_mask, fix_val=fix_val)
 
     def prepare_segments(self, segs):
         """Plan every tile segment for the specialised kernels and compile the structures that
@@ -514,9 +514,11 @@ class StateVector:
             plans.append(seg._sk_plan)
         segjit.ensure_compiled(plans)
 
-    def _run_segment_jit(self, seg, base_hi: int = 0):
+    def _run_segment_jit(self, seg, base_hi: int = 0, fix_mask: int = 0, fix_val: int = 0):
         """One fused segment through its structure-specialised kernel.  The plan (structure) and
-        the coefficient table (values) are kept on the segment object."""
+        the coefficient table (values) are kept on the segment object.  ``fix_mask`` /
+        ``fix_val``: partial launch over the tiles whose non-tile index bits ``fix_mask`` equal
+        ``fix_val`` (the sharded engine pipelines segments against the exchange piece by piece)."""
         from . import segjit
 
         plan = getattr(seg, "_sk_plan", None)
@@ -525,14 +527,21 @@ class StateVector:
             plan = segjit.plan_segment(seg, geom, _low_run(seg.tile_bits))
             seg._sk_plan = plan
             seg._sk_coefs = segjit.coefficients(plan, seg.prims)
-        self._launch_plan(plan, seg._sk_coefs, base_hi)
+        self._launch_plan(plan, seg._sk_coefs, base_hi, fix_mask, fix_val)
 
-    def run_segment(self, seg, base_hi: int = 0):
+    def segment_partial_ok(self, seg) -> bool:
+        """Whether :meth:`run_segment` can run ``seg`` on a subset of its tiles."""
+        return seg.tile_bits is not None and self.jit_enabled(1) \
+            and len(seg.tile_bits) == self.rt_geometry(1)[0]
+
+    def run_segment(self, seg, base_hi: int = 0, fix_mask: int = 0, fix_val: int = 0):
         from .compiler import DIAG, encode_rt_segment, encode_segment
 
         if seg.tile_bits is not None and self.jit_enabled(1) \
                 and len(seg.tile_bits) == self.rt_geometry(1)[0]:
-            return self._run_segment_jit(seg, base_hi)
+            return self._run_segment_jit(seg, base_hi, fix_mask, fix_val)
+        if fix_mask:
+            raise B200QError("partial launches exist for the specialised segment kernels only")
         if seg.tile_bits is None:
             p = seg.prims[0]
             if p.op is not None:
