@@ -239,7 +239,7 @@ int b200q_apply_rtile_bcast(void* vec0, void* vec1, int n, int dtype, int64_t ba
  * Replaces simulate.py:214-235 (gate loop) and adjoint_jacobian.py:121-137 (reverse sweep). */
 int b200q_jit_available(void);
 int b200q_jit_compile(const char* source, const char* const* header_names,
-                      const char* const* header_sources, int n_headers, int lineinfo,
+                      const char* const* header_sources, int n_headers, int lineinfo, int maxreg,
                       void** cubin_out, size_t* size_out);
 void b200q_jit_free(void* cubin);
 int b200q_seg_load(const void* cubin, size_t size, void** handle_out);
@@ -259,6 +259,26 @@ int b200q_seg_launch(void* handle, void* vec0, void* vec1, int n, int dtype, int
  * The reference has no analogue (default.qubit is one array). */
 int b200q_remap_copy(void* dst, size_t dst_pitch, const void* src, size_t src_pitch,
                      size_t run_bytes, size_t count, void* stream);
+/* The same copy as a KERNEL that shares the SMs with a running segment launch: the local half
+ * of an exchange step (staging buffer -> state).  Beside a fused segment launch a copy-engine
+ * device-to-device copy gets 0.4 TB/s and a pitched one waits for the launch boundary.
+ *   mode B200Q_UNPACK_TMA : one thread per CTA keeps four 16 KiB cp.async.bulk copies in flight
+ *                           (one warp, 64 KiB of shared memory: fits beside two resident segment
+ *                           CTAs); 6.3 TB/s of traffic alone, 2 TB/s beside a two-round segment,
+ *                           but starved by segments with many shared-memory transpositions;
+ *   mode B200Q_UNPACK_REGS: through registers, no shared memory: ~1.1 TB/s beside any segment.
+ * `ctas`: 0 = default grid.  Runs that are not multiples of 16 KiB (TMA) / 64 B fall back to
+ * b200q_remap_copy. */
+#define B200Q_UNPACK_TMA 0
+#define B200Q_UNPACK_REGS 1
+int b200q_remap_unpack(void* dst, size_t dst_pitch, const void* src, size_t src_pitch,
+                       size_t run_bytes, size_t count, int mode, int ctas, void* stream);
+/* Flags of the exchange protocol as STREAM MEMORY OPERATIONS (cuStreamWriteValue32 /
+ * cuStreamWaitValue32 with CU_STREAM_WAIT_VALUE_GEQ): `addr` is a 4-byte aligned device address,
+ * local or a peer's (mapped over NVLink).  No kernel is launched: the exchange makes progress
+ * while the segment kernels hold every SM. */
+int b200q_stream_write32(void* addr, uint32_t value, void* stream);
+int b200q_stream_wait_geq32(void* addr, uint32_t value, void* stream);
 
 /* One reverse-sweep step of adjoint differentiation on vecs = [1 + n_bras][2^n] (row 0 = ket):
  *   z_b = <bra_b| G |ket>,  ket <- A ket,  bra_b <- A bra_b      (A = U^dagger, k <= 3)

@@ -61,7 +61,7 @@ SIGNATURES = {
     "b200q_apply_rtile_bcast": (_i, [_p, _p, _i, _i, _i64, _ip, _i, _i, _p, _i, _p, _i, _i, _i, _u64,
                                      _d, _p, _p, _sz, _p]),
     "b200q_jit_available": (_i, []),
-    "b200q_jit_compile": (_i, [C.c_char_p, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), _i, _i,
+    "b200q_jit_compile": (_i, [C.c_char_p, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), _i, _i, _i,
                                C.POINTER(_p), C.POINTER(_sz)]),
     "b200q_jit_free": (None, [_p]),
     "b200q_seg_load": (_i, [_p, _sz, C.POINTER(_p)]),
@@ -69,6 +69,9 @@ SIGNATURES = {
     "b200q_seg_launch": (_i, [_p, _p, _p, _i, _i, _i64, _ip, _i, _i, _i, _i, _ip, _i, _dp, _i, _i,
                               _i, _i, _u64, _u64, _u64, _d, _p, _p, _sz, _p]),
     "b200q_remap_copy": (_i, [_p, _sz, _p, _sz, _sz, _sz, _p]),
+    "b200q_remap_unpack": (_i, [_p, _sz, _p, _sz, _sz, _sz, _i, _i, _p]),
+    "b200q_stream_write32": (_i, [_p, C.c_uint32, _p]),
+    "b200q_stream_wait_geq32": (_i, [_p, C.c_uint32, _p]),
     "b200q_adjoint_step": (_i, [_p, _i, _i, _i, _ip, _i, _ip, _ip, _i, _p, _p, _p, _p, _sz, _p]),
 }
 

@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(CSRC, "libb200q.so")
-SOURCES = ["api.cu", "dm.cu", "rtile.cu", "segk_host.cu"] + [f"rtile_k_{p}_{k}.cu" for p in "df"
+SOURCES = ["api.cu", "dm.cu", "rtile.cu", "segk_host.cu", "remap.cu"] + [f"rtile_k_{p}_{k}.cu" for p in "df"
                                     for k in ("fwd", "ws", "adj", "adj2")]          # compiled in parallel, one object each
 HEADERS = ["common.cuh", "gates.cuh", "measure.cuh", "sample.cuh", "adjoint.cuh", "tile.cuh",
            "rtile.cuh", "rtile_host.h", "rtile_launch.cuh", "segk_args.h", os.path.join("..", "..", "include", "b200q.h")]

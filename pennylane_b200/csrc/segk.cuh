@@ -52,6 +52,9 @@
 typedef SK_REAL real;
 struct __align__(2 * sizeof(SK_REAL)) C { real x, y; };
 struct __align__(64) SkTensorMap { unsigned long long opaque[16]; };
+// the tile maps of vector 0 / 1: a KERNEL PARAMETER (no upload before the launch: a host-to-device
+// copy on the compute stream would queue behind the exchange copies on the copy engines)
+struct __align__(64) SkMaps { SkTensorMap m[2]; };
 
 static constexpr int RB = SK_RB, TB = SK_TB, NV = SK_NV, T = SK_RB + SK_TB, L = SK_L;
 static constexpr int NA = 1 << RB, THREADS = 1 << TB, NW = THREADS / 32;
@@ -501,10 +504,18 @@ __device__ __forceinline__ void sk_xpose(C (&A)[NV][NA], C* tile, const unsigned
 #define SK_TBIT(b) ((tid >> (b)) & 1u)
 #define SK_EBIT(e) ((ext >> (e)) & 1u)
 
-extern "C" __global__ void __launch_bounds__(1 << SK_TB, SK_MINB)
+// Register cap.  SK_MAXREG > 0: __maxnreg__ (it cannot be combined with __launch_bounds__, and
+// launch bounds win over --maxrregcount): 120 registers x 512 resident threads leave 4096
+// registers of the SM to the one-warp CTAs of the exchange's unpack kernel (remap.cu).
+#if defined(SK_MAXREG) && SK_MAXREG > 0
+#define SK_KERNEL_BOUNDS __maxnreg__(SK_MAXREG)
+#else
+#define SK_KERNEL_BOUNDS __launch_bounds__(1 << SK_TB, SK_MINB)
+#endif
+extern "C" __global__ void SK_KERNEL_BOUNDS
 sk_kernel(const __grid_constant__ SkArgs a, C* __restrict__ v0, C* __restrict__ v1,
           const double* __restrict__ coef_g, const long long coef_bstride,
-          const SkTensorMap* __restrict__ tm, double* __restrict__ partials
+          const __grid_constant__ SkMaps tmaps, double* __restrict__ partials
 #if SK_COEF_PARAM
           , const __grid_constant__ SkCoef cf
 #endif
@@ -520,6 +531,7 @@ sk_kernel(const __grid_constant__ SkArgs a, C* __restrict__ v0, C* __restrict__ 
   unsigned long long* bar = koff + NA;                                                 // 1
   double* accs = reinterpret_cast<double*>(bar + 1);                                   // NSLOTS * NW
   const unsigned tid = threadIdx.x;
+  const SkTensorMap* tm = tmaps.m;
 
   {
 #if !SK_COEF_PARAM

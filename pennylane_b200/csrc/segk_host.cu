@@ -138,7 +138,7 @@ extern "C" {
 int b200q_jit_available(void) { return nvrtc() ? 1 : 0; }
 
 int b200q_jit_compile(const char* source, const char* const* header_names, const char* const* header_sources,
-                      int n_headers, int lineinfo, void** cubin_out, size_t* size_out) {
+                      int n_headers, int lineinfo, int maxreg, void** cubin_out, size_t* size_out) {
   B200Q_REQUIRE(source && cubin_out && size_out && n_headers >= 0, "jit_compile: null argument");
   Nvrtc* rt = nvrtc();
   B200Q_REQUIRE(rt, "jit_compile: libnvrtc.so.12 not found (set B200Q_NVRTC to its path)");
@@ -147,6 +147,13 @@ int b200q_jit_compile(const char* source, const char* const* header_names, const
   B200Q_REQUIRE(rc == 0, "jit_compile: nvrtcCreateProgram -> %s", rt->GetErrorString(rc));
   std::vector<const char*> opts = {"--gpu-architecture=sm_100a", "--std=c++17", "-default-device"};
   if (lineinfo) opts.push_back("-lineinfo");
+  // register cap: two resident 256-thread CTAs at <= 120 registers leave 4096 registers of an SM
+  // free — room for the one-warp CTAs of the exchange's unpack kernel (remap.cu)
+  std::string maxreg_opt;
+  if (maxreg > 0) {
+    maxreg_opt = "--maxrregcount=" + std::to_string(maxreg);
+    opts.push_back(maxreg_opt.c_str());
+  }
   rc = rt->CompileProgram(prog, (int)opts.size(), opts.data());
   if (rc != 0) {
     size_t ls = 0;
@@ -187,6 +194,11 @@ int b200q_seg_load(const void* cubin, size_t size, void** handle_out) {
   if (e == cudaSuccess) e = cudaLibraryGetKernel(&k->kern, k->lib, "sk_kernel");
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute((const void*)k->kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  // fixed carve-out (all of it shared): the exchange's unpack kernel (remap.cu) asks for the same,
+  // so its CTAs can join the two resident segment CTAs of an SM
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute((const void*)k->kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                             cudaSharedmemCarveoutMaxShared);
   if (e != cudaSuccess) {
     set_error("seg_load: %s", cudaGetErrorString(e));
     delete k;
@@ -253,11 +265,11 @@ int b200q_seg_launch(void* handle, void* vec0, void* vec1, int n, int dtype, int
   }
   a.ntiles = 1ull << (n - T - nfix);
   const int NV = vec1 ? 2 : 1;
-  CUtensorMap tm[2];
+  alignas(64) CUtensorMap tm[2];        // passed BY VALUE as a kernel parameter (SkMaps)
   memset(tm, 0, sizeof(tm));
   static const int tma_knob = getenv("B200Q_RT_TMA") ? atoi(getenv("B200Q_RT_TMA")) : 1;     // tuning knob
   if (tma_knob && batch == 1) sk_build_tile_maps(a, n, dtype, inmask, L, vec0, vec1, tm);
-  // workspace: [coefficients | ... | tensor maps (last 512 bytes of the table region) | partial sums]
+  // workspace: [coefficients | ... | partial sums]
   // coef_mode 0: one table, copied to shared memory by the kernel; 1: one table per batch
   // element; 2: the table is a kernel parameter (the kernel was compiled with SK_COEF_PARAM)
   const bool coef_batched = coef_mode == 1, coef_param = coef_mode == 2;
@@ -268,8 +280,6 @@ int b200q_seg_launch(void* handle, void* vec0, void* vec1, int n, int dtype, int
   B200Q_REQUIRE(!coef_param || (size_t)n_coef * (elem / 2) <= 4000, "seg_launch: parameter table too large");
   char* w = (char*)work;
   if (!coef_param) B200Q_CHECK(cudaMemcpyAsync(w, coef_host, coef_bytes, cudaMemcpyHostToDevice, s));
-  const size_t tm_off = kTermRegion - 512;
-  if (a.tma_rank > 0) B200Q_CHECK(cudaMemcpyAsync(w + tm_off, tm, sizeof(tm), cudaMemcpyHostToDevice, s));
   double* partials = (double*)(w + kTermRegion);
   const size_t pcap = (work_bytes - kTermRegion) / sizeof(double);
   const int threads = 1 << (T - RB);
@@ -287,7 +297,6 @@ int b200q_seg_launch(void* handle, void* vec0, void* vec1, int n, int dtype, int
   SegKernel* k = (SegKernel*)handle;
   const double* coef_dev = (const double*)w;
   long long bstride = coef_batched ? n_coef : 0;
-  const void* tm_dev = w + tm_off;
   // parameter table in the kernel's precision (ignored by kernels compiled without SK_COEF_PARAM)
   std::vector<double> cf64;
   std::vector<float> cf32;
@@ -296,38 +305,12 @@ int b200q_seg_launch(void* handle, void* vec0, void* vec1, int n, int dtype, int
     cf32.assign(coef_host, coef_host + n_coef);
     cf_arg = cf32.data();
   }
-  void* args[] = {&a, &vec0, &vec1, &coef_dev, &bstride, &tm_dev, &partials, cf_arg};
+  void* args[] = {&a, &vec0, &vec1, &coef_dev, &bstride, tm, &partials, cf_arg};
   B200Q_CHECK(cudaLaunchKernel((const void*)k->kern, grid, dim3(threads), args, smem, s));
   if (nslots > 0) {
     k_sk_final_reduce<<<(unsigned)(batch * nslots), 256, 0, s>>>(partials, out_dev, (int)grid.x, scale);
     B200Q_LAUNCH_CHECK();
   }
-  return 0;
-}
-
-int b200q_remap_copy(void* dst, size_t dst_pitch, const void* src, size_t src_pitch, size_t run_bytes,
-                     size_t count, void* stream) {
-  cudaStream_t s = (cudaStream_t)stream;
-  B200Q_REQUIRE(dst && src && run_bytes > 0 && count > 0, "remap_copy: null / empty argument");
-  B200Q_REQUIRE(dst_pitch >= run_bytes && src_pitch >= run_bytes, "remap_copy: pitch smaller than a run");
-  if (count == 1 || (dst_pitch == run_bytes && src_pitch == run_bytes)) {
-    B200Q_CHECK(cudaMemcpyAsync(dst, src, run_bytes * count, cudaMemcpyDefault, s));
-    return 0;
-  }
-  static const size_t max_pitch = [] {
-    int dev = 0;
-    cudaDeviceProp p;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&p, dev) != cudaSuccess) return (size_t)0x7fffffff;
-    return (size_t)p.memPitch;
-  }();
-  if (dst_pitch <= max_pitch && src_pitch <= max_pitch) {
-    B200Q_CHECK(cudaMemcpy2DAsync(dst, dst_pitch, src, src_pitch, run_bytes, count, cudaMemcpyDefault, s));
-    return 0;
-  }
-  B200Q_REQUIRE(count <= 4096, "remap_copy: %zu runs with a pitch above the 2D-copy limit", count);
-  for (size_t i = 0; i < count; ++i)
-    B200Q_CHECK(cudaMemcpyAsync((char*)dst + i * dst_pitch, (const char*)src + i * src_pitch, run_bytes,
-                                cudaMemcpyDefault, s));
   return 0;
 }
 

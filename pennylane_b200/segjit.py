@@ -492,6 +492,7 @@ def emit_config(plan: SegPlan) -> str:
         f"#define SK_NSLOTS {plan.nslots}", f"#define SK_NEXT {len(plan.ext_pos)}",
         f"#define SK_SWW {g.sww}",
         f"#define SK_COEF_PARAM {1 if plan.coef_param else 0}",
+        f"#define SK_MAXREG {_max_registers()}",
         f"#define SK_RPOS {_arr2([r for r, _ in plan.rounds])}",
         f"#define SK_TPOS {_arr2([t for _, t in plan.rounds])}",
     ]
@@ -600,6 +601,15 @@ def _cache_dirs():
 _SRC_HASH = None
 
 
+def _max_registers() -> int:
+    """Register cap of the specialised kernels (``--maxrregcount``).  120: two resident CTAs of
+    256 threads (or one of 512) leave 4096 registers of an SM free, which is what lets the
+    one-warp CTAs of the exchange's unpack kernel (csrc/remap.cu) run BESIDE a segment launch;
+    at 126-128 registers (the five-round segments) they waited for the launch boundary
+    (tools/micro_corun.py).  B200Q_SK_MAXREG overrides (0 = no cap)."""
+    return int(os.environ.get("B200Q_SK_MAXREG", "120"))
+
+
 def _full_key(plan_key: str) -> str:
     global _SRC_HASH
     if _SRC_HASH is None:
@@ -630,7 +640,7 @@ def compile_plan(plan: SegPlan, save_dir: str | None = None) -> bytes:
     n_arr = (C.c_char_p * 3)(*names)
     t_arr = (C.c_char_p * 3)(*texts)
     out, size = C.c_void_p(), C.c_size_t()
-    check(lib.b200q_jit_compile(src.encode(), n_arr, t_arr, 3, 1, C.byref(out), C.byref(size)))
+    check(lib.b200q_jit_compile(src.encode(), n_arr, t_arr, 3, 1, 0, C.byref(out), C.byref(size)))
     data = C.string_at(out, size.value)
     lib.b200q_jit_free(out)
     with _LOCK:

@@ -448,6 +448,29 @@ class CudaEngine:
         check(self.sv.lib.b200q_remap_copy(C.c_void_p(dst_ptr), dst_pitch, C.c_void_p(src_ptr), src_pitch,
                                            run_bytes, count, C.c_void_p(stream)))
 
+    def remap_unpack(self, dst_ptr, dst_pitch, src_ptr, src_pitch, run_bytes, count, stream, mode=0):
+        """``b200q_remap_unpack``: staging buffer -> state as a kernel that shares the SMs with
+        the segment kernels (mode 0: TMA bulk copies, 1: through registers)."""
+        from ._lib import check
+
+        check(self.sv.lib.b200q_remap_unpack(C.c_void_p(dst_ptr), dst_pitch, C.c_void_p(src_ptr), src_pitch,
+                                             run_bytes, count, int(mode), 0, C.c_void_p(stream)))
+
+    def unit_rounds(self, seg) -> int:
+        """Rounds (= 1 + shared-memory transpositions per tile) of a compiled unit."""
+        plan = getattr(seg, "_sk_plan", None)
+        return len(plan.rounds) if plan is not None else 0
+
+    def stream_write32(self, addr, value, stream):
+        from ._lib import check
+
+        check(self.sv.lib.b200q_stream_write32(C.c_void_p(addr), int(value) & 0xFFFFFFFF, C.c_void_p(stream)))
+
+    def stream_wait_geq32(self, addr, value, stream):
+        from ._lib import check
+
+        check(self.sv.lib.b200q_stream_wait_geq32(C.c_void_p(addr), int(value) & 0xFFFFFFFF, C.c_void_p(stream)))
+
     # -- reductions ------------------------------------------------------------------------
     def expval_terms(self, xs, zs, ys, cs):
         """sum_t cs[t] <psi_local| P_t |psi_local> per batch element -> (B,) float64."""
@@ -603,7 +626,7 @@ class ShardedStateVector:
     """``2**n`` amplitudes over ``dist.get_world_size()`` ranks (a power of two)."""
 
     def __init__(self, num_wires, dist, engine=None, dtype=np.complex128, batch=1, device=None,
-                 fusion=1, stage_bytes=1 << 30, group=None):
+                 fusion=1, stage_bytes=None, group=None):
         self.dist = dist
         self.group = group
         self.world = dist.get_world_size(group)
@@ -623,11 +646,18 @@ class ShardedStateVector:
         self.np_dtype = (np.dtype(np.complex64) if data is not None and "complex64" in str(data.dtype)
                          else np.dtype(dtype) if data is None else np.dtype(np.complex128))
         self.phys = list(range(self.n))
-        self.stage_bytes = int(stage_bytes)
+        # bytes moved per exchange step and staging buffer (three buffers are allocated)
+        # (1 GiB; 512 MiB beside shards of 128 GiB and more, where HBM is nearly full)
+        shard_bytes = (16 if self.np_dtype == np.dtype(np.complex128) else 8) << self.nl
+        self.stage_bytes = int(stage_bytes if stage_bytes is not None
+                               else os.environ.get("B200Q_STAGE_BYTES", (1 << 29) if shard_bytes >= (1 << 37) else (1 << 30)))
         self._stage = None
-        self._symm = None          # (buffer, handle, capacity) of the symmetric staging buffers
+        self._symm = None          # (buffer, handle, capacity, state) of the symmetric staging buffers
         self.stats = {"exchanges": 0, "exchange_bytes": 0, "run_steps": 0, "sweeps": 0}
         self.timer = None          # optional: callable(kind, fn) -> fn() (bench.py times steps)
+        self.comm_records = []     # (start, end) events of the exchange pieces while a timer is set
+        self.trace = None          # list: per-piece CUDA events of windows (tools/trace_window.py)
+        self.exchange_mode = "push"
         self.reset()
 
     # -- bookkeeping ---------------------------------------------------------------------------
@@ -722,8 +752,9 @@ class ShardedStateVector:
                 items.append(["exchange", item])
         claimed: dict = {}                           # item index -> exchange index
         windows: dict = {}
+        overlap = units_of is not None and pb_max > 0 and wmax > 0      # the same on every rank
         for i, it in enumerate(items):
-            if it[0] != "exchange":
+            if it[0] != "exchange" or not overlap:
                 continue
             top = self.nl - it[1].k
             before, j = [], i - 1
@@ -735,24 +766,40 @@ class ShardedStateVector:
             while j < len(items) and len(after) < wmax and items[j][0] == "unit" and items[j][2] is not None:
                 after.append(j)
                 j += 1
+            # busy masks of the (da, db) candidate windows; the choice of the piece bits must be
+            # the SAME on every rank (the pieces of an exchange have to match), while the segments
+            # differ from rank to rank (gates controlled by a rank bit are skipped on half of the
+            # ranks): OR the masks over the ranks, then every rank scores the same table
+            tab = []
+            for da in range(wmax + 1):
+                for db in range(wmax + 1):
+                    busy = 0
+                    for x in before[max(0, len(before) - da):] + after[:db]:
+                        busy |= items[x][2]
+                    tab.append(busy)
+            avail = self._gather_masks(tab + [len(before), len(after)])
+            tab = [0] * len(tab)
+            for row in avail:
+                for t in range(len(tab)):
+                    tab[t] |= row[t]
+            max_a, max_b = max(r[-2] for r in avail), max(r[-1] for r in avail)
             best = None
-            for da in range(len(before), -1, -1):
-                for db in range(len(after), -1, -1):
+            for da in range(min(wmax, max_a), -1, -1):
+                for db in range(min(wmax, max_b), -1, -1):
                     if da + db == 0:
                         continue
-                    idx = before[len(before) - da:] + after[:db]
-                    busy = 0
-                    for x in idx:
-                        busy |= items[x][2]
-                    got = _free_bit_window(busy, top, pb_max, min_bit)
+                    got = _free_bit_window(tab[da * (wmax + 1) + db], top, pb_max, min_bit)
                     if got is None:
                         continue
                     lo, pb = got
-                    score = (min(pb, 2), da + db, min(da, db), pb, lo)
+                    # long runs first (2**lo amplitudes per copy row: the unpack copy of 128 KiB
+                    # rows runs at less than half the rate of 16 MiB rows), then window size
+                    score = (min(pb, 2), min(lo, 16), da + db, min(da, db), pb, lo)
                     if best is None or score > best[0]:
-                        best = (score, before[len(before) - da:], after[:db], lo, pb)
+                        best = (score, da, db, lo, pb)
             if best is not None:
-                _, a_idx, b_idx, lo, pb = best
+                _, da, db, lo, pb = best
+                a_idx, b_idx = before[max(0, len(before) - da):], after[:db]
                 windows[i] = (a_idx, b_idx, lo, pb)
                 for x in a_idx + b_idx:
                     claimed[x] = i
@@ -800,19 +847,52 @@ class ShardedStateVector:
                 self.stats["windows"] = self.stats.get("windows", 0) + 1
         self.phys = list(program["final"])
 
+    def _gather_masks(self, values):
+        """All ranks' copies of a short list of non-negative integers (< 2**62): [[...] per rank]."""
+        if self.world == 1:
+            return [list(values)]
+        import torch
+
+        data = getattr(self.engine, "data", None)
+        dev = data.device if data is not None else "cpu"
+        mine = torch.tensor([int(v) for v in values], dtype=torch.int64, device=dev)
+        out = [torch.empty_like(mine) for _ in range(self.world)]
+        self.dist.all_gather(out, mine, group=self.group)
+        return [[int(v) for v in t.cpu().tolist()] for t in out]
+
     def _run_window(self, a_units, ex, b_units, lo, pb):
         """[segments] -> exchange -> [segments], piece by piece (see :meth:`_schedule`)."""
         P = 1 << pb
         mask = (P - 1) << lo
         ctx = self._exchange_begin(ex, lo, pb)
+        # unpack kernel: TMA bulk copies unless a segment of the window has many shared-memory
+        # transpositions per tile (they starve the bulk copies: csrc/remap.cu), then registers
+        mode = os.environ.get("B200Q_UNPACK_MODE", "tma")      # "auto" / "regs": measured slower end to end
+        rounds_of = getattr(self.engine, "unit_rounds", None)
+        heavy = rounds_of is not None and any(rounds_of(u) >= 4 for u in list(a_units) + list(b_units))
+        ctx["unpack_mode"] = 1 if (mode == "regs" or (mode == "auto" and heavy)) else 0
+        tr = self.trace
+
+        def mark(tag, p):
+            if tr is not None and "compute" in ctx:
+                import torch
+
+                e = torch.cuda.Event(enable_timing=True)
+                e.record(ctx["compute"])
+                tr.append((tag, p, [e]))
+
         for p in range(P):
+            mark("a0", p)
             for u in a_units:
                 self.engine.run_unit(u, mask, p << lo)
+            mark("a1", p)
             self._exchange_piece(ctx, p)
         for p in range(P):
             self._exchange_wait(ctx, p)
+            mark("b0", p)
             for u in b_units:
                 self.engine.run_unit(u, mask, p << lo)
+            mark("b1", p)
         self._exchange_end(ctx)
         return len(a_units) + len(b_units)
 
@@ -873,7 +953,7 @@ class ShardedStateVector:
 
     # -- the exchange --------------------------------------------------------------------------
     def _symm_stage(self, numel, dtype, device):
-        """Two staging buffers in SYMMETRIC memory (torch.distributed._symmetric_memory: every
+        """Three staging buffers in SYMMETRIC memory (torch.distributed._symmetric_memory: every
         rank can address every other rank's copy over NVLink).  Allocated and rendezvous'ed ONCE
         per process and (group, dtype) and shared by every ShardedStateVector; the decision to use
         them is COLLECTIVE (a rank whose allocation failed would otherwise take the NCCL path
@@ -898,7 +978,10 @@ class ShardedStateVector:
 
             if device.type != "cuda" or os.environ.get("B200Q_EXCHANGE", "symm") != "symm":
                 raise RuntimeError("symmetric exchange disabled")
-            buf = symm.empty(2 * numel, dtype=dtype, device=device)
+            # + 512 bytes of flags (uint32 landed[64], consumed[64]) behind the three buffers
+            buf = symm.empty(3 * numel + 512 // torch.empty(0, dtype=dtype).element_size(), dtype=dtype,
+                             device=device)
+            buf[3 * numel:].zero_()
             ok = torch.ones(1, dtype=torch.int32, device=device)
         except Exception as e:                       # noqa: BLE001 - any failure -> NCCL path
             err = repr(e)
@@ -911,7 +994,7 @@ class ShardedStateVector:
         if int(ok.item()) == 1:
             try:
                 hdl = symm.rendezvous(buf, self.group if self.group is not None else self.dist.group.WORLD)
-                entry = (buf, hdl, numel)
+                entry = (buf, hdl, numel, {"t": 0, "flag_off": 3 * numel * buf.element_size()})
             except Exception as e:                   # noqa: BLE001
                 err = repr(e)
         ok2 = torch.tensor([1 if entry is not None else 0], dtype=torch.int32, device=device)
@@ -954,13 +1037,17 @@ class ShardedStateVector:
         per_partner = max(1, self.stage_bytes // (itemsize * len(partners)))
         cap = min(chunk >> pb, 1 << (per_partner.bit_length() - 1))      # amplitudes per partner and step
         ctx = {"ex": ex, "data": data, "chunk": chunk, "q": q, "partners": partners, "lo": lo, "pb": pb,
-               "cap": cap, "itemsize": itemsize, "it": 0, "events": {}, "symm": None}
-        if data.is_cuda and self._symm_stage(cap * len(partners), data.dtype, data.device) is not None:
+               "cap": cap, "itemsize": itemsize, "it": 0, "events": {}, "symm": None, "unpacked": []}
+        if data.is_cuda and self._symm_stage(max(cap * len(partners), self.stage_bytes // itemsize), data.dtype,
+                                             data.device) is not None:
             import torch
 
             ctx["symm"] = self._symm
             if getattr(self, "_comm_stream", None) is None:
-                self._comm_stream = torch.cuda.Stream(device=data.device)
+                # high priority: the barrier kernels and copies of an exchange step must not queue
+                # behind the next (multi-millisecond, every-SM) segment launch of the compute stream
+                self._comm_stream = torch.cuda.Stream(device=data.device, priority=-1)    # NVLink pushes + barriers
+                self._unpack_stream = torch.cuda.Stream(device=data.device, priority=-1)  # staging -> state
             ctx["compute"] = torch.cuda.current_stream(data.device)
         elif self._stage is None or self._stage.numel() < cap * len(partners) or self._stage.dtype != data.dtype:
             import torch
@@ -985,13 +1072,26 @@ class ShardedStateVector:
                 yield first + o * pitch, run, pitch, min(rows, count - o)
 
     def _exchange_piece(self, ctx, p):
-        """Start the transfer of piece ``p`` (every slab).  Symmetric-memory path: asynchronous,
-        on the communication stream, behind everything issued so far on the compute stream; per
-        step every rank PACKS what it gives away into its staging buffer (a copy-engine copy),
-        one device-side barrier, then every rank copies what it receives straight out of its
-        partners' staging buffers over NVLink into place.  Two staging buffers alternate, so the
-        barrier of step i+1 (stream-ordered behind the pulls of step i on every rank) is also
-        the "buffer i may be overwritten" signal.  Other backends: blocking send / recv."""
+        """Start the transfer of piece ``p`` (every slab).  Symmetric-memory path (K9 of SURVEY.md
+        section 2c): asynchronous, on two communication streams behind everything issued so far
+        on the compute stream, and made of copy-engine copies and stream memory operations ONLY —
+        no kernel: a segment launch keeps every SM busy for milliseconds (at 34 qubits a piece
+        of a segment runs 6.5 ms) and a kernel of the communication streams, the device-side
+        barrier of torch's symmetric memory included, was measured to wait for the next launch
+        boundary (tools/trace_window.py, profiles/r2_exchange_trace.txt).  Per step (at most
+        ``cap`` amplitudes per partner)
+          NVLink stream : [wait until the partner has consumed step t-3]  PUSH my slab piece
+                          straight into the partner's staging buffer (copy-engine copy with a
+                          peer destination: 690-740 GB/s beside the sweeps, where pulls drop to
+                          440 because remote reads wait on the partner's saturated HBM), then
+                          write ``landed[me] = t+1`` into the partner's flags
+                          (cuStreamWriteValue32 over NVLink);
+          unpack stream : wait for ``landed[partner] >= t+1`` in MY flags (cuStreamWaitValue32),
+                          copy what the partners left in my staging buffer into place, then
+                          write ``consumed[me] = t+1`` into every rank's flags.
+        ``t`` counts the steps of all exchanges of the process (the same sequence on every
+        rank); three staging buffers rotate, so the push of step t+1 overlaps the unpack of
+        step t.  Other backends: blocking send / recv."""
         data, chunk, partners, q = ctx["data"], ctx["chunk"], ctx["partners"], ctx["q"]
         lo, pb, cap, isz = ctx["lo"], ctx["pb"], ctx["cap"], ctx["itemsize"]
         B = data.shape[0]
@@ -1002,33 +1102,72 @@ class ShardedStateVector:
             return
         import torch
 
-        buf, hdl, half = ctx["symm"]
-        comm = self._comm_stream
+        buf, hdl, third, st = ctx["symm"]
+        link, unpack = self._comm_stream, self._unpack_stream
         ev = torch.cuda.Event()
         ev.record(ctx["compute"])
-        comm.wait_event(ev)
-        cs = comm.cuda_stream
+        link.wait_event(ev)
+        unpack.wait_event(ev)
+        timing = self.timer is not None or self.trace is not None
+        marks = []
+
+        def mark(stream):
+            e = torch.cuda.Event(enable_timing=True)
+            e.record(stream)
+            marks.append(e)
+
+        if timing:
+            mark(link)
+        eng = self.engine
         base, sbase = data.data_ptr(), buf.data_ptr()
+        peers = hdl.buffer_ptrs
         row_stride = data.stride(0) * isz
-        with torch.cuda.stream(comm):
-            for b in range(B):
-                for off, run, pitch, count in self._piece_steps(chunk, lo, pb, p, cap):
-                    pp = ctx["it"] & 1
-                    ctx["it"] += 1
-                    for s_, (j, r) in enumerate(partners):
-                        self.engine.remap_copy(sbase + (pp * half + s_ * cap) * isz, run * isz,
-                                               base + b * row_stride + (j * chunk + off) * isz, pitch * isz,
-                                               run * isz, count, cs)
-                    hdl.barrier(channel=pp)
-                    for s_, (j, r) in enumerate(partners):
-                        # partner r holds value j of the exchanged bits; in ITS partner list (all
-                        # values but j, ascending) my value q sits at index q - (q > j)
-                        s_there = q - (1 if q > j else 0)
-                        remote = hdl.get_buffer(r, (cap,), data.dtype, pp * half + s_there * cap)
-                        self.engine.remap_copy(base + b * row_stride + (j * chunk + off) * isz, pitch * isz,
-                                               remote.data_ptr(), run * isz, run * isz, count, cs)
-            done = torch.cuda.Event()
-            done.record(comm)
+        ls, us = link.cuda_stream, unpack.cuda_stream
+        me, foff = self.rank, st["flag_off"]
+        landed = lambda r, src: peers[r] + foff + 4 * src              # noqa: E731  landed[src] on rank r
+        consumed = lambda r, src: peers[r] + foff + 256 + 4 * src      # noqa: E731
+        done = None
+        for b in range(B):
+            for off, run, pitch, count in self._piece_steps(chunk, lo, pb, p, cap):
+                t = st["t"]
+                st["t"] += 1
+                slot = (t % 3) * third
+                for s_, (j, r) in enumerate(partners):
+                    if t >= 3:
+                        eng.stream_wait_geq32(consumed(me, r), t - 2, ls)
+                    # partner r holds value j of the exchanged bits; in ITS partner list (all
+                    # values but j, ascending) my value q sits at index q - (q > j)
+                    s_there = q - (1 if q > j else 0)
+                    eng.remap_copy(peers[r] + (slot + s_there * cap) * isz, run * isz,
+                                   base + b * row_stride + (j * chunk + off) * isz, pitch * isz,
+                                   run * isz, count, ls)
+                    eng.stream_write32(landed(r, me), t + 1, ls)
+                # my unpack overwrites the slab piece my own push reads: it also waits for that push
+                pushed = torch.cuda.Event(enable_timing=self.trace is not None)
+                pushed.record(link)
+                if self.trace is not None:
+                    marks.append(pushed)
+                unpack.wait_event(pushed)
+                for s_, (j, r) in enumerate(partners):
+                    eng.stream_wait_geq32(landed(me, r), t + 1, us)
+                if self.trace is not None:
+                    mark(unpack)
+                for s_, (j, r) in enumerate(partners):
+                    eng.remap_unpack(base + b * row_stride + (j * chunk + off) * isz, pitch * isz,
+                                     sbase + (slot + s_ * cap) * isz, run * isz, run * isz, count, us,
+                                     ctx.get("unpack_mode", 0))
+                for r in range(self.world):
+                    if r != me:
+                        eng.stream_write32(consumed(r, me), t + 1, us)
+                if self.trace is not None:
+                    mark(unpack)
+        done = torch.cuda.Event(enable_timing=timing)
+        done.record(unpack)
+        if timing:
+            mark(link)
+            self.comm_records.append((marks[0], done))
+        if self.trace is not None:
+            self.trace.append(("comm", p, marks + [done]))
         ctx["events"][p] = done
 
     def _exchange_piece_p2p(self, ctx, p):
@@ -1064,13 +1203,6 @@ class ShardedStateVector:
     def _exchange_end(self, ctx):
         for p in list(ctx["events"]):
             self._exchange_wait(ctx, p)
-        if ctx["symm"] is not None:
-            import torch
-
-            _, hdl, _ = ctx["symm"]
-            with torch.cuda.stream(self._comm_stream):
-                hdl.barrier(channel=0)
-                hdl.barrier(channel=1)
         self.stats["exchanges"] += 1
 
     def remap(self, want_local_bits, nxt=None):

@@ -52,6 +52,41 @@ class NumpyEngine:
             self.applied += 1
         return len(handle)
 
+    # partial runs (the window schedule of sharded.ShardedStateVector._schedule): every operator
+    # is a unit; it can run on the part of the state where index bits outside its wires are fixed
+    def units(self, handle):
+        if self.batch != 1 or not getattr(self, "divisible", True):
+            return None
+        out = []
+        for op in handle:
+            busy = 0
+            for w in op.wires:
+                busy |= 1 << (self.n - 1 - int(w))
+            out.append((op, busy))
+        return out
+
+    def run_unit(self, op, fix_mask=0, fix_val=0):
+        if not fix_mask:
+            self.run([op])
+            return 1
+        n = self.n
+        st = self.data.numpy().reshape((2,) * n)
+        index, wmap, nxt = [], {}, 0
+        for axis in range(n):
+            b = n - 1 - axis
+            if (fix_mask >> b) & 1:
+                index.append((fix_val >> b) & 1)
+            else:
+                index.append(slice(None))
+                wmap[axis] = nxt
+                nxt += 1
+        assert all(int(w) in wmap for w in op.wires), "a fixed bit is one of the operator's wires"
+        sub = st[tuple(index)]
+        sub[...] = apply_operation(op.map_wires(wmap), np.ascontiguousarray(sub))
+        self.applied += 1
+        self.partial_runs = getattr(self, "partial_runs", 0) + 1
+        return 1
+
     # reductions
     def expval_terms(self, xs, zs, ys, cs):
         psi = self.data.numpy()

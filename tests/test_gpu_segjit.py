@@ -167,3 +167,88 @@ def test_adjoint_of_the_ansatz_and_split_parameters(monkeypatch):
     monkeypatch.setenv("B200Q_JIT", "0")             # same split through the record interpreter
     jac = np.array(adjoint.adjoint_jacobian(tape, fusion=1), dtype=float)
     assert np.max(np.abs(jac - ref)) < 1e-12
+
+
+@pytest.mark.parametrize("n,pb", [(16, 2), (17, 3), (15, 1)])
+def test_partial_launches_cover_the_state(n, pb):
+    """``fix_mask`` / ``fix_val`` of b200q_seg_launch: running every segment of a circuit piece by
+    piece (2**pb partial launches over the tiles whose free index bits equal p) gives the state
+    of the whole launches, bit for bit, and the oracle's to 1e-12; the pieces of one segment
+    touch disjoint amplitudes (a piece alone leaves the others untouched)."""
+    import bench
+    from pennylane_b200.sharded import _free_bit_window
+    from pennylane_b200.statevector import StateVector
+
+    ops_ = bench.hea_ops(n, layers=3)
+    ref = _state_oracle(ops_, n)
+    sv = StateVector(n)
+    segs = sv.compile_fused(ops_, level=1)
+    sv.prepare_segments(segs)
+    whole = StateVector(n)
+    pieces = 0
+    for seg in segs:
+        whole.run_segment(seg)
+        busy = 0
+        for b in seg.tile_bits or range(n):
+            busy |= 1 << b
+        win = _free_bit_window(busy, n, pb, 0) if sv.segment_partial_ok(seg) else None
+        if win is None:
+            sv.run_segment(seg)
+            continue
+        lo, k = win
+        mask = ((1 << k) - 1) << lo
+        before = sv.to_numpy().reshape(-1).copy()
+        sv.run_segment(seg, 0, mask, 0)                       # piece 0 alone
+        mid = sv.to_numpy().reshape(-1)
+        idx = np.arange(1 << n)
+        untouched = (idx & mask) != 0
+        assert np.array_equal(mid[untouched], before[untouched])
+        for p in range(1, 1 << k):
+            sv.run_segment(seg, 0, mask, p << lo)
+        pieces += 1
+    assert pieces > 0
+    got = sv.to_numpy().reshape(-1)
+    assert np.array_equal(got, whole.to_numpy().reshape(-1))
+    assert np.max(np.abs(got - ref)) < 1e-12                  # tolerance: 1e-12 (complex128)
+
+
+def test_remap_copy_pack_unpack():
+    """b200q_remap_copy: strided piece of a slab -> dense staging (pack) and back (unpack)."""
+    import ctypes as C
+
+    import torch
+
+    from pennylane_b200._lib import check, load
+
+    lib = load()
+    dev = torch.device("cuda:0")
+    src = torch.arange(1 << 16, dtype=torch.float64, device=dev)
+    for run, pitch, count, off in [(64, 256, 100, 128), (512, 512, 7, 0), (1, 8, 1000, 3), (4096, 16384, 3, 4096)]:
+        stage = torch.zeros(run * count, dtype=torch.float64, device=dev)
+        stream = torch.cuda.current_stream().cuda_stream
+        check(lib.b200q_remap_copy(C.c_void_p(stage.data_ptr()), run * 8, C.c_void_p(src.data_ptr() + off * 8),
+                                   pitch * 8, run * 8, count, C.c_void_p(stream)))
+        want = torch.as_strided(src, (count, run), (pitch, 1), off).contiguous().reshape(-1)
+        assert torch.equal(stage, want)
+        dst = torch.full((1 << 16,), -1.0, dtype=torch.float64, device=dev)
+        check(lib.b200q_remap_copy(C.c_void_p(dst.data_ptr() + off * 8), pitch * 8, C.c_void_p(stage.data_ptr()),
+                                   run * 8, run * 8, count, C.c_void_p(stream)))
+        view = torch.as_strided(dst, (count, run), (pitch, 1), off)
+        assert torch.equal(view.contiguous().reshape(-1), want)
+        touched = torch.zeros(1 << 16, dtype=torch.bool, device=dev)
+        torch.as_strided(touched, (count, run), (pitch, 1), off).fill_(True)
+        assert torch.all(dst[~touched] == -1.0)
+    # the kernel versions of the unpack copy (TMA bulk copies / registers), pitched and contiguous
+    big = torch.arange(1 << 22, dtype=torch.float64, device=dev)
+    for mode in (0, 1):
+        for run, pitch, count, off in [(2048, 8192, 100, 4096), (1 << 14, 1 << 14, 5, 0), (8, 64, 1000, 8),
+                                       (1 << 12, 1 << 15, 64, 1 << 12)]:
+            stage = big[: run * count].clone()
+            dst = torch.full((1 << 22,), -1.0, dtype=torch.float64, device=dev)
+            check(lib.b200q_remap_unpack(C.c_void_p(dst.data_ptr() + off * 8), pitch * 8, C.c_void_p(stage.data_ptr()),
+                                         run * 8, run * 8, count, mode, 0, C.c_void_p(stream)))
+            view = torch.as_strided(dst, (count, run), (pitch, 1), off)
+            assert torch.equal(view.contiguous().reshape(-1), stage), (mode, run, pitch, count)
+            touched = torch.zeros(1 << 22, dtype=torch.bool, device=dev)
+            torch.as_strided(touched, (count, run), (pitch, 1), off).fill_(True)
+            assert torch.all(dst[~touched] == -1.0)

@@ -102,6 +102,31 @@ def _check_all(dist, n, seed, fusion, world_note=""):
     return out
 
 
+def _check_windows(dist, n, seed):
+    """Exchanges pipelined against the segments around them (sharded._schedule / _run_window):
+    the state equals the oracle's and at least one window ran."""
+    import pennylane_b200 as qb
+    from oracle import simulate as o_sim
+    from pennylane_b200.sharded import ShardedStateVector
+    from test_sharded_gloo import _hea
+
+    ops_ = _hea(n, 4, seed)
+    out = {}
+    for pb in (3, 1):
+        os.environ["B200Q_EXCHANGE_PIECE_BITS"] = str(pb)
+        try:
+            sv = ShardedStateVector(n, dist, fusion=1, stage_bytes=1 << 16)
+            prog = sv.compile(ops_)
+            nwin = sum(1 for e in prog["schedule"] if e[0] == "window")
+            sv.run(prog)
+            st, _ = o_sim.get_final_state(qb.QuantumScript(ops_, []))
+            out[f"state_pb{pb}"] = float(np.max(np.abs(sv.to_numpy() - np.asarray(st).reshape(-1))))
+            out[f"no_window_pb{pb}"] = 0.0 if (nwin > 0 or dist.get_world_size() == 1) else 1.0
+        finally:
+            os.environ.pop("B200Q_EXCHANGE_PIECE_BITS", None)
+    return out
+
+
 @pytest.mark.parametrize("fusion", [0, 1])
 def test_world1_cuda_engine_matches_oracle(dist1, fusion):
     res = _check_all(dist1, 14, 21, fusion)
@@ -123,6 +148,12 @@ def _worker(rank, world, port, q_):
         for fusion in (0, 1):
             for k, v in _check_all(dist, 15, 33, fusion).items():
                 res[f"f{fusion}_{k}"] = v
+        # the overlapped schedule: specialised segment kernels forced on (their partial launches
+        # are what lets a segment run piece by piece beside the exchange), 17 qubits so that
+        # index bits outside the 12-bit tiles exist
+        os.environ["B200Q_JIT"] = "1"
+        for k, v in _check_windows(dist, 17, 5).items():
+            res[f"win_{k}"] = v
         q_.put((rank, "ok", res))
         dist.destroy_process_group()
     except Exception:                                   # noqa: BLE001

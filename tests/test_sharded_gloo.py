@@ -136,6 +136,31 @@ def w_state(rank, world, n, kind, seed):
     return float(np.max(np.abs(got - ref))), dict(sv.stats), list(sv.phys)
 
 
+def w_window(rank, world, n, seed, piece_bits, stage_bytes):
+    """The overlapped schedule (ShardedStateVector._schedule / _run_window): segments on either
+    side of an exchange run piece by piece, the exchange moves one piece at a time."""
+    from np_engine import NumpyEngine
+    from pennylane_b200.sharded import ShardedStateVector
+
+    os.environ["B200Q_EXCHANGE_PIECE_BITS"] = str(piece_bits)
+    os.environ["B200Q_EXCHANGE_MIN_BIT"] = "0"          # tiny shards: any index bit may cut the pieces
+    try:
+        ops_ = _hea(n, 3, seed) + _mixed_circuit(n, seed + 1)
+        g = world.bit_length() - 1
+        eng = NumpyEngine(n - g)
+        sv = ShardedStateVector(n, dist, engine=eng, stage_bytes=stage_bytes)
+        prog = sv.compile(ops_)
+        kinds = [e[0] for e in prog["schedule"]]
+        sv.run(prog)
+        got = sv.to_numpy()
+        ref = _oracle_state(n, ops_)
+        return (float(np.max(np.abs(got - ref))), kinds.count("window"), kinds.count("exchange"),
+                getattr(eng, "partial_runs", 0), dict(sv.stats))
+    finally:
+        os.environ.pop("B200Q_EXCHANGE_PIECE_BITS", None)
+        os.environ.pop("B200Q_EXCHANGE_MIN_BIT", None)
+
+
 def w_expval(rank, world, n, seed):
     import pennylane_b200 as qb
     from oracle import simulate as o_sim
@@ -298,6 +323,41 @@ def test_sharded_state_matches_oracle(world, kind):
         assert err < 1e-12, err
         assert stats["exchanges"] >= 1
     assert len({tuple(r[2]) for r in res}) == 1          # every rank tracks the same map
+
+
+@pytest.mark.parametrize("world,piece_bits,stage_bytes", [(2, 3, 4096), (4, 2, 256), (2, 1, 1 << 20), (4, 3, 64)])
+def test_overlapped_exchange_windows_match_oracle(world, piece_bits, stage_bytes):
+    n = 9
+    res = run_ranks(world, "w_window", n, 11, piece_bits, stage_bytes)
+    ref_bytes = run_ranks(world, "w_window", n, 11, 0, stage_bytes)
+    for (err, nwin, nex, partial, stats), (err0, nwin0, nex0, partial0, stats0) in zip(res, ref_bytes):
+        assert err < 1e-12 and err0 < 1e-12
+        assert nwin > 0 and partial > 0, "no exchange was pipelined"
+        assert nwin0 == 0 and partial0 == 0, "B200Q_EXCHANGE_PIECE_BITS=0 must switch the overlap off"
+        assert nwin + nex == nex0
+        # cutting an exchange into pieces moves exactly the same bytes
+        assert stats["exchange_bytes"] == stats0["exchange_bytes"] and stats["exchanges"] == stats0["exchanges"]
+
+
+def test_piece_steps_cover_each_slab_exactly_once():
+    from pennylane_b200.sharded import ShardedStateVector, _free_bit_window
+
+    for chunk_bits, lo, pb, cap in [(10, 4, 2, 8), (10, 4, 2, 64), (10, 7, 3, 16), (12, 0, 3, 4), (8, 8, 0, 32),
+                                    (8, 8, 0, 1 << 8), (9, 5, 1, 1 << 12)]:
+        chunk = 1 << chunk_bits
+        seen = np.zeros(chunk, dtype=int)
+        for p in range(1 << pb):
+            for off, run, pitch, count in ShardedStateVector._piece_steps(chunk, lo, pb, p, cap):
+                assert run * count <= max(cap, run)
+                for c in range(count):
+                    idx = np.arange(off + c * pitch, off + c * pitch + run)
+                    assert np.all(((idx >> lo) & ((1 << pb) - 1)) == p)
+                    seen[idx] += 1
+        assert np.all(seen == 1), (chunk_bits, lo, pb, cap)
+    assert _free_bit_window(0b0000_0111, 8, 3, 0) == (5, 3)
+    assert _free_bit_window(0b0110_0111, 8, 3, 0) == (3, 2)
+    assert _free_bit_window(0b1010_1011, 8, 3, 2) == (6, 1)
+    assert _free_bit_window(0b1111_1111, 8, 3, 0) is None
 
 
 @pytest.mark.parametrize("world", [2, 4])
