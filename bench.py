@@ -417,6 +417,11 @@ def run_ours(args):
                 per_wire[str(list(op.wires))] = round(
                     2 * credited_bytes(op, n) / (e0.elapsed_time(e1) * 1e-3) / 1e9 / peak, 3)
             per_gate[name]["frac_per_wires"] = per_wire
+            if name == "CNOT":
+                # control on index bit 0: the touched amplitudes are every other 16 bytes, so every
+                # 32-byte DRAM sector is read and written: the bytes that move are 2*S, not S
+                key = str(list(plist[-1].wires))
+                per_gate[name]["bit0_control_frac_at_sector_level"] = {key: round(2 * per_wire[key], 3)}
         # Wide dense blocks (apply_operation.py:202-255, the tensordot path): compute-bound from
         # K = 5 on — 4 * 2^K DFMA per amplitude against 32 bytes — so their roofline is the FP64
         # pipe (34.1 TFLOP/s measured with tools/micro/fp64_forms.cu, profiles/r2_fp64_forms.txt).

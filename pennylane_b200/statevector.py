@@ -314,6 +314,7 @@ class StateVector:
             if op.meas_val.concretize(mid_measurements):
                 self.apply_operation(op.base, mid_measurements=mid_measurements, rng=rng)
             return
+        SWEEPS["per_gate"] += 1
         if name in ("Identity", "Barrier", "WireCut", "Snapshot"):
             return
         if name == "GlobalPhase":
@@ -486,6 +487,9 @@ class StateVector:
     def _launch_plan(self, plan, coefs, base_hi: int = 0, fix_mask: int = 0, fix_val: int = 0):
         from . import segjit
 
+        if not fix_mask or not fix_val:          # a partial launch counts once (its first piece)
+            SWEEPS["fused_segments"] += 1
+
         if coefs.ndim == 2 and coefs.shape[0] != self.batch:   # broadcast parameters
             if self.batch != 1:
                 raise ValueError(f"broadcast gates of batch {coefs.shape[0]} on a state of "
@@ -542,6 +546,7 @@ class StateVector:
             return self._run_segment_jit(seg, base_hi, fix_mask, fix_val)
         if fix_mask:
             raise B200QError("partial launches exist for the specialised segment kernels only")
+        SWEEPS["fused_segments"] += seg.tile_bits is not None
         if seg.tile_bits is None:
             p = seg.prims[0]
             if p.op is not None:
@@ -763,6 +768,10 @@ class StateVector:
 
 _XMAT = np.array([[0, 1], [1, 0]], dtype=np.complex128)
 _RT_GEOM: dict = {}
+#: launches over the whole state issued by this process (tools/run_configs.py, bench.py): fused
+#: segment launches and per-gate kernels
+SWEEPS = {"fused_segments": 0, "per_gate": 0}
+
 
 
 def _low_run(tile_bits) -> int:
