@@ -104,6 +104,36 @@ def _qwc(w1, w2):
     return all(w1[k] == w2[k] for k in w1 if k in w2)
 
 
+def compute_partition_indices(words):
+    """pauli/grouping/group_observables.py:389-432 with grouping_type 'qwc' and method 'lf', on
+    Pauli words given as {wire: 'X'|'Y'|'Z'}.  The adjacency matrix of the complement graph
+    (:340-386: entry (i, j) set when some wire carries two different non-identity factors), its
+    largest-first greedy colouring (rustworkx ``graph_greedy_color``: nodes by descending degree,
+    stable; smallest colour absent from the neighbours), and the grouping of :238-243 (colours in
+    the order of their lowest index, indices ascending)."""
+    m = len(words)
+    if all(len(w) == 0 for w in words):
+        return (tuple(range(m)),)
+    wires = sorted({k for w in words for k in w}, key=str)
+    code = {"X": 1, "Y": 2, "Z": 3}
+    P = np.array([[code.get(w.get(k), 0) for k in wires] for w in words], dtype=np.int8)
+    Pb = P[:, None]
+    adj = np.logical_or.reduce((P * Pb) * (P - Pb), axis=2)
+    degree = adj.sum(axis=1)
+    order = np.argsort(-degree, kind="stable")
+    colours = -np.ones(m, dtype=int)
+    for i in order:
+        taken = set(colours[np.nonzero(adj[i])[0]].tolist())
+        c = 0
+        while c in taken:
+            c += 1
+        colours[i] = c
+    parts = {}
+    for i in range(m):
+        parts.setdefault(int(colours[i]), []).append(i)
+    return tuple(tuple(v) for v in parts.values())
+
+
 def _group_measurements(mps):                  # sampling.py:46-98
     if len(mps) == 1:
         return [mps], [[0]]
@@ -118,15 +148,10 @@ def _group_measurements(mps):                  # sampling.py:46-98
         else:
             other.append([mp]); other_idx.append([i])
     groups, gidx = [], []
-    # qubit-wise-commuting partition, greedy in order (compute_partition_indices, 'qwc')
-    for i, mp in pauli:
-        w = _pauli_word_of(mp.obs)
-        for g, gi in zip(groups, gidx):
-            if all(_qwc(w, _pauli_word_of(m.obs)) for m in g):
-                g.append(mp); gi.append(i)
-                break
-        else:
-            groups.append([mp]); gidx.append([i])
+    if pauli:
+        for part in compute_partition_indices([_pauli_word_of(mp.obs) for _, mp in pauli]):
+            groups.append([pauli[k][1] for k in part])
+            gidx.append([pauli[k][0] for k in part])
     if no_obs:
         groups.append(no_obs); gidx.append(no_obs_idx)
     return groups + other, gidx + other_idx

@@ -301,12 +301,34 @@ def _qwc(w1, w2) -> bool:
     return all(w1[k] == w2[k] for k in w1 if k in w2)
 
 
+def _qwc_partition(words):
+    """``compute_partition_indices(observables, "qwc", "lf")`` (pauli/grouping/
+    group_observables.py:389-432) without rustworkx: greedy colouring of the graph whose edges
+    join the words that do NOT commute qubit-wise (:340-386, :168-193), nodes taken by descending
+    degree — ``graph_greedy_color``'s largest-first order, a stable sort, so ties stay in index
+    order — each getting the smallest colour none of its neighbours has; the groups come out in
+    the order of the lowest index of each colour, indices ascending inside a group (:238-243).
+    The order matters: it is the order in which the shot budget's uniforms are drawn."""
+    m = len(words)
+    if all(len(w) == 0 for w in words):                     # :389-394: nothing acts on a wire
+        return [list(range(m))]
+    adj = [[j for j in range(m) if j != i and not _qwc(words[i], words[j])] for i in range(m)]
+    colour: dict = {}
+    for i in sorted(range(m), key=lambda k: -len(adj[k])):
+        used = {colour[j] for j in adj[i] if j in colour}
+        c = 0
+        while c in used:
+            c += 1
+        colour[i] = c
+    groups: dict = {}
+    for i in range(m):
+        groups.setdefault(colour[i], []).append(i)
+    return list(groups.values())
+
+
 def _group_measurements(mps):
     """sampling.py:46-98.  Pauli-word observables are partitioned into qubit-wise commuting
-    groups greedily in tape order (the reference colours the QWC graph with rustworkx's
-    largest-first heuristic, pauli/grouping/group_observables.py:389-432 — same groups whenever
-    the greedy and the colouring agree, which covers single-group tapes; the order of several
-    non-commuting groups, and hence RNG consumption order, may differ)."""
+    groups by :func:`_qwc_partition` (the reference's largest-first colouring)."""
     if len(mps) == 1:
         return [list(mps)], [[0]]
     pauli, other, other_idx, no_obs, no_obs_idx = [], [], [], [], []
@@ -320,14 +342,10 @@ def _group_measurements(mps):
         else:
             other.append([mp]); other_idx.append([i])
     groups, gidx = [], []
-    for i, mp in pauli:
-        w = _pauli_word_of(mp.obs)
-        for g, gi in zip(groups, gidx):
-            if all(_qwc(w, _pauli_word_of(m.obs)) for m in g):
-                g.append(mp); gi.append(i)
-                break
-        else:
-            groups.append([mp]); gidx.append([i])
+    if pauli:
+        for part in _qwc_partition([_pauli_word_of(mp.obs) for _, mp in pauli]):
+            groups.append([pauli[k][1] for k in part])
+            gidx.append([pauli[k][0] for k in part])
     if no_obs:
         groups.append(no_obs); gidx.append(no_obs_idx)
     return groups + other, gidx + other_idx

@@ -11,9 +11,11 @@ from oracle.apply_operation import apply_operation
 
 
 class NumpyEngine:
-    def __init__(self, nl, batch=1):
+    def __init__(self, nl, batch=1, dtype=np.complex128):
         self.n = nl
-        self.data = torch.zeros((batch, 1 << nl), dtype=torch.complex128)
+        self.np_dtype = np.dtype(dtype)
+        self.data = torch.zeros((batch, 1 << nl),
+                                dtype=torch.complex64 if self.np_dtype == np.complex64 else torch.complex128)
         self.applied = 0
 
     @property
@@ -30,7 +32,7 @@ class NumpyEngine:
             self.data[:, index] = 1.0
 
     def set_local_state(self, arr):
-        arr = np.asarray(arr, dtype=np.complex128).reshape(-1, 1 << self.n)
+        arr = np.asarray(arr, dtype=self.np_dtype).reshape(-1, 1 << self.n)
         self.data = torch.from_numpy(np.ascontiguousarray(arr).copy())
 
     def resize_batch(self, batch):
@@ -48,7 +50,8 @@ class NumpyEngine:
             batched = self.batch > 1
             st = self.data.numpy().reshape(((self.batch,) if batched else ()) + (2,) * self.n)
             out = apply_operation(op, st, is_state_batched=batched)
-            self.data = torch.from_numpy(np.ascontiguousarray(out).reshape(-1, 1 << self.n).copy())
+            # results are stored in the engine's precision (a complex64 shard drifts in norm by 1e-7)
+            self.data = torch.from_numpy(np.ascontiguousarray(out, dtype=self.np_dtype).reshape(-1, 1 << self.n).copy())
             self.applied += 1
         return len(handle)
 

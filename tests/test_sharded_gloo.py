@@ -312,6 +312,31 @@ def w_mcm(rank, world, n, seed, shots):
     return len(got), len(ref), bool(same), sorted({tuple(int(x) for x in a[1:]) for a in got})
 
 
+def w_mcm_c64(rank, world, n, seed):
+    """complex64 shards (round-1 advisor finding): re-measuring a wire that is deterministically
+    |0> or |1> gives p = 1 + O(1e-7); the reference renormalises within 10 eps of the STATE's
+    precision (apply_operation.py:451-457), so the draw must use the shard's dtype, not float64's
+    eps, or it raises 'probabilities greater than 1'."""
+    from np_engine import NumpyEngine
+    from pennylane_b200 import ops as q
+    from pennylane_b200.mcm import measure
+    from pennylane_b200.sharded import ShardedStateVector
+
+    g = world.bit_length() - 1
+    sv = ShardedStateVector(n, dist, engine=NumpyEngine(n - g, dtype=np.complex64), dtype=np.complex64)
+    assert sv.np_dtype == np.dtype(np.complex64)
+    rng = np.random.default_rng(seed)
+    outcomes = {}
+    gates = _hea(n, 3, seed)
+    first, again = [], []
+    for w in (0, 1, n - 1):                       # wire 0 (and 1 for world 4) sit on rank bits
+        m_a, m_b = measure(w), measure(w)
+        gates += [m_a.measurements[0], m_b.measurements[0]]
+        first.append(m_a.measurements[0]); again.append(m_b.measurements[0])
+    sv.apply_gates(gates, outcomes, rng)
+    return [int(outcomes[m]) for m in first], [int(outcomes[m]) for m in again], float(sv.norm2())
+
+
 # ---------------------------------------------------------------------------------------------
 # tests
 # ---------------------------------------------------------------------------------------------
@@ -407,6 +432,14 @@ def test_sharded_mid_circuit_measurements_match_oracle(world):
     for n_got, n_ref, same, outcomes in run_ranks(world, "w_mcm", 6, 13, 12):
         assert n_got == n_ref == 12 and same
         assert len(outcomes) > 1                       # several branches were actually visited
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_sharded_mid_measure_on_complex64_shards_renormalises(world):
+    for seed in (3, 4, 5):
+        for first, again, norm in run_ranks(world, "w_mcm_c64", 7, seed):
+            assert first == again                     # a repeated measurement repeats its outcome
+            assert abs(norm - 1.0) < 1e-5             # complex64 tolerance
 
 
 @pytest.mark.parametrize("world", [2, 4])

@@ -119,6 +119,20 @@ def main():
                        "shots_per_s_prefix_once_branch_cache": shots / t_cached,
                        "shots_per_s_full_tape_per_shot": shots / t_full}
 
+    # the same dynamic circuit through mcm_method="tree-traversal" (tree_mcm.py; reference
+    # simulate.py:396-611): the outcome tree is walked once, every node splits its shot budget,
+    # terminal samples are drawn once per leaf
+    simulate(dynamic_tape(Mq, 2)[0], rng=np.random.default_rng(0), fusion=1, mcm_method="tree-traversal")
+    torch.cuda.synchronize()
+    tree = {}
+    for sh in (shots, 100 * shots):
+        t0 = time.perf_counter()
+        simulate(dynamic_tape(Mq, sh)[0], rng=np.random.default_rng(1), fusion=1, mcm_method="tree-traversal")
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        tree[f"shots_{sh}"] = {"seconds": dt, "shots_per_s": sh / dt}
+    out["tree_traversal"] = {"qubits": Mq, "mid_circuit_measurements": 4, "leaves_at_most": 16, **tree}
+
     from oracle.simulate import simulate as oracle_simulate
     n_cpu, cpu_shots = 20, 3
     t0 = time.perf_counter()
