@@ -198,8 +198,9 @@ def run_sharded(args, dist, rank, world, local_rank):
             "exchange": {"per_step": sv_stats_per_step(ex_bytes, args.steps),
                          "count_per_step": n_windows + n_plain,
                          "overlapped_with_sweeps": n_windows, "not_overlapped": n_plain,
-                         "mode": "symmetric-memory pulls on a second stream, pipelined piece by piece against the "
-                                 "segments before / after (sharded._schedule)" if sv_symm
+                         "mode": "copy-engine pushes into the partners' staging buffers (peer-mapped symmetric memory), "
+                                 "stream-memory-op flags, TMA unpack kernel; two communication streams, pipelined "
+                                 "piece by piece against the segments before / after (sharded._schedule)" if sv_symm
                                  else "NCCL send/recv (no overlap)",
                          "comm_stream_seconds_per_step": comm_s / args.steps if comm_s else None,
                          "sent_gbps_per_gpu": (ex_bytes / comm_s / 1e9) if comm_s > 0 else

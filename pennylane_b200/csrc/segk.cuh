@@ -401,16 +401,26 @@ __device__ __forceinline__ void sk_scale(C (&A)[NV][NA], const Coefs& cs, const 
 template <unsigned XR, unsigned ZR, bool ODD, int SLOT>
 __device__ __forceinline__ void sk_gen(const C (&A)[NV][NA], const Coefs& cs, const unsigned off,
                                        const unsigned tpar, double* accs, const unsigned tid) {
-  double acc = 0.0;
+  // two FMAs per amplitude into four independent chains (the sign of the term is a compile-time
+  // operand negation); the first version formed the product (DMUL + DFMA) and added it (DADD):
+  // 24 FP64 instructions per record and thread instead of 16
+  double ac[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
   for (int k = 0; k < NA; ++k) {
     const C b = A[NV - 1][k], x = A[0][k ^ XR];
-    double val;
-    if (ODD) val = fma((double)b.y, (double)x.y, (double)b.x * (double)x.x);
-    else val = fma(-(double)b.y, (double)x.x, (double)b.x * (double)x.y);
-    if (__popc((unsigned)(k ^ XR) & ZR) & 1) acc -= val;
-    else acc += val;
+    const bool neg = __popc((unsigned)(k ^ XR) & ZR) & 1;
+    const double bx = neg ? -(double)b.x : (double)b.x, by = neg ? -(double)b.y : (double)b.y;
+    double& a0 = ac[2 * (k & 1)];
+    double& a1 = ac[2 * (k & 1) + 1];
+    if (ODD) {
+      a0 = fma(bx, (double)x.x, a0);
+      a1 = fma(by, (double)x.y, a1);
+    } else {
+      a0 = fma(bx, (double)x.y, a0);
+      a1 = fma(-by, (double)x.x, a1);
+    }
   }
+  double acc = (ac[0] + ac[1]) + (ac[2] + ac[3]);
   const C cf = cs.pair(off);
   acc *= tpar ? -(double)cf.x : (double)cf.x;
   acc = sk_warp_sum(acc);

@@ -134,10 +134,12 @@ def test_world1_cuda_engine_matches_oracle(dist1, fusion):
         assert v < 1e-12, (k, v)
 
 
-def _worker(rank, world, port, q_):
+def _worker(rank, world, port, q_, exchange="symm"):
     try:
         import torch
         import torch.distributed as dist
+
+        os.environ["B200Q_EXCHANGE"] = exchange       # "nccl": the send / recv fallback of the exchange
 
         os.environ["MASTER_ADDR"] = "127.0.0.1"
         os.environ["MASTER_PORT"] = str(port)
@@ -145,7 +147,7 @@ def _worker(rank, world, port, q_):
         dist.init_process_group("nccl", rank=rank, world_size=world,
                                 device_id=torch.device(f"cuda:{rank}"))
         res = {}
-        for fusion in (0, 1):
+        for fusion in ((0, 1) if exchange == "symm" else (1,)):
             for k, v in _check_all(dist, 15, 33, fusion).items():
                 res[f"f{fusion}_{k}"] = v
         # the overlapped schedule: specialised segment kernels forced on (their partial launches
@@ -160,8 +162,11 @@ def _worker(rank, world, port, q_):
         q_.put((rank, "err", traceback.format_exc()))
 
 
-@pytest.mark.parametrize("world", [2, 4])
-def test_multi_gpu_exchange_matches_oracle(world):
+@pytest.mark.parametrize("world,exchange", [(2, "symm"), (4, "symm"), (2, "nccl")])
+def test_multi_gpu_exchange_matches_oracle(world, exchange):
+    """``exchange``: "symm" = pushes over peer-mapped symmetric memory with stream-memory-op
+    flags and the TMA unpack kernel; "nccl" = the ``isend`` / ``irecv`` fallback taken when the
+    symmetric allocation is refused (same window schedule, blocking pieces)."""
     import torch
     import torch.multiprocessing as mp
 
@@ -170,7 +175,7 @@ def test_multi_gpu_exchange_matches_oracle(world):
     ctx = mp.get_context("spawn")
     q_ = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q_)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q_, exchange)) for r in range(world)]
     for p in procs:
         p.start()
     for _ in range(world):
