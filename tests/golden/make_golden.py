@@ -159,6 +159,90 @@ cases.append({"id": "adjoint_jacobian_ry_z", "type": "jacobian",
               "measurements": [{"kind": "expval", "obs": g("PauliZ", [0])}],
               "expected": [[float(-np.sin(x))]], "atol": 1e-8})
 
+# ---- tests/devices/qubit/test_simulate.py:172-261 (the same circuit at the angles of the four
+#      interface tests; gradients of those tests are pinned by the adjoint cases below) --------------
+for tag, phi_i, lines in (("autograd", -0.52, ":172-189"), ("jax", 0.678, ":192-214"),
+                          ("torch", -0.526, ":216-237"), ("tf", 4.873, ":240-260")):
+    cases.append({"id": f"simulate_rx_expval_yz_{tag}_angle", "type": "simulate",
+                  "source": f"tests/devices/qubit/test_simulate.py{lines}",
+                  "ops": [g("RX", [0], [phi_i])],
+                  "measurements": [{"kind": "expval", "obs": g("PauliY", [0])},
+                                   {"kind": "expval", "obs": g("PauliZ", [0])}],
+                  "expected": [c(-np.sin(phi_i)), c(np.cos(phi_i))], "atol": 1e-8})
+# ---- tests/devices/qubit/test_simulate.py:263-268 ---------------------------------------------------------
+cases.append({"id": "simulate_rx_pi_expval_z", "type": "simulate",
+              "source": "tests/devices/qubit/test_simulate.py:263-268",
+              "ops": [g("RX", [0], [np.pi])],
+              "measurements": [{"kind": "expval", "obs": g("PauliZ", [0])}],
+              "expected": [c(-1.0)], "atol": 1e-8})
+# ---- tests/devices/qubit/test_simulate.py:1003-1076 (quantum-information measurements of IsingXX(phi)|00>)
+phi_q = -0.623
+d_i = np.array([[np.cos(phi_q / 2) ** 2, 0], [0, np.sin(phi_q / 2) ** 2]])
+d_both = np.array([[np.cos(phi_q / 2) ** 2, 0, 0, 0.0 + np.sin(phi_q) * 0.5j], [0, 0, 0, 0], [0, 0, 0, 0],
+                   [0.0 - np.sin(phi_q) * 0.5j, 0, 0, np.sin(phi_q / 2) ** 2]])
+root = np.sqrt(1 - 4 * np.cos(phi_q / 2) ** 2 * np.sin(phi_q / 2) ** 2)
+eigs = [e for e in ((1 + root) / 2, (1 - root) / 2) if e > 0]
+entropy = -np.sum(np.array(eigs) * np.log(eigs))
+cases.append({"id": "simulate_qinfo_isingxx", "type": "simulate",
+              "source": "tests/devices/qubit/test_simulate.py:1003-1076",
+              "ops": [g("IsingXX", [0, 1], [phi_q])],
+              "measurements": [{"kind": "density_matrix", "wires": [0]}, {"kind": "density_matrix", "wires": [1]},
+                               {"kind": "density_matrix", "wires": [0, 1]}, {"kind": "vn_entropy", "wires": [0]},
+                               {"kind": "vn_entropy", "wires": [1]},
+                               {"kind": "mutual_info", "wires0": [0], "wires1": [1]}],
+              "expected": [c(d_i), c(d_i), c(d_both), c(entropy), c(entropy), c(2 * entropy)], "atol": 1e-8})
+
+# ---- tests/devices/qubit/test_adjoint_jacobian.py:133-149 (three RX, diagonal Jacobian) -----------------------
+par3 = [np.pi, np.pi / 2, np.pi / 3]
+cases.append({"id": "adjoint_jacobian_multiple_rx", "type": "jacobian",
+              "source": "tests/devices/qubit/test_adjoint_jacobian.py:133-149",
+              "ops": [g("RX", [i], [par3[i]]) for i in range(3)], "trainable": [0, 1, 2],
+              "measurements": [{"kind": "expval", "obs": g("PauliZ", [i])} for i in range(3)],
+              "expected": (-np.diag(np.sin(par3))).tolist(), "atol": 1e-8})
+# ---- :230-268 (Hermitian observable on wires 0, 2) and :270-298 (X0 @ Y2): the same closed form ----------------
+a_, b_, c_ = 0.5, 0.3, -0.7
+ops3 = [g("RX", [0], [a_]), g("RX", [1], [b_]), g("RX", [2], [c_]), g("CNOT", [0, 1]), g("CNOT", [1, 2])]
+exp3 = [np.cos(a_) * np.sin(b_) * np.sin(c_), np.cos(b_) * np.sin(a_) * np.sin(c_),
+        np.cos(c_) * np.sin(b_) * np.sin(a_)]
+mx = np.kron(np.array([[0, 1], [1, 0]]), np.array([[0, -1j], [1j, 0]]))
+cases.append({"id": "adjoint_jacobian_hermitian_x0y2", "type": "jacobian",
+              "source": "tests/devices/qubit/test_adjoint_jacobian.py:230-268",
+              "ops": ops3, "trainable": [0, 1, 2],
+              "measurements": [{"kind": "expval", "obs": {"name": "Hermitian", "wires": [0, 2], "matrix": c(mx)}}],
+              "expected": [exp3], "atol": 1e-8})
+cases.append({"id": "adjoint_jacobian_tensor_x0y2", "type": "jacobian",
+              "source": "tests/devices/qubit/test_adjoint_jacobian.py:270-298",
+              "ops": ops3, "trainable": [0, 1, 2],
+              "measurements": [{"kind": "expval", "obs": {"name": "Prod", "ops": [g("PauliX", [0]), g("PauliY", [2])]}}],
+              "expected": [exp3], "atol": 1e-8})
+# ---- :392-432 (JVP, two parameters) and :503-545 (VJP, two parameters), RY(x) RZ(y) on one wire --------------
+y = 1.221
+jac3 = np.array([[-np.sin(x), 0], [np.cos(x) * np.cos(y), -np.sin(x) * np.sin(y)],
+                 [np.cos(x) * np.sin(y), np.sin(x) * np.cos(y)]])
+mps3 = [{"kind": "expval", "obs": g(nm, [0])} for nm in ("PauliZ", "PauliX", "PauliY")]
+for tg in ((0.0, 0.653), (1.232, 2.963)):
+    cases.append({"id": f"adjoint_jvp_multi_param_single_obs_{tg[1]}", "type": "jvp",
+                  "source": "tests/devices/qubit/test_adjoint_jacobian.py:392-407",
+                  "ops": [g("RY", [0], [x]), g("RZ", [0], [y])], "trainable": [0, 1], "tangents": list(tg),
+                  "measurements": [mps3[2]], "expected": [float(jac3[2] @ np.array(tg))], "atol": 1e-8})
+    cases.append({"id": f"adjoint_jvp_multi_param_multi_obs_{tg[1]}", "type": "jvp",
+                  "source": "tests/devices/qubit/test_adjoint_jacobian.py:409-432",
+                  "ops": [g("RY", [0], [x]), g("RZ", [0], [y])], "trainable": [0, 1], "tangents": list(tg),
+                  "measurements": mps3, "expected": (jac3 @ np.array(tg)).tolist(), "atol": 1e-8})
+# :434-455 uses wire labels [1, 0] / ["a", "b"]; transcribed on the standard labels it maps them to
+cases.append({"id": "adjoint_jvp_two_wires_ry_rx", "type": "jvp",
+              "source": "tests/devices/qubit/test_adjoint_jacobian.py:434-455",
+              "ops": [g("RY", [0], [x]), g("RX", [1], [y])], "trainable": [0, 1], "tangents": [1.232, 2.963],
+              "measurements": [{"kind": "expval", "obs": g("PauliZ", [0])}, {"kind": "expval", "obs": g("PauliY", [1])},
+                               {"kind": "expval", "obs": g("PauliX", [0])}],
+              "expected": (np.array([[-np.sin(x), 0], [0, -np.cos(y)], [np.cos(x), 0]]) @ np.array([1.232, 2.963])).tolist(),
+              "atol": 1e-8})
+for ct in ((0.0, 0.653, 0.0), (1.236, 0.0, 0.573), (1.232, 2.963, 1.942)):
+    cases.append({"id": f"adjoint_vjp_multi_param_multi_obs_{ct[0]}", "type": "vjp",
+                  "source": "tests/devices/qubit/test_adjoint_jacobian.py:519-545",
+                  "ops": [g("RY", [0], [x]), g("RZ", [0], [y])], "trainable": [0, 1], "cotangents": list(ct),
+                  "measurements": mps3, "expected": (np.array(ct) @ jac3).tolist(), "atol": 1e-8})
+
 out = os.path.join(HERE, "reference_known_answers.json")
 json.dump({"reference": "PennyLaneAI/pennylane v0.46.0-dev81 (tests/devices/qubit/*)",
            "generated_by": "tests/golden/make_golden.py", "cases": cases}, open(out, "w"), indent=1)

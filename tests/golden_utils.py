@@ -39,6 +39,10 @@ def build_mp(spec):
         return qb.state()
     if "obs" in spec:
         return getattr(qb, kind)(build_op(spec["obs"]))
+    if kind == "mutual_info":
+        return qb.mutual_info(spec["wires0"], spec["wires1"])
+    if kind in ("density_matrix", "vn_entropy", "purity"):
+        return getattr(qb, kind)(spec["wires"])
     return getattr(qb, kind)(wires=spec["wires"])
 
 
