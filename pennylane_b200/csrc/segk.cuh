@@ -398,9 +398,14 @@ __device__ __forceinline__ void sk_scale(C (&A)[NV][NA], const Coefs& cs, const 
 // sign_k = (-1)^(popc((k ^ XR) & ZR) + tpar).  XR / ZR: X and Z parts of the Pauli term on
 // register bits; `tpar`: parity of the thread / external Z part (+ the i^2 of two Y factors);
 // ODD: an odd number of Y factors (the term is i * real Pauli: take Re instead of Im).
-template <unsigned XR, unsigned ZR, bool ODD, int SLOT>
-__device__ __forceinline__ void sk_gen(const C (&A)[NV][NA], const Coefs& cs, const unsigned off,
-                                       const unsigned tpar, double* accs, const unsigned tid) {
+// The per-thread part of it: coef * sum over this thread's amplitudes.  The warp reduction is
+// shared between up to four terms (sk_gen_flush*): a butterfly that halves the number of lanes
+// per value at each step needs 6 double shuffles for four values (5 for two) where four separate
+// reductions need 20 — ncu on the reverse sweep: SHFL 8.5 % of the issued instructions and
+// mio_throttle the top stall.
+template <unsigned XR, unsigned ZR, bool ODD>
+__device__ __forceinline__ double sk_gen_val(const C (&A)[NV][NA], const Coefs& cs, const unsigned off,
+                                             const unsigned tpar) {
   // two FMAs per amplitude into four independent chains (the sign of the term is a compile-time
   // operand negation); the first version formed the product (DMUL + DFMA) and added it (DADD):
   // 24 FP64 instructions per record and thread instead of 16
@@ -420,11 +425,47 @@ __device__ __forceinline__ void sk_gen(const C (&A)[NV][NA], const Coefs& cs, co
       a1 = fma(-by, (double)x.x, a1);
     }
   }
-  double acc = (ac[0] + ac[1]) + (ac[2] + ac[3]);
+  const double acc = (ac[0] + ac[1]) + (ac[2] + ac[3]);
   const C cf = cs.pair(off);
-  acc *= tpar ? -(double)cf.x : (double)cf.x;
-  acc = sk_warp_sum(acc);
-  if ((tid & 31u) == 0) accs[SLOT * NW + (tid >> 5)] += acc;
+  return acc * (tpar ? -(double)cf.x : (double)cf.x);
+}
+__device__ __forceinline__ double sk_shx(const double v, const int o) { return __shfl_xor_sync(0xffffffffu, v, o); }
+// warp sums of one / two / four per-thread values into accs[slot][warp]; the slots of one call
+// are distinct (the host adds values of the same slot before), fixed order: deterministic
+template <int S0>
+__device__ __forceinline__ void sk_gen_flush1(double v0, double* accs, const unsigned tid) {
+  v0 = sk_warp_sum(v0);
+  if ((tid & 31u) == 0) accs[S0 * NW + (tid >> 5)] += v0;
+}
+template <int S0, int S1>
+__device__ __forceinline__ void sk_gen_flush2(const double v0, const double v1, double* accs, const unsigned tid) {
+  const bool hi = tid & 16u;
+  double m = (hi ? v1 : v0) + sk_shx(hi ? v0 : v1, 16);      // lanes 0-15: v0, lanes 16-31: v1
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) m += sk_shx(m, o);
+  if ((tid & 15u) == 0) accs[(hi ? S1 : S0) * NW + (tid >> 5)] += m;
+}
+template <int S0, int S1, int S2>
+__device__ __forceinline__ void sk_gen_flush3(const double v0, const double v1, const double v2, double* accs,
+                                              const unsigned tid) {
+  const bool hi = tid & 16u, mid = tid & 8u;
+  const double m0 = (hi ? v2 : v0) + sk_shx(hi ? v0 : v2, 16);   // lanes 0-15: (v0, v1), 16-31: (v2, -)
+  const double m1 = (hi ? 0.0 : v1) + sk_shx(hi ? v1 : 0.0, 16);
+  double m = (mid ? m1 : m0) + sk_shx(mid ? m0 : m1, 8);
+#pragma unroll
+  for (int o = 4; o > 0; o >>= 1) m += sk_shx(m, o);
+  if ((tid & 7u) == 0 && !(hi && mid)) accs[(hi ? S2 : (mid ? S1 : S0)) * NW + (tid >> 5)] += m;
+}
+template <int S0, int S1, int S2, int S3>
+__device__ __forceinline__ void sk_gen_flush4(const double v0, const double v1, const double v2, const double v3,
+                                              double* accs, const unsigned tid) {
+  const bool hi = tid & 16u, mid = tid & 8u;
+  const double m0 = (hi ? v2 : v0) + sk_shx(hi ? v0 : v2, 16);   // lanes 0-15: (v0, v1), 16-31: (v2, v3)
+  const double m1 = (hi ? v3 : v1) + sk_shx(hi ? v1 : v3, 16);
+  double m = (mid ? m1 : m0) + sk_shx(mid ? m0 : m1, 8);         // 8-lane groups: v0, v1, v2, v3
+#pragma unroll
+  for (int o = 4; o > 0; o >>= 1) m += sk_shx(m, o);
+  if ((tid & 7u) == 0) accs[(hi ? (mid ? S3 : S2) : (mid ? S1 : S0)) * NW + (tid >> 5)] += m;
 }
 
 // ---- tile movement ----------------------------------------------------------------------------

@@ -492,7 +492,9 @@ def emit_config(plan: SegPlan) -> str:
         f"#define SK_NSLOTS {plan.nslots}", f"#define SK_NEXT {len(plan.ext_pos)}",
         f"#define SK_SWW {g.sww}",
         f"#define SK_COEF_PARAM {1 if plan.coef_param else 0}",
-        f"#define SK_MAXREG {_max_registers()}",
+        # the cap leaves room for the exchange's unpack kernel beside FORWARD segments; the reverse
+        # sweep (NV = 2, one 512-thread CTA per SM) never runs inside an exchange window
+        f"#define SK_MAXREG {_max_registers() if g.NV == 1 else 128}",
         f"#define SK_RPOS {_arr2([r for r, _ in plan.rounds])}",
         f"#define SK_TPOS {_arr2([t for _, t in plan.rounds])}",
     ]
@@ -520,10 +522,32 @@ def _par_expr(mt, me, const=0) -> str:
     return "((" + " + ".join(parts) + ") & 1u)" if parts else "0u"
 
 
+#: Generator terms whose warp sums share one butterfly.  0 (default): ADJACENT terms only (no gate
+#: between them), so no value stays live across gate code; 2 / 4: groups across gates — measured
+#: slower (0.875 s vs 0.785 s per 30-qubit Jacobian: the pending values spill at the register cap);
+#: 1: one reduction per term (0.794 s).
+_GEN_GROUP = int(os.environ.get("B200Q_SK_GEN_GROUP", "0"))
+
+
 def emit_body(plan: SegPlan) -> str:
     out = []
+    pending = []                                    # [(variable, slot)] generator terms awaiting their warp sum
+
+    def flush():
+        # one butterfly per group of 4 / 2 / 1 values with DISTINCT slots (sk_gen_flush*)
+        while pending:
+            grp = pending[:4] if len(pending) >= 4 else pending[:len(pending)]
+            del pending[:len(grp)]
+            names = ", ".join(v for v, _ in grp)
+            slots = ", ".join(str(sl) for _, sl in grp)
+            out.append(f"sk_gen_flush{len(grp)}<{slots}>({names}, accs, tid);")
+
+    ngen = 0
     for rec in plan.ir:
         k = rec[0]
+        if k in ("xpose", "scale") or (_GEN_GROUP == 0 and k != "gen"):
+            flush()                                 # do not carry pending values across a transposition
+                                                    # (group 0: nor across any gate — adjacent terms only)
         if k == "load":
             out.append(f"SK_LOAD({rec[1]})")
         elif k == "fetch":
@@ -562,12 +586,22 @@ def emit_body(plan: SegPlan) -> str:
             out.append(f"sk_diag<{rc[0]}u, {rc[1]}u, {rc[2]}u, {rc[3]}u, {rc[4]}u>(A, SK_COEF({off}), {i0});")
         elif k == "gen":
             _, xr, zr, odd, slot, off, (zt, ze, c) = rec
-            out.append(f"sk_gen<{xr}u, {zr}u, {'true' if odd else 'false'}, {slot}>(A, SK_COEF({off}), "
-                       f"{_par_expr(zt, ze, c)}, accs, tid);")
+            expr = (f"sk_gen_val<{xr}u, {zr}u, {'true' if odd else 'false'}>(A, SK_COEF({off}), "
+                    f"{_par_expr(zt, ze, c)})")
+            same = [v for v, sl in pending if sl == slot]
+            if same:                                # same parameter: add in registers, one slot per butterfly
+                out.append(f"{same[0]} += {expr};")
+            else:
+                out.append(f"double g{ngen} = {expr};")
+                pending.append((f"g{ngen}", slot))
+                ngen += 1
+                if len(pending) == (_GEN_GROUP or 4):
+                    flush()
         elif k == "scale":
             out.append(f"sk_scale(A, SK_COEF({rec[1]}));")
         else:  # pragma: no cover
             raise AssertionError(k)
+    flush()
     return "\n".join("    " + line for line in out) + "\n"
 
 
