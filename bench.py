@@ -150,6 +150,13 @@ def cpu_baseline_sample(n_full, n_twin=26, gates_per_kind=8, repeat=1):
     while n_twin > 20 and 6 * 16 * (1 << n_twin) > avail:
         n_twin -= 1
     cores = os.cpu_count() or 1
+    # torchrun exports OMP_NUM_THREADS=1: give numpy's BLAS / OpenMP pools every host core back
+    # for the CPU arm (the reference's numpy kernels use whatever the pools offer)
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=cores)
+    except Exception:
+        pass
     rng = np.random.default_rng(3)
     wires = [int(round(x)) for x in np.linspace(0, n_twin - 1, gates_per_kind)]
     ops_ = []
