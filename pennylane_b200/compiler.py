@@ -20,6 +20,7 @@ a device option; the unfused path stays the bit-for-bit-stable default for parit
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -425,11 +426,19 @@ class Segment:
 
 def pack_segments(prims: list[Prim], n: int, T: int = 12, L: int = 5, max_ops: int = 96,
                   max_mat: int = 1024, round_budget: int | None = None, RB: int = 4,
-                  sww: int = 3) -> list[Segment]:
+                  sww: int = 3, trim_rounds: bool = False) -> list[Segment]:
     """``round_budget``: the primitives of a segment that do not fit that many rounds of the
     register kernel (``RB`` register bits per round) are handed back and packed later — an extra
     shared-memory transposition per tile costs about a quarter of a sweep, so single-qubit blocks
-    that a later segment can take for free should not force one."""
+    that a later segment can take for free should not force one.
+
+    ``trim_rounds``: the same hand-back, applied only where it is free.  Measured per-segment time
+    at 30 qubits: ``max(5.75 ms, 2.0 + 1.0 (rounds - 1) + 0.2 blocks)`` — a segment of 4+ rounds is
+    bound by its transpositions while its neighbours of 2 rounds idle at the memory time.  The
+    greedy packer lets the segment that closes a layer's CNOT chain also take the NEXT layer's
+    single-qubit blocks on its bits, which costs it a round or two; if dropping a few trailing
+    uncontrolled single-qubit blocks saves a round, they are handed back (the lowest ``L`` bits are
+    in every tile, the following two-round segments have a spare register slot for them)."""
     T = min(T, n)
     L = min(L, T)
     free = T - L
@@ -497,6 +506,25 @@ def pack_segments(prims: list[Prim], n: int, T: int = 12, L: int = 5, max_ops: i
                     segments.append(Segment(bits, seg, sum(p.ngates for p in seg), rounds))
                     remaining = keep
                     continue
+            elif trim_rounds and len(bits) == T and len(bits) > RB and not any(p.kind == SWAP for p in seg):
+                full = schedule_rounds(seg, bits, RB, sww)
+                best = None
+                for budget in (len(full) - 1, len(full) - 2):
+                    if len(full) < 4 or budget < 2:
+                        break
+                    rounds, left = schedule_rounds_budget(seg, bits, RB, sww, budget)
+                    if left and len(left) < len(seg) and len(left) <= 6 and all(
+                            q.kind == DENSE1 and not q.ctrl and q.mat0 is None for q in left):
+                        best = (rounds, left)
+                if best is not None:
+                    rounds, left = best
+                    drop = {id(p) for p in left}
+                    seg = [p for p in seg if id(p) not in drop]
+                    order = {id(p): i for i, p in enumerate(remaining)}
+                    keep = sorted(keep + left, key=lambda p: order[id(p)])
+                    segments.append(Segment(bits, seg, sum(p.ngates for p in seg), rounds))
+                    remaining = keep
+                    continue
             segments.append(Segment(bits, seg, sum(p.ngates for p in seg)))
         remaining = keep
     return segments
@@ -517,13 +545,17 @@ def lower_all(ops_, bit_of, batched_ok: bool = False) -> list[Prim]:
 
 def compile_ops(ops_, n: int, bit_of=None, level: int = 1, T: int = 12, L: int = 5,
                 batched_ok: bool = False, fold_cx: bool = True, round_budget: int | None = None,
-                RB: int = 4, sww: int = 3):
-    """Operators -> list of :class:`Segment`."""
+                RB: int = 4, sww: int = 3, trim_rounds: bool | None = None):
+    """Operators -> list of :class:`Segment`.  ``trim_rounds`` (default: on for the specialised
+    kernels, i.e. ``fold_cx`` off; B200Q_TRIM_ROUNDS=0 switches it off): see pack_segments."""
+    if trim_rounds is None:
+        trim_rounds = (not fold_cx) and os.environ.get("B200Q_TRIM_ROUNDS", "1") != "0"
     if bit_of is None:
         bit_of = lambda w: n - 1 - int(w)          # noqa: E731
     prims = lower_all(ops_, bit_of, batched_ok)
     prims = merge_blocks(prims, level, fold_cx)
-    return pack_segments(prims, n, T=T, L=L, round_budget=round_budget, RB=RB, sww=sww)
+    return pack_segments(prims, n, T=T, L=L, round_budget=round_budget, RB=RB, sww=sww,
+                         trim_rounds=bool(trim_rounds))
 
 
 def _expand_select(prims):
@@ -630,6 +662,14 @@ class RtOp(C.Structure):
 
 
 assert C.sizeof(RtOp) == 64
+
+
+def _first_min_pos(sww):
+    """Lowest tile position that may be a register bit in the FIRST round.  The first round reads
+    the landing buffer in natural (unswizzled) order: a register bit below position ``sww`` makes
+    that one read 2- to 8-way bank-conflicting (tuning knob B200Q_FIRST_MIN_POS; default: sww)."""
+    v = _os.environ.get("B200Q_FIRST_MIN_POS")
+    return sww if v is None else int(v)
 
 
 @dataclass
@@ -803,7 +843,7 @@ def _schedule_rounds_critical(prims, tile_bits, RB: int, sww: int = 3, max_round
     while left or first:
         closing = max_rounds is not None and len(rounds) == max_rounds - 1
         if first:
-            allowed = set(range(min(sww, T - RB), T))
+            allowed = set(range(min(_first_min_pos(sww), T - RB), T))
             if closing:
                 allowed &= io_allowed
             R, run, _ = run_round(allowed, True)
@@ -859,7 +899,7 @@ def _schedule_rounds_order(prims, tile_bits, RB: int, sww: int = 3):
             # The first round is read out of the landing buffer the bulk copies filled (natural,
             # unswizzled order), not from global memory: any position >= sww may be a register
             # bit; positions 0..sww-1 stay on the lowest lane bits (conflict-free reads).
-            R, run, keep = greedy(set(range(min(sww, T - RB), T)), remaining)
+            R, run, keep = greedy(set(range(min(_first_min_pos(sww), T - RB), T)), remaining)
             io = True
         else:
             # prefer a round that is IO-compatible when it finishes the segment

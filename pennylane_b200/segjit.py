@@ -249,7 +249,10 @@ def plan_segment(seg, geom: Geometry, L: int, forms_hint=None, final_scale: bool
     tile_bits = list(seg.tile_bits)
     assert len(tile_bits) == geom.T
     RB, TB = geom.RB, geom.TB
-    rounds = getattr(seg, "rounds", None) or cc.schedule_rounds(seg.prims, tile_bits, RB, geom.sww)
+    rounds = getattr(seg, "rounds", None)
+    if rounds and len(rounds[0].rpos) != RB:         # scheduled by the packer for another geometry
+        rounds = None
+    rounds = rounds or cc.schedule_rounds(seg.prims, tile_bits, RB, geom.sww)
     bld = _Builder(geom, tile_bits, L)
     index_of = {id(p): i for i, p in enumerate(seg.prims)}
     nrounds = len(rounds)

@@ -119,7 +119,7 @@ def test_structure_key_is_independent_of_values_and_positions():
         segs = cc.compile_ops(bench.hea_ops(n, seed=seed), n, level=1, T=geom.T, L=5, fold_cx=False)
         keys[seed] = [sj.plan_segment(s, geom, 5).key for s in segs]
     assert keys[3] == keys[4]
-    assert len(set(keys[3])) <= 16
+    assert len(set(keys[3])) <= 20
     # every block of the ansatz is RZ.RY: the real kernel + one phase
     segs = cc.compile_ops(bench.hea_ops(n), n, level=1, T=geom.T, L=5, fold_cx=False)
     plan = sj.plan_segment(segs[1], geom, 5)
