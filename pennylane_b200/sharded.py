@@ -17,11 +17,21 @@ ordinary gate on ``nl`` wires and the single-GPU engine (fused segments included
 unchanged.  When a non-diagonal target sits on a rank bit the planner (``plan``) inserts a
 *remap*: ``k`` rank bits are exchanged with the top ``k`` local bits.  With that choice the data
 a rank sends to each of its ``2**k - 1`` partners is one contiguous slice of its shard and what
-it receives lands in the very same slice, so the exchange is in place: grouped
-``isend``/``irecv`` (``ncclSend``/``ncclRecv`` under ``torch.distributed``) through a bounded
-staging buffer; nothing the size of a second shard is allocated.  Victims are chosen Belady-style
+it receives lands in the very same slice, so the exchange is in place through bounded staging
+buffers; nothing the size of a second shard is allocated.  Victims are chosen Belady-style
 (the local bits whose next non-diagonal use is furthest away) and moved to the top local
 positions with ordinary SWAP gates that ride in the preceding fused segment.
+
+The exchange (K9).  On CUDA the slab pieces are PUSHED into the partners' staging buffers by
+copy-engine copies whose destination is peer memory (``torch.distributed._symmetric_memory``
+supplies the mapping), *landed* / *consumed* flags are stream memory operations, and the staging
+buffer is unpacked into place by a TMA kernel that shares the SMs with the sweeps
+(``csrc/remap.cu``); three staging buffers rotate on two communication streams.  An exchange is
+cut into pieces along index bits that the segments before and after it leave alone, and those
+segments run piece by piece (partial launches) so that transfer and sweeps overlap
+(``_schedule`` / ``_run_window``).  Grouped ``isend``/``irecv`` (``ncclSend``/``ncclRecv`` under
+``torch.distributed``) stay as the fallback when the symmetric allocation is refused, and are
+what the ``gloo`` tests exercise.
 
 Reductions.  Pauli-sum expectation values: every rank evaluates the terms whose X/Y factors are
 local (Z factors on rank bits are signs), partial sums are all-gathered and added in rank order
@@ -657,7 +667,6 @@ class ShardedStateVector:
         self.timer = None          # optional: callable(kind, fn) -> fn() (bench.py times steps)
         self.comm_records = []     # (start, end) events of the exchange pieces while a timer is set
         self.trace = None          # list: per-piece CUDA events of windows (tools/trace_window.py)
-        self.exchange_mode = "push"
         self.reset()
 
     # -- bookkeeping ---------------------------------------------------------------------------
@@ -1037,7 +1046,7 @@ class ShardedStateVector:
         per_partner = max(1, self.stage_bytes // (itemsize * len(partners)))
         cap = min(chunk >> pb, 1 << (per_partner.bit_length() - 1))      # amplitudes per partner and step
         ctx = {"ex": ex, "data": data, "chunk": chunk, "q": q, "partners": partners, "lo": lo, "pb": pb,
-               "cap": cap, "itemsize": itemsize, "it": 0, "events": {}, "symm": None, "unpacked": []}
+               "cap": cap, "itemsize": itemsize, "events": {}, "symm": None}
         if data.is_cuda and self._symm_stage(max(cap * len(partners), self.stage_bytes // itemsize), data.dtype,
                                              data.device) is not None:
             import torch
