@@ -732,9 +732,27 @@ def schedule_rounds(prims, tile_bits, RB: int, sww: int = 3):
     return b if len(b) < len(a) else a
 
 
+def low_run(tile_bits) -> int:
+    """Number of leading tile bits that are contiguous from bit 0 (the kernel's L)."""
+    run = 0
+    for i, b in enumerate(tile_bits):
+        if b != i:
+            break
+        run += 1
+    return run
+
+
+def io_lanes(tile_bits, RB) -> int:
+    """Tile positions that stay on the lanes in the last (store) round: the contiguous low run of
+    the tile, at most _IO_LANES — a position above the run is not contiguous in memory, keeping it on
+    the lanes buys no coalescing and costs the round its register slot (with L = 4 tiles it forced a
+    third round on every 8-target segment)."""
+    return min(_IO_LANES, low_run(tile_bits), len(tile_bits) - RB)
+
+
 def _round_helpers(tile_bits, RB, sww):
     T = len(tile_bits)
-    lanes = min(_IO_LANES, T - RB)
+    lanes = io_lanes(tile_bits, RB)
     io_allowed = set(range(lanes, T))
 
     def finish(R, io):

@@ -384,7 +384,8 @@ def get_program(sv, ops_, level, T=None, L=None, bit_of=None):
     n = sv.n
     dT, dL = sv.default_tile()
     T = T or dT
-    L = dL if L is None else L
+    if L is None:                                    # programs always run on the specialised kernels
+        L = min(segjit.default_low_bits(sv.dtype_code, 1), T)
     if bit_of is None:
         bit_of_f = lambda w: n - 1 - int(w)          # noqa: E731
         bkey = None

@@ -152,6 +152,17 @@ class Geometry:
         return 3 if self.dtype_code else 4
 
 
+def default_low_bits(dtype_code: int, nv: int = 1) -> int:
+    """Contiguous low tile bits (L) the packer reserves for the specialised kernels.  complex128
+    forward: 4 (256-byte runs: the same copy ceiling as 512-byte ones, and 8 free tile bits instead
+    of 7 — the 30-qubit ansatz packs into 27 segments / 67 rounds instead of 29 / 77: 187.8 ->
+    174.5 ms per step, tools/microbench_segk.py); everything else: 5."""
+    env = os.environ.get("B200Q_TILE_L")
+    if env:
+        return int(env)
+    return 4 if (dtype_code and nv == 1) else 5
+
+
 def default_geometry(dtype_code: int, nv: int = 1) -> Geometry:
     """Forward: T = 12 (c128) / 13 (c64), 256 threads, 2 CTAs per SM.  Adjoint (two vectors per
     thread): one register bit fewer, 512 threads, 1 CTA per SM (B200Q_SK_ADJ=1: 256 x 2)."""
@@ -350,7 +361,7 @@ def plan_segment(seg, geom: Geometry, L: int, forms_hint=None, final_scale: bool
         off = bld.alloc(2, "scale", -1, list(bld.norm_idx))
         bld.ir.append(("scale", off))
     last = rounds[-1]
-    lanes = min(cc._IO_LANES, geom.T - RB)
+    lanes = cc.io_lanes(tile_bits, RB)
     assert all(r >= lanes for r in last.rpos) and last.tpos[:lanes] == list(range(lanes))
     plan = SegPlan(geom, L, tile_bits, [(list(r.rpos), list(r.tpos)) for r in rounds], bld.ir,
                    list(bld.ext), max(2, bld.ncoef), len(slot_params), bld.fill, bld.forms,

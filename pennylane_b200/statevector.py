@@ -456,6 +456,10 @@ class StateVector:
         dT, dL = self.default_tile()
         rtT, _, _ = self.rt_geometry(1)
         jit = self.jit_enabled(1) and (T or dT) == rtT
+        if jit:
+            from . import segjit
+
+            dL = min(segjit.default_low_bits(self.dtype_code, 1), dT)
         budget = None
         if jit:
             budget = int(os.environ.get("B200Q_ROUND_BUDGET", 0)) or None      # tuning knob
