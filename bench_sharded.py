@@ -1,12 +1,15 @@
 """Multi-GPU arm of bench.py (`--gpus N` under torchrun): the statevector sharded over N ranks.
 
-Weak scaling: `args.qubits + log2(N)` qubits, i.e. the same 16 GiB shard per GPU as the 1-GPU
-workload; the circuit is the same hardware-efficient ansatz (8 layers, expval(Z0)).  One step =
-reset + the whole circuit (fused segments on every shard + the qubit-remapping exchanges over
-NVLink) + the expectation value.  Timed on the device with CUDA events between barriers, max over
-ranks.  Besides the contract keys the line carries the split of the step into shard-local sweeps
-(HBM roofline) and exchanges (NVLink: bytes sent per GPU / time, against the 770 GB/s measured
-peer-copy figure of B200_PROFILING.md).
+Weak scaling at BASELINE's multi-GPU shard size: 33 local qubits (128 GiB of complex128 per GPU),
+i.e. 34 / 35 / 36 qubits on 2 / 4 / 8 GPUs (`--weak16g`: 30 + log2 N qubits, the 1-GPU shard); the
+circuit is the same hardware-efficient ansatz (8 layers, expval(Z0)).  One step = reset + the whole
+circuit (fused segments on every shard + the qubit-remapping exchanges over NVLink, overlapped with
+the segments around them) + the expectation value.  Timed on the device with CUDA events between
+barriers, max over ranks.  Besides the contract keys the line carries `parity` (a 20-qubit twin
+through the same path against the oracle), `closed_form_check` (full size), the split of the step
+into shard-local sweeps (HBM roofline) and exchanges (NVLink: bytes sent per GPU over the time the
+communication streams were busy, against the 770 GB/s measured peer-copy figure of
+B200_PROFILING.md; `visible_seconds_per_step` = what the exchanges add to the sweeps' own time).
 """
 from __future__ import annotations
 
