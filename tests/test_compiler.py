@@ -286,3 +286,51 @@ def test_reverse_sweep_keeps_one_dense_record_per_wire_and_layer():
             jac[param] += -sums[slot]
     assert sorted(filled) == list(range(len(trainable)))
     assert np.max(np.abs(jac - ref)) < 1e-12
+
+
+from pennylane_b200 import compiler as cc  # noqa: E402
+
+
+def test_trim_rounds_keeps_every_primitive_and_saves_rounds():
+    """pack_segments(trim_rounds=True): trailing single-qubit blocks are handed to later segments
+    when that saves a round; no primitive is lost or duplicated, the segment count stays, the
+    total number of rounds does not grow, and the circuit still reproduces the oracle's state
+    (through the plan emulator)."""
+    import bench
+    from pennylane_b200 import segjit as sj
+
+    n = 30
+    geom = sj.default_geometry(1, 1)
+    ops_ = bench.hea_ops(n, 8)
+    prims = cc.merge_blocks(cc.lower_all(ops_, lambda w: n - 1 - int(w), False), 1, False)
+    out = {}
+    for trim in (False, True):
+        segs = cc.pack_segments(list(prims), n, T=geom.T, L=5, RB=geom.RB, sww=geom.sww, trim_rounds=trim)
+        ids = [id(p) for s in segs for p in s.prims]
+        assert sorted(ids) == sorted(id(p) for p in prims)
+        rounds = [len(s.rounds or cc.schedule_rounds(s.prims, s.tile_bits, geom.RB, geom.sww)) for s in segs]
+        out[trim] = (len(segs), sum(rounds), max(rounds))
+    assert out[True][0] == out[False][0]
+    assert out[True][1] < out[False][1] and out[True][2] < out[False][2]
+
+
+def test_store_lanes_follow_the_contiguous_low_run():
+    """compiler.io_lanes: only the tile's contiguous low run stays on the lanes in the store round
+    (a position above the run is not contiguous in memory); with L = 4 tiles an 8-target segment
+    then fits two rounds."""
+    assert cc.low_run([0, 1, 2, 3, 7, 9]) == 4 and cc.low_run([0, 1, 2, 3, 4, 5]) == 6 and cc.low_run([1, 2]) == 0
+    assert cc.io_lanes([0, 1, 2, 3, 10, 11, 12, 13, 14, 15, 16, 17], 4) == 4
+    assert cc.io_lanes([0, 1, 2, 3, 4, 11, 12, 13, 14, 15, 16, 17], 4) == 5
+    assert cc.io_lanes(list(range(12)), 4) == min(cc._IO_LANES, 8)
+    import bench
+    from pennylane_b200 import segjit as sj
+
+    geom = sj.default_geometry(1, 1)
+    n = 30
+    segs = cc.compile_ops(bench.hea_ops(n, 8), n, level=1, T=geom.T, L=4, fold_cx=False, RB=geom.RB, sww=geom.sww)
+    rounds = [len(s.rounds or cc.schedule_rounds(s.prims, s.tile_bits, geom.RB, geom.sww)) for s in segs]
+    assert len(segs) <= 27 and sum(rounds) <= 70
+    for s in segs:
+        last = (s.rounds or cc.schedule_rounds(s.prims, s.tile_bits, geom.RB, geom.sww))[-1]
+        lanes = cc.io_lanes(s.tile_bits, geom.RB)
+        assert all(r >= lanes for r in last.rpos) and last.tpos[:lanes] == list(range(lanes))
