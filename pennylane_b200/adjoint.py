@@ -241,7 +241,7 @@ def _accumulate_slot_sums(raw, gather, n_rows, n_bras):
     return vals
 
 
-def _reverse_sweep_fused(tape, sweep: "_Sweep", level: int = 1):
+def _reverse_sweep_fused(tape, sweep: "_Sweep", level: int = 1, _pre=None):
     """Reverse sweep through ``b200q_apply_rtile`` in adjoint mode: one read + one write of the
     ket and of each bra per SEGMENT of gates (instead of per gate), generator inner products
     accumulated inside the same pass.  Returns (vals[n_trainable][n_bras], filled, trainable)
@@ -253,36 +253,41 @@ def _reverse_sweep_fused(tape, sweep: "_Sweep", level: int = 1):
     ket = sweep.ket
     n = sweep.n
     jit = ket.jit_enabled(2)
-    if not jit and ket.jit_possible(2):
-        # below the size threshold a tape STRUCTURE is compiled the second time it is swept
-        from . import program
-        ops_seen = [op for op in tape.operations[tape.num_preps:] if op.name != "Snapshot"]
-        if not any(getattr(op, "batch_size", None) is not None for op in ops_seen) and \
-                program.seen_before(program.structure_key(ops_seen, (
-                    "adjoint-seen", tuple(tape.trainable_params), n, ket.dtype_code, int(level)))):
-            with ket.hot():
-                return _reverse_sweep_fused(tape, sweep, level)
-    if jit:
-        from . import segjit
+    # One pass over the operators per call (this is host time on every gradient of a small
+    # register): the structure key of the sweep — reverse order, jit geometry — serves both the
+    # "seen before" promotion below the size threshold and the program cache.
+    cache_key, sweep_ops = None, None
+    if _pre is not None:                                   # the promoted second pass of this call
+        from . import program, segjit
         geom = segjit.default_geometry(ket.dtype_code, 2)
+        cache_key, sweep_ops = _pre
+    elif jit or ket.jit_possible(2):
+        import os
+
+        from . import program, segjit
+        geom = segjit.default_geometry(ket.dtype_code, 2)
+        sweep_ops = [op for op in reversed(tape.operations[tape.num_preps:]) if op.name != "Snapshot"]
+        key, scalar = program._structure_key(sweep_ops, (
+            "adjoint", tuple(tape.trainable_params), n, ket.dtype_code, int(level), geom.T, geom.RB,
+            MAX_SEGMENT_OPS, os.environ.get("B200Q_TILE_L"), os.environ.get("B200Q_IO_LANES")))
+        if scalar or not any(getattr(op, "batch_size", None) is not None for op in sweep_ops):
+            cache_key = key
+    if not jit and cache_key is not None:
+        # below the size threshold a tape STRUCTURE is compiled the second time it is swept
+        if program.cached(cache_key) or program.seen_before(("adjoint-seen", cache_key)):
+            with ket.hot():
+                return _reverse_sweep_fused(tape, sweep, level, _pre=(cache_key, sweep_ops))
+    if jit:
         T, RB = geom.T, geom.RB
     else:
         T, RB, _ = ket.rt_geometry(2)
     if n < T:
         return None
-    cache_key = None
     n_sweep_ops = 0
     if jit:
         # structure-keyed cache of the whole reverse program; only the values are rebound
-        import os
-
-        from . import program
-        sweep_ops = [op for op in reversed(tape.operations[tape.num_preps:]) if op.name != "Snapshot"]
         n_sweep_ops = len(sweep_ops)
-        if not any(getattr(op, "batch_size", None) is not None for op in sweep_ops):
-            cache_key = program.structure_key(sweep_ops, (
-                "adjoint", tuple(tape.trainable_params), n, ket.dtype_code, int(level), T, RB,
-                MAX_SEGMENT_OPS, os.environ.get("B200Q_TILE_L"), os.environ.get("B200Q_IO_LANES")))
+        if cache_key is not None:
             cached = program.lookup(cache_key)
             if cached is not None:
                 try:
